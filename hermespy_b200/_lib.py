@@ -1,0 +1,142 @@
+"""ctypes binding of ``libhermes_b200.so`` (the C-ABI declared in ``include/hermes_b200.h``).
+
+There is no CPU fallback: if the shared library has not been built (``python -m hermespy_b200.build``
+or ``__graft_entry__.build()``) importing the compute API raises, and every compute call fails with
+``HermesB200Error`` when no CUDA device is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+HB_OK = 0
+HB_ERR_INVALID = 1
+HB_ERR_CUDA = 2
+HB_ERR_UNSUPPORTED = 3
+HB_ERR_NO_DEVICE = 4
+
+HB_F32 = 0
+HB_F64 = 1
+
+HB_SOS_AUTO = 0
+HB_SOS_POLY = 1
+HB_SOS_DIRECT = 2
+
+HB_MAX_TAPS = 256
+
+
+class HermesB200Error(RuntimeError):
+    """Raised for every non-zero status of the C-ABI (carries ``status``)."""
+
+    def __init__(self, status: int, message: str) -> None:
+        super().__init__(f"libhermes_b200 status {status}: {message}")
+        self.status = status
+
+
+class FadingProblem(C.Structure):
+    """Mirror of ``hb_fading_problem``."""
+
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("num_tx", C.c_int32),
+        ("num_rx", C.c_int32),
+        ("num_samples", C.c_int32),
+        ("max_delay", C.c_int32),
+        ("num_taps", C.c_int32),
+        ("num_sinusoids", C.c_int32),
+        ("precision", C.c_int32),
+        ("io_complex128", C.c_int32),
+        ("sos_mode", C.c_int32),
+        ("omega_max", C.c_double),
+        ("tap_delay", C.POINTER(C.c_int32)),
+        ("omega", C.c_void_p),
+        ("phi", C.c_void_p),
+        ("amp", C.c_void_p),
+        ("spatial", C.c_void_p),
+    ]
+
+
+class FadingPlanInfo(C.Structure):
+    """Mirror of ``hb_fading_plan_info``."""
+
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("tile", C.c_int32),
+        ("poly_order", C.c_int32),
+        ("num_groups", C.c_int32),
+        ("num_tiles", C.c_int32),
+        ("launches", C.c_int32),
+        ("error_bound", C.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_LIB = None
+
+
+def library_path() -> Path:
+    override = os.environ.get("HERMES_B200_LIB")
+    if override:
+        return Path(override)
+    return Path(__file__).resolve().parent / "lib" / "libhermes_b200.so"
+
+
+def _declare(lib: C.CDLL) -> None:
+    lib.hb_version.restype = C.c_int
+    lib.hb_version.argtypes = []
+    lib.hb_last_error.restype = C.c_char_p
+    lib.hb_last_error.argtypes = []
+    lib.hb_device_count.restype = C.c_int
+    lib.hb_device_count.argtypes = []
+    lib.hb_fading_plan.restype = C.c_int
+    lib.hb_fading_plan.argtypes = [C.POINTER(FadingProblem), C.POINTER(FadingPlanInfo)]
+    lib.hb_fading_propagate.restype = C.c_int
+    lib.hb_fading_propagate.argtypes = [
+        C.POINTER(FadingProblem),
+        C.c_void_p,
+        C.c_void_p,
+        C.c_void_p,
+        C.POINTER(FadingPlanInfo),
+    ]
+    lib.hb_fading_propagate_host.restype = C.c_int
+    lib.hb_fading_propagate_host.argtypes = [
+        C.POINTER(FadingProblem),
+        C.c_void_p,
+        C.c_void_p,
+        C.c_int32,
+        C.POINTER(FadingPlanInfo),
+    ]
+    lib.hb_fading_state.restype = C.c_int
+    lib.hb_fading_state.argtypes = [C.POINTER(FadingProblem), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+    lib.hb_release.restype = None
+    lib.hb_release.argtypes = []
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise loudly when it is missing."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not path.exists():
+            raise HermesB200Error(
+                HB_ERR_NO_DEVICE,
+                f"{path} not found -- build it with `python -m hermespy_b200.build` "
+                "(there is no CPU fallback for the channel kernels)",
+            )
+        lib = C.CDLL(str(path))
+        _declare(lib)
+        _LIB = lib
+    return _LIB
+
+
+def check(status: int) -> None:
+    if status != HB_OK:
+        msg = load().hb_last_error()
+        raise HermesB200Error(status, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+def device_count() -> int:
+    return int(load().hb_device_count())

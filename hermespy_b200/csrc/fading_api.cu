@@ -1,0 +1,519 @@
+// C-ABI entry points of the fading hot path: planning, device-resident launch, host-buffer pipeline.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "fading_kernels.cuh"
+
+namespace hb {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  cudaGetLastError();  // clear the sticky-less error state
+  return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? HB_ERR_NO_DEVICE : HB_ERR_CUDA;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible (%s); libhermes_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return HB_ERR_NO_DEVICE;
+  }
+  return HB_OK;
+}
+
+// ---- problem validation / delay groups -------------------------------------------------------------
+static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
+  if (!p) {
+    set_error("problem pointer is NULL");
+    return HB_ERR_INVALID;
+  }
+  if (p->batch < 0 || p->num_tx < 1 || p->num_rx < 0 || p->num_samples < 0 || p->max_delay < 0 ||
+      p->num_sinusoids < 0) {
+    set_error("invalid problem shape (B=%d Ntx=%d Nrx=%d T=%d D=%d N=%d)", p->batch, p->num_tx, p->num_rx,
+              p->num_samples, p->max_delay, p->num_sinusoids);
+    return HB_ERR_INVALID;
+  }
+  if (p->num_taps < 1 || p->num_taps > HB_MAX_TAPS) {
+    set_error("number of taps %d outside [1, %d]", p->num_taps, HB_MAX_TAPS);
+    return p->num_taps < 1 ? HB_ERR_INVALID : HB_ERR_UNSUPPORTED;
+  }
+  if (!p->tap_delay) {
+    set_error("tap_delay is NULL");
+    return HB_ERR_INVALID;
+  }
+  if (p->precision != HB_F32 && p->precision != HB_F64) {
+    set_error("unknown precision %d", p->precision);
+    return HB_ERR_INVALID;
+  }
+  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_DIRECT) {
+    set_error("unknown sos_mode %d", p->sos_mode);
+    return HB_ERR_INVALID;
+  }
+  memset(dt, 0, sizeof(*dt));
+  dt->num_taps = p->num_taps;
+  int g = -1;
+  for (int l = 0; l < p->num_taps; ++l) {
+    const int d = p->tap_delay[l];
+    if (d < 0 || d > p->max_delay) {
+      set_error("tap %d: delay %d outside [0, max_delay=%d]", l, d, p->max_delay);
+      return HB_ERR_INVALID;
+    }
+    if (l > 0 && d < p->tap_delay[l - 1]) {
+      set_error("tap delays must be ascending (tap %d)", l);
+      return HB_ERR_INVALID;
+    }
+    dt->tap_delay[l] = d;
+    if (g < 0 || d != dt->group_delay[g]) {
+      ++g;
+      dt->group_delay[g] = d;
+      dt->group_start[g] = (uint16_t)l;
+    }
+  }
+  dt->num_groups = g + 1;
+  dt->group_start[dt->num_groups] = (uint16_t)p->num_taps;
+  return HB_OK;
+}
+
+static int pick_ntx_template(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8)); }
+
+struct Plan {
+  int mode, tile, P, ntiles, Dpad, ntx_tpl, taps_per_chunk;
+  size_t smem;
+  double bound;
+};
+
+constexpr size_t kSmemSoftLimit = 72 * 1024;   // keeps >= 3 CTAs per SM
+constexpr size_t kSmemHardLimit = 200 * 1024;  // below the 227 KB per-CTA maximum
+constexpr double kPolyTarget = 5e-8;           // truncation bound, relative to the RMS tap gain
+
+static double poly_bound(double u_half, int P, int K) {
+  if (u_half <= 0.0) return 0.0;
+  double t = 1.0;
+  for (int p = 1; p <= P; ++p) t *= u_half / (double)p;
+  const double tail = u_half < (double)(P + 1) ? 1.0 / (1.0 - u_half / (double)(P + 1)) : 1e30;
+  return sqrt((double)K) * t * tail;
+}
+
+static size_t poly_smem(int ntx_tpl, int tile, int Dpad, int G, int P, int nrx) {
+  return sizeof(float2) * ((size_t)ntx_tpl * (tile + Dpad) + (size_t)G * P + (size_t)nrx * ntx_tpl);
+}
+
+static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
+  const int Tout = p->num_samples + p->max_delay;
+  const int K = p->num_sinusoids + 1;
+  pl->Dpad = (p->max_delay + 1) & ~1;
+  pl->ntx_tpl = pick_ntx_template(std::min(p->num_tx, 8));
+  pl->bound = 0.0;
+  const bool f64 = p->precision == HB_F64;
+  const int tile_cap = std::max(kThreads, ((Tout + kThreads - 1) / kThreads) * kThreads);
+
+  bool poly = !f64 && p->sos_mode != HB_SOS_DIRECT;
+  if (f64 && p->sos_mode == HB_SOS_POLY) {
+    set_error("HB_F64 parity mode only supports direct evaluation");
+    return HB_ERR_UNSUPPORTED;
+  }
+  if (poly) {
+    static const int kOrders[] = {1, 2, 3, 4, 6, 8};
+    static const int kTiles[] = {2048, 1024, 512, 256};
+    double best_cost = 1e300;
+    int best_P = 0, best_tile = 0;
+    double best_bound = 0;
+    for (int P : kOrders) {
+      for (int tile0 : kTiles) {
+        const int tile = std::min(tile0, tile_cap);
+        if (poly_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx) > kSmemSoftLimit &&
+            tile > kThreads)
+          continue;
+        const double bnd = poly_bound(0.5 * p->omega_max * tile, P, K);
+        if (bnd > kPolyTarget) continue;
+        const double cost = dt.num_groups * (2.0 * (P - 1) + 6.0 * pl->ntx_tpl) +
+                            60.0 * p->num_taps * K / (double)tile;
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_P = P;
+          best_tile = tile;
+          best_bound = bnd;
+        }
+      }
+    }
+    if (best_P == 0) {
+      if (p->sos_mode == HB_SOS_POLY) {
+        set_error("HB_SOS_POLY requested but omega_max=%g rad/sample cannot meet the %g bound", p->omega_max,
+                  kPolyTarget);
+        return HB_ERR_UNSUPPORTED;
+      }
+      poly = false;
+    } else {
+      pl->mode = HB_SOS_POLY;
+      pl->P = best_P;
+      pl->tile = best_tile;
+      pl->bound = best_bound;
+      pl->smem = poly_smem(pl->ntx_tpl, pl->tile, pl->Dpad, dt.num_groups, pl->P, p->num_rx);
+      pl->taps_per_chunk = 0;
+    }
+  }
+  if (!poly) {
+    pl->mode = HB_SOS_DIRECT;
+    pl->P = 0;
+    pl->tile = kThreads;
+    const size_t csz = f64 ? sizeof(double2) : sizeof(float2);
+    const size_t spsz = f64 ? sizeof(double2) : sizeof(uint2);
+    const size_t rsz = f64 ? sizeof(double) : sizeof(float);
+    int tpc = (int)std::max<size_t>(1, kDirectParamBytes / (K * spsz));
+    tpc = std::min(tpc, p->num_taps);
+    pl->taps_per_chunk = tpc;
+    pl->smem = csz * ((size_t)pl->ntx_tpl * (pl->tile + pl->Dpad) + (size_t)p->num_rx * pl->ntx_tpl) +
+               (size_t)tpc * K * spsz + (size_t)tpc * 2 * rsz;
+  }
+  // Very long delay spreads: shrink the antenna chunk before giving up.
+  while (pl->smem > kSmemHardLimit && pl->ntx_tpl > 1) {
+    const int old = pl->ntx_tpl;
+    pl->ntx_tpl = old / 2;
+    const size_t per_ant = (f64 && pl->mode == HB_SOS_DIRECT ? sizeof(double2) : sizeof(float2)) *
+                           ((size_t)(pl->tile + pl->Dpad) + p->num_rx);
+    pl->smem -= per_ant * (old - pl->ntx_tpl);
+  }
+  if (pl->smem > kSmemHardLimit) {
+    set_error("delay spread of %d samples needs %zu bytes of shared memory per CTA (limit %zu)", p->max_delay,
+              pl->smem, kSmemHardLimit);
+    return HB_ERR_UNSUPPORTED;
+  }
+  pl->ntiles = std::max(1, (Tout + pl->tile - 1) / pl->tile);
+  return HB_OK;
+}
+
+static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_problem* p,
+                      hb_fading_plan_info* info) {
+  if (!info) return;
+  const int chunks = (p->num_tx + pl.ntx_tpl - 1) / pl.ntx_tpl;
+  info->mode = pl.mode;
+  info->tile = pl.tile;
+  info->poly_order = pl.P;
+  info->num_groups = dt.num_groups;
+  info->num_tiles = pl.ntiles;
+  info->launches = (pl.mode == HB_SOS_POLY ? 1 : 0) + chunks;
+  info->error_bound = pl.bound;
+}
+
+template <int P>
+static int launch_coef(const FadingArgs& a, const DelayTable& dt, cudaStream_t st) {
+  sos_poly_coef_kernel<P><<<(unsigned)((size_t)a.ntiles * a.B), 128, 0, st>>>(a, dt);
+  HB_CUDA(cudaGetLastError());
+  return HB_OK;
+}
+
+static int launch_coef_any(int P, const FadingArgs& a, const DelayTable& dt, cudaStream_t st) {
+  switch (P) {
+    case 1: return launch_coef<1>(a, dt, st);
+    case 2: return launch_coef<2>(a, dt, st);
+    case 3: return launch_coef<3>(a, dt, st);
+    case 4: return launch_coef<4>(a, dt, st);
+    case 6: return launch_coef<6>(a, dt, st);
+    case 8: return launch_coef<8>(a, dt, st);
+  }
+  set_error("polynomial order %d outside the compiled set", P);
+  return HB_ERR_UNSUPPORTED;
+}
+
+static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& a, const DelayTable& dt,
+                        cudaStream_t st) {
+  if (pl.mode == HB_SOS_POLY) {
+    switch (pl.ntx_tpl) {
+      case 1: return launch_tdl_poly<1>(pl.P, io128, a, dt, pl.smem, st);
+      case 2: return launch_tdl_poly<2>(pl.P, io128, a, dt, pl.smem, st);
+      case 4: return launch_tdl_poly<4>(pl.P, io128, a, dt, pl.smem, st);
+      default: return launch_tdl_poly<8>(pl.P, io128, a, dt, pl.smem, st);
+    }
+  }
+  switch (pl.ntx_tpl) {
+    case 1: return launch_tdl_direct<1>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
+    case 2: return launch_tdl_direct<2>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
+    case 4: return launch_tdl_direct<4>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
+    default: return launch_tdl_direct<8>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
+  }
+}
+
+// Enqueue one batched propagation on `st`; all pointers are device pointers.
+static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, const Plan& pl, const void* x,
+                            void* y, cudaStream_t st) {
+  const int Tout = p->num_samples + p->max_delay;
+  if (p->batch == 0 || Tout == 0 || p->num_rx == 0) return HB_OK;
+  FadingArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x;
+  a.y = y;
+  a.omega = p->omega;
+  a.phi = p->phi;
+  a.amp = p->amp;
+  a.spatial = reinterpret_cast<const double2*>(p->spatial);
+  a.B = p->batch;
+  a.ntx = p->num_tx;
+  a.nrx = p->num_rx;
+  a.T = p->num_samples;
+  a.D = p->max_delay;
+  a.L = p->num_taps;
+  a.K = p->num_sinusoids + 1;
+  a.tile = pl.tile;
+  a.ntiles = pl.ntiles;
+  a.Dpad = pl.Dpad;
+  if ((size_t)a.ntiles * a.B > 0x7fffffffull) {
+    set_error("grid of %zu CTAs exceeds the launch limit; split the batch", (size_t)a.ntiles * a.B);
+    return HB_ERR_UNSUPPORTED;
+  }
+  float2* coef = nullptr;
+  if (pl.mode == HB_SOS_POLY) {
+    const size_t bytes = sizeof(float2) * (size_t)a.B * a.ntiles * dt.num_groups * pl.P;
+    HB_CUDA(cudaMallocAsync((void**)&coef, bytes, st));
+    a.coef = coef;
+    if (int e = launch_coef_any(pl.P, a, dt, st)) {
+      cudaFreeAsync(coef, st);
+      return e;
+    }
+  }
+  int rc = HB_OK;
+  for (int tx0 = 0; tx0 < p->num_tx && rc == HB_OK; tx0 += pl.ntx_tpl) {
+    a.tx0 = tx0;
+    a.ntx_chunk = std::min(pl.ntx_tpl, p->num_tx - tx0);
+    a.accumulate = tx0 > 0;
+    rc = launch_chunk(pl, p->precision == HB_F64, p->io_complex128 != 0, a, dt, st);
+  }
+  if (coef) cudaFreeAsync(coef, st);
+  return rc;
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------------------
+constexpr int kSlots = 3;
+struct HostPipe {
+  cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+  void* buf[kSlots] = {nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0};
+  int device = -1;
+};
+static HostPipe g_pipe;
+static std::mutex g_pipe_mu;
+
+static int pipe_prepare(size_t bytes) {
+  int dev = 0;
+  HB_CUDA(cudaGetDevice(&dev));
+  if (g_pipe.device != dev) {
+    for (int s = 0; s < kSlots; ++s) {
+      if (g_pipe.buf[s]) cudaFree(g_pipe.buf[s]);
+      if (g_pipe.st[s]) cudaStreamDestroy(g_pipe.st[s]);
+      g_pipe.buf[s] = nullptr;
+      g_pipe.cap[s] = 0;
+      g_pipe.st[s] = nullptr;
+    }
+    g_pipe.device = dev;
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    if (!g_pipe.st[s]) HB_CUDA(cudaStreamCreateWithFlags(&g_pipe.st[s], cudaStreamNonBlocking));
+    if (g_pipe.cap[s] < bytes) {
+      if (g_pipe.buf[s]) HB_CUDA(cudaFree(g_pipe.buf[s]));
+      g_pipe.buf[s] = nullptr;
+      g_pipe.cap[s] = 0;
+      HB_CUDA(cudaMalloc(&g_pipe.buf[s], bytes));
+      g_pipe.cap[s] = bytes;
+    }
+  }
+  return HB_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+int hb_version(void) { return HB_VERSION; }
+
+const char* hb_last_error(void) { return g_err; }
+
+int hb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int hb_fading_plan(const hb_fading_problem* p, hb_fading_plan_info* info) {
+  DelayTable dt;
+  if (int e = build_delay_table(p, &dt)) return e;
+  Plan pl;
+  if (int e = make_plan(p, dt, &pl)) return e;
+  fill_info(pl, dt, p, info);
+  return HB_OK;
+}
+
+int hb_fading_propagate(const hb_fading_problem* p, const void* x, void* y, void* stream,
+                        hb_fading_plan_info* info) {
+  DelayTable dt;
+  if (int e = build_delay_table(p, &dt)) return e;
+  Plan pl;
+  if (int e = make_plan(p, dt, &pl)) return e;
+  fill_info(pl, dt, p, info);
+  if (int e = require_device()) return e;
+  if (p->batch > 0 && (!x || !y || !p->omega || !p->phi || !p->amp || !p->spatial)) {
+    set_error("NULL device pointer in fading problem");
+    return HB_ERR_INVALID;
+  }
+  return propagate_device(p, dt, pl, x, y, (cudaStream_t)stream);
+}
+
+int hb_fading_propagate_host(const hb_fading_problem* p, const void* x, void* y, int32_t chunk_links,
+                             hb_fading_plan_info* info) {
+  DelayTable dt;
+  if (int e = build_delay_table(p, &dt)) return e;
+  Plan pl;
+  if (int e = make_plan(p, dt, &pl)) return e;
+  fill_info(pl, dt, p, info);
+  if (int e = require_device()) return e;
+  const int Tout = p->num_samples + p->max_delay;
+  if (p->batch == 0 || Tout == 0 || p->num_rx == 0) return HB_OK;
+  if (!x || !y || !p->omega || !p->phi || !p->amp || !p->spatial) {
+    set_error("NULL host pointer in fading problem");
+    return HB_ERR_INVALID;
+  }
+  const size_t esz = p->io_complex128 ? 16 : 8;
+  const int K = p->num_sinusoids + 1;
+  const size_t x_link = esz * (size_t)p->num_tx * p->num_samples;
+  const size_t y_link = esz * (size_t)p->num_rx * Tout;
+  const size_t om_link = sizeof(double) * (size_t)p->num_taps * K;
+  const size_t am_link = sizeof(double) * (size_t)p->num_taps * 2;
+  const size_t s_link = 16 * (size_t)p->num_rx * p->num_tx;
+  int chunk = chunk_links;
+  if (chunk <= 0) {
+    const size_t target = 48u << 20;  // ~48 MB of input per chunk keeps the copy engines busy
+    chunk = (int)std::max<size_t>(1, target / std::max<size_t>(1, x_link + y_link));
+    // at least kSlots chunks so that copies and kernels overlap
+    chunk = std::min(chunk, std::max(1, (p->batch + kSlots - 1) / kSlots));
+  }
+  chunk = std::min(chunk, p->batch);
+  // per-slot device layout: x | y | omega | phi | amp | spatial
+  const size_t off_x = 0;
+  const size_t off_y = align_up(off_x + x_link * chunk, 256);
+  const size_t off_om = align_up(off_y + y_link * chunk, 256);
+  const size_t off_ph = align_up(off_om + om_link * chunk, 256);
+  const size_t off_am = align_up(off_ph + om_link * chunk, 256);
+  const size_t off_s = align_up(off_am + am_link * chunk, 256);
+  const size_t total = align_up(off_s + s_link * chunk, 256);
+
+  std::lock_guard<std::mutex> lock(g_pipe_mu);
+  if (int e = pipe_prepare(total)) return e;
+  int rc = HB_OK;
+  int ci = 0;
+  for (int b0 = 0; b0 < p->batch && rc == HB_OK; b0 += chunk, ++ci) {
+    const int nb = std::min(chunk, p->batch - b0);
+    const int s = ci % kSlots;
+    cudaStream_t st = g_pipe.st[s];
+    char* base = (char*)g_pipe.buf[s];
+    // stream order on slot s guarantees the previous D2H of this slot finished before we overwrite it
+    hb_fading_problem q = *p;
+    q.batch = nb;
+    q.omega = (const double*)(base + off_om);
+    q.phi = (const double*)(base + off_ph);
+    q.amp = (const double*)(base + off_am);
+    q.spatial = base + off_s;
+#define HB_TRY(call)                          \
+  do {                                        \
+    cudaError_t _e = (call);                  \
+    if (_e != cudaSuccess) {                  \
+      rc = cuda_fail(_e, #call);              \
+      break;                                  \
+    }                                         \
+  } while (0)
+    do {
+      HB_TRY(cudaMemcpyAsync(base + off_om, (const char*)p->omega + om_link * b0, om_link * nb,
+                             cudaMemcpyHostToDevice, st));
+      HB_TRY(cudaMemcpyAsync(base + off_ph, (const char*)p->phi + om_link * b0, om_link * nb,
+                             cudaMemcpyHostToDevice, st));
+      HB_TRY(cudaMemcpyAsync(base + off_am, (const char*)p->amp + am_link * b0, am_link * nb,
+                             cudaMemcpyHostToDevice, st));
+      HB_TRY(cudaMemcpyAsync(base + off_s, (const char*)p->spatial + s_link * b0, s_link * nb,
+                             cudaMemcpyHostToDevice, st));
+      HB_TRY(cudaMemcpyAsync(base + off_x, (const char*)x + x_link * b0, x_link * nb, cudaMemcpyHostToDevice,
+                             st));
+      rc = propagate_device(&q, dt, pl, base + off_x, base + off_y, st);
+      if (rc != HB_OK) break;
+      HB_TRY(cudaMemcpyAsync((char*)y + y_link * b0, base + off_y, y_link * nb, cudaMemcpyDeviceToHost, st));
+    } while (0);
+#undef HB_TRY
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    cudaError_t e = cudaStreamSynchronize(g_pipe.st[s]);
+    if (e != cudaSuccess && rc == HB_OK) rc = cuda_fail(e, "cudaStreamSynchronize(pipeline)");
+  }
+  return rc;
+}
+
+int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_delay_out, void* stream) {
+  DelayTable dt;
+  if (int e = build_delay_table(p, &dt)) return e;
+  if (group_delay_out)
+    for (int g = 0; g < dt.num_groups; ++g) group_delay_out[g] = dt.group_delay[g];
+  if (p->batch == 0 || p->num_samples == 0) return HB_OK;
+  if (int e = require_device()) return e;
+  if (!h || !p->omega || !p->phi || !p->amp) {
+    set_error("NULL device pointer in fading state request");
+    return HB_ERR_INVALID;
+  }
+  FadingArgs a;
+  memset(&a, 0, sizeof(a));
+  a.y = h;
+  a.omega = p->omega;
+  a.phi = p->phi;
+  a.amp = p->amp;
+  a.B = p->batch;
+  a.T = p->num_samples;
+  a.L = p->num_taps;
+  a.K = p->num_sinusoids + 1;
+  a.ntiles = (p->num_samples + kThreads - 1) / kThreads;
+  const size_t blocks = (size_t)a.ntiles * dt.num_groups * a.B;
+  if (blocks > 0x7fffffffull) {
+    set_error("state grid of %zu CTAs exceeds the launch limit; split the batch", blocks);
+    return HB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f64 = p->precision == HB_F64, io128 = p->io_complex128 != 0;
+  if (f64 && io128) sos_state_kernel<double, double2><<<(unsigned)blocks, kThreads, 0, st>>>(a, dt);
+  else if (f64) sos_state_kernel<double, float2><<<(unsigned)blocks, kThreads, 0, st>>>(a, dt);
+  else if (io128) sos_state_kernel<float, double2><<<(unsigned)blocks, kThreads, 0, st>>>(a, dt);
+  else sos_state_kernel<float, float2><<<(unsigned)blocks, kThreads, 0, st>>>(a, dt);
+  HB_CUDA(cudaGetLastError());
+  return HB_OK;
+}
+
+void hb_release(void) {
+  std::lock_guard<std::mutex> lock(g_pipe_mu);
+  for (int s = 0; s < kSlots; ++s) {
+    if (g_pipe.buf[s]) cudaFree(g_pipe.buf[s]);
+    if (g_pipe.st[s]) cudaStreamDestroy(g_pipe.st[s]);
+    g_pipe.buf[s] = nullptr;
+    g_pipe.cap[s] = 0;
+    g_pipe.st[s] = nullptr;
+  }
+  g_pipe.device = -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,4 @@
+#include "fading_inst.cuh"
+namespace hb {
+HB_INSTANTIATE_FADING(8)
+}

@@ -1,0 +1,394 @@
+// Fading hot path kernels (sm_100a).
+//
+//   K1  sos_poly_coef_kernel   per (link, tile, delay group): Taylor moments of the Rician
+//                              sum-of-sinusoids tap gain about the tile centre      (fading.py:293-343)
+//   K3+K4 tdl_poly_kernel      y = S @ sum_g shift_{d_g}(x * h_g), h_g from the K1 moments by Horner;
+//                              x tile + delay halo staged in shared memory            (fading.py:371-406)
+//   K1+K3+K4 tdl_direct_kernel same result with one sincos per sinusoid per sample: MUFU pipe (float,
+//                              32-bit fixed-point phase accumulators) or FP64 parity mode (double)
+//   sos_state_kernel           SISO tap gains h[B, G, T] for the channel state        (fading.py:345-358)
+//
+// Algebra used by the gather form: the reference scatters  z[:, d_l + n] += x[:, n] h_l[n]; each output
+// sample m gathers  z[:, m] = sum_l x[:, m - d_l] h_l[m - d_l]  over taps with 0 <= m - d_l < T.  Taps whose
+// rounded delays coincide share x[:, m - d] and only ever appear as their sum, so they are merged into
+// one "delay group" whose gain is the sum of the member taps' gains.
+#pragma once
+#include "hb_common.cuh"
+
+namespace hb {
+
+struct FadingArgs {
+  const void* x;
+  void* y;
+  const double* omega;     // [B, L, K]
+  const double* phi;       // [B, L, K]
+  const double* amp;       // [B, L, 2]
+  const double2* spatial;  // [B, Nrx, Ntx]
+  const float2* coef;      // [B, ntiles, G, P]  (poly mode)
+  int B, ntx, nrx, T, D, L, K;
+  int tile, ntiles, Dpad;
+  int tx0, ntx_chunk, accumulate;
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1: Taylor moments.  For output index m = q*tile + i, r = (i - tile/2) / tile in [-1/2, 1/2):
+//   h_g(m - d_g) = sum_{l in g} sum_k amp_lk exp(j(omega_lk (m - d_g) + phi_lk))
+//                = sum_p r^p * coef[g][p],
+//   coef[g][p]   = sum_{l,k} amp_lk e^{j theta_lk} (j u_lk)^p / p!,
+//   theta_lk = phi_lk + omega_lk (q*tile + tile/2 - d_g),   u_lk = omega_lk * tile.
+// theta is formed and range-reduced in FP64 (it reaches 1e3..1e6 rad for long frames), the sincos and the
+// moment recurrence run in FP32.  One warp per delay group, lanes over the (tap, sinusoid) pairs of the
+// group in a fixed order -> deterministic sums.
+template <int P>
+__global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
+                                                            const __grid_constant__ DelayTable dt) {
+  const int b = blockIdx.x / a.ntiles, q = blockIdx.x - b * a.ntiles;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = a.K, G = dt.num_groups;
+  const double centre = (double)q * a.tile + 0.5 * a.tile;
+  const double* om_b = a.omega + (size_t)b * a.L * K;
+  const double* ph_b = a.phi + (size_t)b * a.L * K;
+  const double* am_b = a.amp + (size_t)b * a.L * 2;
+  for (int g = warp; g < G; g += 4) {
+    const int l0 = dt.group_start[g], l1 = dt.group_start[g + 1];
+    const double shift = centre - (double)dt.group_delay[g];
+    float accr[P], acci[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) accr[p] = acci[p] = 0.f;
+    for (int idx = l0 * K + lane; idx < l1 * K; idx += 32) {
+      const int l = idx / K, k = idx - l * K;
+      const double om = om_b[idx];
+      const double th = fma(om, shift, ph_b[idx]);
+      double t = th * kInvTwoPi;
+      t -= rint(t);
+      float s, c;
+      sincosf((float)(t * kTwoPi), &s, &c);
+      const float am = (float)am_b[2 * l + (k != 0)];
+      float tr = am * c, ti = am * s;
+      const float u = (float)(om * (double)a.tile);
+      accr[0] += tr;
+      acci[0] += ti;
+#pragma unroll
+      for (int p = 1; p < P; ++p) {
+        const float f = u * (1.0f / (float)p);
+        const float nr = -ti * f, ni = tr * f;  // times (j u / p)
+        tr = nr;
+        ti = ni;
+        accr[p] += tr;
+        acci[p] += ti;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        accr[p] += __shfl_xor_sync(0xffffffffu, accr[p], o);
+        acci[p] += __shfl_xor_sync(0xffffffffu, acci[p], o);
+      }
+    }
+    if (lane == 0) {
+      float2* out = const_cast<float2*>(a.coef) + (((size_t)b * a.ntiles + q) * G + g) * P;
+#pragma unroll
+      for (int p = 0; p < P; ++p) out[p] = make_float2(accr[p], acci[p]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage x[b, tx0 : tx0+NTX, q*tile - Dpad : q*tile + tile) into shared memory, zero outside [0, T).
+template <int NTX, typename C, typename IO>
+__device__ __forceinline__ void stage_x_tile(C* xs, const FadingArgs& a, int b, int q, int W) {
+  const IO* xb = reinterpret_cast<const IO*>(a.x) + ((size_t)b * a.ntx + a.tx0) * a.T;
+  const int n0 = q * a.tile - a.Dpad;
+  using R = decltype(C::x);
+#pragma unroll
+  for (int j = 0; j < NTX; ++j) {
+    const bool live = j < a.ntx_chunk;
+    const IO* row = xb + (size_t)j * a.T;
+#pragma unroll 4
+    for (int c = threadIdx.x; c < W; c += kThreads) {
+      const int n = n0 + c;
+      C v;
+      v.x = (R)0;
+      v.y = (R)0;
+      if (live && n >= 0 && n < a.T) v = Conv<R>::from(ldg_stream(row + n));
+      xs[j * W + c] = v;
+    }
+  }
+}
+
+template <int NTX, typename C>
+__device__ __forceinline__ void stage_spatial(C* Ss, const FadingArgs& a, int b) {
+  using R = decltype(C::x);
+  const double2* Sb = a.spatial + (size_t)b * a.nrx * a.ntx;
+  for (int c = threadIdx.x; c < a.nrx * NTX; c += kThreads) {
+    const int irx = c / NTX, j = c - irx * NTX;
+    C v;
+    v.x = (R)0;
+    v.y = (R)0;
+    if (j < a.ntx_chunk) v = Conv<R>::from(Sb[irx * a.ntx + a.tx0 + j]);
+    Ss[c] = v;
+  }
+}
+
+// y[b, irx, m] (=|+=) sum_j S[irx, j] z[j]
+template <int NTX, typename C, typename IO>
+__device__ __forceinline__ void spatial_store(const C* Ss, const C (&z)[NTX], const FadingArgs& a, int b,
+                                              int m) {
+  using R = decltype(C::x);
+  const int Tout = a.T + a.D;
+  IO* yb = reinterpret_cast<IO*>(a.y) + (size_t)b * a.nrx * Tout + m;
+  for (int irx = 0; irx < a.nrx; ++irx) {
+    C acc;
+    acc.x = (R)0;
+    acc.y = (R)0;
+#pragma unroll
+    for (int j = 0; j < NTX; ++j) cmac<R>(acc, Ss[irx * NTX + j], z[j]);
+    IO* dst = yb + (size_t)irx * Tout;
+    if (a.accumulate) {
+      const IO old = *dst;
+      acc.x += (R)old.x;
+      acc.y += (R)old.y;
+    }
+    stg_stream(dst, IoConv<IO>::make(acc.x, acc.y));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 + K4 (polynomial tap gains).  grid (ntiles, B), 256 threads, R samples per thread per pass.
+template <int NTX, int P, int R, typename IO>
+__global__ void __launch_bounds__(kThreads) tdl_poly_kernel(const FadingArgs a,
+                                                            const __grid_constant__ DelayTable dt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x / a.ntiles, q = blockIdx.x - b * a.ntiles, tid = threadIdx.x;
+  const int W = a.tile + a.Dpad;
+  const int G = dt.num_groups;
+  float2* xs = reinterpret_cast<float2*>(smem_raw);
+  float2* cs = xs + NTX * W;
+  float2* Ss = cs + G * P;
+
+  stage_x_tile<NTX, float2, IO>(xs, a, b, q, W);
+  {
+    const float2* cb = a.coef + ((size_t)b * a.ntiles + q) * G * P;
+    for (int c = tid; c < G * P; c += kThreads) cs[c] = cb[c];
+  }
+  stage_spatial<NTX, float2>(Ss, a, b);
+  __syncthreads();
+
+  const int Tout = a.T + a.D;
+  const float inv_tile = 1.0f / (float)a.tile;
+  const float half = 0.5f * (float)a.tile;
+  for (int base = 0; base < a.tile; base += kThreads * R) {
+    if ((long long)q * a.tile + base >= Tout) break;
+    // tile is a multiple of 256, so the number of live sample slots is uniform over the CTA
+    const int nu = min(R, (a.tile - base) / kThreads);
+    float2 z[R][NTX];
+    float rr[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      rr[u] = ((float)(base + u * kThreads + tid) - half) * inv_tile;
+#pragma unroll
+      for (int j = 0; j < NTX; ++j) z[u][j] = make_float2(0.f, 0.f);
+    }
+    for (int g = 0; g < G; ++g) {
+      const int off = base + tid + a.Dpad - dt.group_delay[g];
+      float2 c[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) c[p] = cs[g * P + p];
+      float2 h[R];
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        float2 v = c[P - 1];
+#pragma unroll
+        for (int p = P - 2; p >= 0; --p) {
+          v.x = fmaf(v.x, rr[u], c[p].x);
+          v.y = fmaf(v.y, rr[u], c[p].y);
+        }
+        h[u] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < NTX; ++j) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          if (u < nu) {  // keeps off + u*256 < W; samples outside the frame are zeros in xs
+            const float2 xv = xs[j * W + off + u * kThreads];
+            cmac<float>(z[u][j], xv, h[u]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int m = q * a.tile + base + u * kThreads + tid;
+      if (u < nu && m < Tout) spatial_store<NTX, float2, IO>(Ss, z[u], a, b, m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct evaluation: one sincos per (tap, sinusoid, sample).  tile == 256, one sample per thread.
+//   REAL = float : phases kept as 32-bit binary angles (2^32 = one turn).  The start phase of each
+//                  sinusoid at the first sample of the tile is formed in FP64 and rounded once; stepping by
+//                  the rounded increment w for < 256 samples adds < 256 * 2^-33 turns = 1.9e-7 rad.
+//                  Wrap-around of the unsigned accumulator IS the range reduction; __sincosf then sees
+//                  |angle| <= pi where its absolute error is 2^-21.4.
+//   REAL = double: theta = omega * n + phi, sincos in FP64 -- the parity mode.
+template <typename REAL> struct SinParam;
+template <> struct SinParam<float> { using type = uint2; };     // (phase0, increment) binary angles
+template <> struct SinParam<double> { using type = double2; };  // (phi, omega)
+
+constexpr int kDirectParamBytes = 32 * 1024;  // per tap-chunk staging budget in shared memory
+
+template <int NTX, typename REAL, typename IO>
+__global__ void __launch_bounds__(kThreads) tdl_direct_kernel(const FadingArgs a,
+                                                              const __grid_constant__ DelayTable dt,
+                                                              const int taps_per_chunk) {
+  using C = typename Cplx<REAL>::type;
+  using SP = typename SinParam<REAL>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x / a.ntiles, q = blockIdx.x - b * a.ntiles, tid = threadIdx.x;
+  const int W = a.tile + a.Dpad;
+  const int K = a.K;
+  C* xs = reinterpret_cast<C*>(smem_raw);
+  C* Ss = xs + NTX * W;
+  SP* sp = reinterpret_cast<SP*>(Ss + a.nrx * NTX);
+  REAL* am = reinterpret_cast<REAL*>(sp + taps_per_chunk * K);
+
+  stage_x_tile<NTX, C, IO>(xs, a, b, q, W);
+  stage_spatial<NTX, C>(Ss, a, b);
+
+  const double* om_b = a.omega + (size_t)b * a.L * K;
+  const double* ph_b = a.phi + (size_t)b * a.L * K;
+  const double* am_b = a.amp + (size_t)b * a.L * 2;
+  const int m = q * a.tile + tid;  // output sample of this thread
+
+  C z[NTX];
+#pragma unroll
+  for (int j = 0; j < NTX; ++j) {
+    z[j].x = (REAL)0;
+    z[j].y = (REAL)0;
+  }
+
+  for (int l0 = 0; l0 < a.L; l0 += taps_per_chunk) {
+    const int lc = min(taps_per_chunk, a.L - l0);
+    __syncthreads();  // previous chunk fully consumed (also orders the staging above on the first pass)
+    for (int idx = tid; idx < lc * K; idx += kThreads) {
+      const int l = l0 + idx / K;
+      const double om = om_b[(size_t)l0 * K + idx];
+      const double ph = ph_b[(size_t)l0 * K + idx];
+      if constexpr (sizeof(REAL) == 4) {
+        // phase at the first output sample of the tile, i.e. input index n = q*tile - d_l
+        const double n_first = (double)q * a.tile - (double)dt.tap_delay[l];
+        double t = fma(om, n_first, ph) * kInvTwoPi;
+        t -= floor(t);
+        double wq = om * kInvTwoPi;
+        wq -= rint(wq);
+        uint2 v;
+        v.x = (uint32_t)(unsigned long long)(t * 4294967296.0);
+        v.y = (uint32_t)(long long)rint(wq * 4294967296.0);
+        sp[idx] = v;
+      } else {
+        sp[idx] = make_double2(ph, om);
+      }
+    }
+    for (int idx = tid; idx < lc * 2; idx += kThreads) am[idx] = (REAL)am_b[(size_t)l0 * 2 + idx];
+    __syncthreads();
+
+    for (int ll = 0; ll < lc; ++ll) {
+      const int d = dt.tap_delay[l0 + ll];
+      const SP* spl = sp + ll * K;
+      REAL sr = 0, si = 0, lr = 0, li = 0;
+      if constexpr (sizeof(REAL) == 4) {
+        const float scale = 1.4629180792671596e-9f;  // 2*pi / 2^32
+        {
+          const uint2 v = spl[0];
+          const int ang = (int)(v.x + v.y * (uint32_t)tid);
+          __sincosf((float)ang * scale, &li, &lr);
+        }
+#pragma unroll 4
+        for (int k = 1; k < K; ++k) {
+          const uint2 v = spl[k];
+          const int ang = (int)(v.x + v.y * (uint32_t)tid);
+          float s, c;
+          __sincosf((float)ang * scale, &s, &c);
+          sr += c;
+          si += s;
+        }
+      } else {
+        const double n = (double)(m - d);
+        {
+          const double2 v = spl[0];
+          sincos(fma(v.y, n, v.x), &li, &lr);
+        }
+        for (int k = 1; k < K; ++k) {
+          const double2 v = spl[k];
+          double s, c;
+          sincos(fma(v.y, n, v.x), &s, &c);
+          sr += c;
+          si += s;
+        }
+      }
+      C h;
+      h.x = am[2 * ll] * lr + am[2 * ll + 1] * sr;
+      h.y = am[2 * ll] * li + am[2 * ll + 1] * si;
+      const int off = tid + a.Dpad - d;
+#pragma unroll
+      for (int j = 0; j < NTX; ++j) cmac<REAL>(z[j], xs[j * W + off], h);
+    }
+  }
+  if (m < a.T + a.D) spatial_store<NTX, C, IO>(Ss, z, a, b, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SISO tap gains for the channel state: h[b, g, n] = sum_{l in g} h_l[n], n = 0..T-1 (input time).
+template <typename REAL, typename IO>
+__global__ void __launch_bounds__(kThreads) sos_state_kernel(const FadingArgs a,
+                                                             const __grid_constant__ DelayTable dt) {
+  // grid.x = B * G * ntiles with ntiles = ceil(T / 256)
+  const int bg = blockIdx.x / a.ntiles;
+  const int b = bg / dt.num_groups, g = bg - b * dt.num_groups;
+  const int n = (blockIdx.x - bg * a.ntiles) * kThreads + threadIdx.x;
+  if (n >= a.T) return;
+  const int K = a.K;
+  const int l0 = dt.group_start[g], l1 = dt.group_start[g + 1];
+  const double* om_b = a.omega + (size_t)b * a.L * K;
+  const double* ph_b = a.phi + (size_t)b * a.L * K;
+  const double* am_b = a.amp + (size_t)b * a.L * 2;
+  REAL hr = 0, hi = 0;
+  for (int l = l0; l < l1; ++l) {
+    REAL sr = 0, si = 0, lr = 0, li = 0;
+    for (int k = 0; k < K; ++k) {
+      const double th = fma(om_b[l * K + k], (double)n, ph_b[l * K + k]);
+      REAL s, c;
+      if constexpr (sizeof(REAL) == 4) {
+        double t = th * kInvTwoPi;
+        t -= rint(t);
+        sincosf((float)(t * kTwoPi), &s, &c);
+      } else {
+        sincos(th, &s, &c);
+      }
+      if (k == 0) {
+        lr = c;
+        li = s;
+      } else {
+        sr += c;
+        si += s;
+      }
+    }
+    hr += (REAL)am_b[2 * l] * lr + (REAL)am_b[2 * l + 1] * sr;
+    hi += (REAL)am_b[2 * l] * li + (REAL)am_b[2 * l + 1] * si;
+  }
+  IO* out = reinterpret_cast<IO*>(a.y) + ((size_t)b * dt.num_groups + g) * a.T + n;
+  *out = IoConv<IO>::make(hr, hi);
+}
+
+// ---- per-NTX launchers implemented in fading_inst_ntx*.cu -----------------------------------------
+template <int NTX>
+int launch_tdl_poly(int P, bool io128, const FadingArgs& a, const DelayTable& dt, size_t smem,
+                    cudaStream_t st);
+template <int NTX>
+int launch_tdl_direct(bool f64, bool io128, const FadingArgs& a, const DelayTable& dt, int taps_per_chunk,
+                      size_t smem, cudaStream_t st);
+template <int NTX> constexpr int poly_samples_per_thread() { return NTX <= 2 ? 4 : (NTX <= 4 ? 2 : 1); }
+
+}  // namespace hb

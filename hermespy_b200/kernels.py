@@ -1,0 +1,374 @@
+"""Batched, device-facing Python API over the C-ABI (torch tensors carry the device memory).
+
+This is the layer the host-side channel classes (``hermespy_b200.fading``) and the batched drop
+runner call.  Nothing here computes on the CPU: numpy is used only to lay out parameter blocks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import HB_F32, HB_F64, HB_SOS_AUTO, HB_SOS_DIRECT, HB_SOS_POLY, FadingPlanInfo, FadingProblem
+
+_PRECISION = {"f32": HB_F32, "f64": HB_F64, HB_F32: HB_F32, HB_F64: HB_F64}
+_SOS_MODE = {"auto": HB_SOS_AUTO, "poly": HB_SOS_POLY, "direct": HB_SOS_DIRECT}
+_SOS_NAME = {HB_SOS_POLY: "poly", HB_SOS_DIRECT: "direct"}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def fading_param_block(
+    power: np.ndarray,
+    delay: np.ndarray,
+    los_gain: np.ndarray,
+    nlos_gain: np.ndarray,
+    los_angle: np.ndarray,
+    nlos_angle: np.ndarray,
+    los_phase: np.ndarray,
+    nlos_phase: np.ndarray,
+    los_doppler,
+    nlos_doppler,
+    gain,
+    fs: float,
+) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Lay out the kernel parameter block for B links (leading axes broadcast).
+
+    ``h_l[n] = amp[l,0] e^{j(omega[l,0] n + phi[l,0])} + amp[l,1] sum_{k>=1} e^{j(omega[l,k] n + phi[l,k])}``
+    reproduces the reference's tap impulse (hermespy/channel/fading/fading.py:326-342) with
+    ``omega[l,0] = w_los cos(theta_l0)/fs`` and ``omega[l,k] = w_nlos cos((2 pi k + theta_lk)/N)/fs``.
+    Angle/phase arrays may carry a leading batch axis ``[B, L(, N)]``; profile arrays are ``[L]``.
+    """
+    nlos_angle = np.asarray(nlos_angle, dtype=np.float64)
+    nlos_phase = np.asarray(nlos_phase, dtype=np.float64)
+    los_angle = np.asarray(los_angle, dtype=np.float64)
+    los_phase = np.asarray(los_phase, dtype=np.float64)
+    N = nlos_angle.shape[-1]
+    lead = nlos_angle.shape[:-2]
+    L = nlos_angle.shape[-2]
+    k = 1.0 + np.arange(N)
+    w_los = np.asarray(los_doppler, dtype=np.float64).reshape(lead + (1,)) if np.ndim(los_doppler) else float(los_doppler)
+    w_nlos = (
+        np.asarray(nlos_doppler, dtype=np.float64).reshape(lead + (1, 1)) if np.ndim(nlos_doppler) else float(nlos_doppler)
+    )
+    g = np.asarray(gain, dtype=np.float64).reshape(lead + (1,)) if np.ndim(gain) else float(gain)
+    omega = np.empty(lead + (L, N + 1), dtype=np.float64)
+    phi = np.empty(lead + (L, N + 1), dtype=np.float64)
+    amp = np.empty(lead + (L, 2), dtype=np.float64)
+    omega[..., 0] = w_los * np.cos(los_angle) / fs
+    omega[..., 1:] = w_nlos * np.cos((2.0 * np.pi * k + nlos_angle) / N) / fs if N > 0 else 0.0
+    phi[..., 0] = los_phase
+    phi[..., 1:] = nlos_phase
+    scale = np.sqrt(g * np.asarray(power, dtype=np.float64))
+    amp[..., 0] = np.asarray(los_gain, dtype=np.float64) * scale
+    amp[..., 1] = np.asarray(nlos_gain, dtype=np.float64) * scale
+    return omega, phi, amp
+
+
+@dataclass
+class FadingBatch:
+    """Parameters of B fading links that share one delay profile (one kernel launch).
+
+    Device tensors: ``omega/phi [B, L, N+1]`` float64, ``amp [B, L, 2]`` float64,
+    ``spatial [B, Nrx, Ntx]`` complex128.  ``tap_delay`` is a host int32 vector (ascending).
+    """
+
+    tap_delay: np.ndarray
+    max_delay: int
+    omega: "object"
+    phi: "object"
+    amp: "object"
+    spatial: "object"
+    omega_max: float
+
+    @property
+    def batch(self) -> int:
+        return int(self.omega.shape[0])
+
+    @property
+    def num_taps(self) -> int:
+        return int(self.omega.shape[1])
+
+    @property
+    def num_sinusoids(self) -> int:
+        return int(self.omega.shape[2]) - 1
+
+    @property
+    def num_rx(self) -> int:
+        return int(self.spatial.shape[1])
+
+    @property
+    def num_tx(self) -> int:
+        return int(self.spatial.shape[2])
+
+    @classmethod
+    def from_numpy(cls, tap_delay, max_delay, omega, phi, amp, spatial, omega_max=None, device="cuda"):
+        torch = _torch()
+        omega = np.ascontiguousarray(omega, dtype=np.float64)
+        if omega_max is None:
+            omega_max = float(np.abs(omega).max()) if omega.size else 0.0
+        dev = torch.device(device)
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev, non_blocking=False)
+
+        return cls(
+            tap_delay=np.ascontiguousarray(tap_delay, dtype=np.int32),
+            max_delay=int(max_delay),
+            omega=up(omega, np.float64),
+            phi=up(phi, np.float64),
+            amp=up(amp, np.float64),
+            spatial=up(spatial, np.complex128),
+            omega_max=float(omega_max),
+        )
+
+
+def _problem(
+    *,
+    batch,
+    num_tx,
+    num_rx,
+    num_samples,
+    max_delay,
+    num_taps,
+    num_sinusoids,
+    precision,
+    io128,
+    sos_mode,
+    omega_max,
+    tap_delay: np.ndarray,
+    omega_ptr,
+    phi_ptr,
+    amp_ptr,
+    spatial_ptr,
+) -> Tuple[FadingProblem, np.ndarray]:
+    td = np.ascontiguousarray(tap_delay, dtype=np.int32)
+    if td.ndim != 1 or td.shape[0] != num_taps:
+        raise ValueError("tap_delay must be a vector with one entry per tap")
+    p = FadingProblem()
+    p.batch = int(batch)
+    p.num_tx = int(num_tx)
+    p.num_rx = int(num_rx)
+    p.num_samples = int(num_samples)
+    p.max_delay = int(max_delay)
+    p.num_taps = int(num_taps)
+    p.num_sinusoids = int(num_sinusoids)
+    p.precision = _PRECISION[precision]
+    p.io_complex128 = 1 if io128 else 0
+    p.sos_mode = _SOS_MODE[sos_mode]
+    p.omega_max = float(omega_max)
+    p.tap_delay = td.ctypes.data_as(C.POINTER(C.c_int32))
+    p.omega = omega_ptr
+    p.phi = phi_ptr
+    p.amp = amp_ptr
+    p.spatial = spatial_ptr
+    return p, td  # td must outlive the call
+
+
+def _info_dict(info: FadingPlanInfo) -> dict:
+    d = info.as_dict()
+    d["mode"] = _SOS_NAME.get(d["mode"], d["mode"])
+    return d
+
+
+def fading_plan(batch: FadingBatch, num_samples: int, precision="f32", sos_mode="auto", io128=False) -> dict:
+    """Ask the library which kernel path / tile / polynomial order it would use (no GPU needed)."""
+    lib = _lib.load()
+    p, keep = _problem(
+        batch=batch.batch,
+        num_tx=batch.num_tx,
+        num_rx=batch.num_rx,
+        num_samples=num_samples,
+        max_delay=batch.max_delay,
+        num_taps=batch.num_taps,
+        num_sinusoids=batch.num_sinusoids,
+        precision=precision,
+        io128=io128,
+        sos_mode=sos_mode,
+        omega_max=batch.omega_max,
+        tap_delay=batch.tap_delay,
+        omega_ptr=None,
+        phi_ptr=None,
+        amp_ptr=None,
+        spatial_ptr=None,
+    )
+    info = FadingPlanInfo()
+    _lib.check(lib.hb_fading_plan(C.byref(p), C.byref(info)))
+    return _info_dict(info)
+
+
+def fading_propagate(x, batch: FadingBatch, precision="f32", sos_mode="auto", out=None, return_info=False):
+    """Propagate ``x[B, Ntx, T]`` (cuda complex64/complex128) over B fading links -> ``y[B, Nrx, T+D]``.
+
+    Enqueued on torch's current stream; no synchronization.  GPU counterpart of
+    ``MultipathFadingSample._propagate`` (hermespy/channel/fading/fading.py:371-406) for a whole batch.
+    """
+    torch = _torch()
+    lib = _lib.load()
+    if not x.is_cuda:
+        raise _lib.HermesB200Error(_lib.HB_ERR_NO_DEVICE, "x must be a CUDA tensor (no CPU fallback)")
+    if x.dtype not in (torch.complex64, torch.complex128):
+        raise ValueError("x must be complex64 or complex128")
+    if x.dim() != 3:
+        raise ValueError("x must have shape [B, Ntx, T]")
+    B, ntx, T = (int(s) for s in x.shape)
+    if B != batch.batch:
+        raise ValueError(f"batch mismatch: x has {B} links, parameters have {batch.batch}")
+    if ntx != batch.num_tx:
+        raise ValueError(
+            f"Number of signal streams to be propagated does not match the number of transmitter antennas ({ntx} != {batch.num_tx}))"
+        )
+    x = x.contiguous()
+    io128 = x.dtype == torch.complex128
+    Tout = T + batch.max_delay
+    if out is None:
+        out = torch.empty((B, batch.num_rx, Tout), dtype=x.dtype, device=x.device)
+    else:
+        if tuple(out.shape) != (B, batch.num_rx, Tout) or out.dtype != x.dtype or not out.is_contiguous():
+            raise ValueError("out has the wrong shape / dtype / layout")
+    p, keep = _problem(
+        batch=B,
+        num_tx=ntx,
+        num_rx=batch.num_rx,
+        num_samples=T,
+        max_delay=batch.max_delay,
+        num_taps=batch.num_taps,
+        num_sinusoids=batch.num_sinusoids,
+        precision=precision,
+        io128=io128,
+        sos_mode=sos_mode,
+        omega_max=batch.omega_max,
+        tap_delay=batch.tap_delay,
+        omega_ptr=batch.omega.data_ptr(),
+        phi_ptr=batch.phi.data_ptr(),
+        amp_ptr=batch.amp.data_ptr(),
+        spatial_ptr=batch.spatial.data_ptr(),
+    )
+    info = FadingPlanInfo()
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(
+            lib.hb_fading_propagate(C.byref(p), x.data_ptr(), out.data_ptr(), C.c_void_p(stream), C.byref(info))
+        )
+    del keep
+    if return_info:
+        return out, _info_dict(info)
+    return out
+
+
+def fading_propagate_host(
+    x: np.ndarray,
+    tap_delay: np.ndarray,
+    max_delay: int,
+    omega: np.ndarray,
+    phi: np.ndarray,
+    amp: np.ndarray,
+    spatial: np.ndarray,
+    omega_max: Optional[float] = None,
+    precision="f32",
+    sos_mode="auto",
+    out: Optional[np.ndarray] = None,
+    chunk_links: int = 0,
+    return_info=False,
+):
+    """Host-buffer entry (what a drop-in plugin calls): numpy in, numpy out, copies inside the call.
+
+    ``x`` is ``[B, Ntx, T]`` complex64 or complex128 (the reference's ``SignalBlock`` dtype).
+    """
+    lib = _lib.load()
+    x = np.ascontiguousarray(x)
+    if x.dtype not in (np.complex64, np.complex128):
+        raise ValueError("x must be complex64 or complex128")
+    if x.ndim != 3:
+        raise ValueError("x must have shape [B, Ntx, T]")
+    B, ntx, T = x.shape
+    omega = np.ascontiguousarray(omega, dtype=np.float64)
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    amp = np.ascontiguousarray(amp, dtype=np.float64)
+    spatial = np.ascontiguousarray(spatial, dtype=np.complex128)
+    if omega.shape != phi.shape or omega.ndim != 3 or omega.shape[0] != B:
+        raise ValueError("omega/phi must have shape [B, L, N+1]")
+    L, K = omega.shape[1], omega.shape[2]
+    if amp.shape != (B, L, 2):
+        raise ValueError("amp must have shape [B, L, 2]")
+    if spatial.ndim != 3 or spatial.shape[0] != B or spatial.shape[2] != ntx:
+        raise ValueError(
+            f"Number of signal streams to be propagated does not match the number of transmitter antennas ({ntx} != {spatial.shape[-1]}))"
+        )
+    nrx = spatial.shape[1]
+    if omega_max is None:
+        omega_max = float(np.abs(omega).max()) if omega.size else 0.0
+    Tout = T + int(max_delay)
+    if out is None:
+        out = np.empty((B, nrx, Tout), dtype=x.dtype)
+    elif out.shape != (B, nrx, Tout) or out.dtype != x.dtype or not out.flags.c_contiguous:
+        raise ValueError("out has the wrong shape / dtype / layout")
+    p, keep = _problem(
+        batch=B,
+        num_tx=ntx,
+        num_rx=nrx,
+        num_samples=T,
+        max_delay=max_delay,
+        num_taps=L,
+        num_sinusoids=K - 1,
+        precision=precision,
+        io128=x.dtype == np.complex128,
+        sos_mode=sos_mode,
+        omega_max=omega_max,
+        tap_delay=tap_delay,
+        omega_ptr=omega.ctypes.data,
+        phi_ptr=phi.ctypes.data,
+        amp_ptr=amp.ctypes.data,
+        spatial_ptr=spatial.ctypes.data,
+    )
+    info = FadingPlanInfo()
+    _lib.check(
+        lib.hb_fading_propagate_host(C.byref(p), x.ctypes.data, out.ctypes.data, int(chunk_links), C.byref(info))
+    )
+    del keep
+    if return_info:
+        return out, _info_dict(info)
+    return out
+
+
+def fading_state(batch: FadingBatch, num_samples: int, precision="f32", io128=True):
+    """SISO tap gains ``h[B, G, T]`` and the G distinct integer delays (fading.py:345-358)."""
+    torch = _torch()
+    lib = _lib.load()
+    td = np.ascontiguousarray(batch.tap_delay, dtype=np.int32)
+    G = int(np.unique(td).size)
+    dev = batch.omega.device
+    h = torch.empty((batch.batch, G, int(num_samples)), dtype=torch.complex128 if io128 else torch.complex64, device=dev)
+    p, keep = _problem(
+        batch=batch.batch,
+        num_tx=batch.num_tx,
+        num_rx=batch.num_rx,
+        num_samples=num_samples,
+        max_delay=batch.max_delay,
+        num_taps=batch.num_taps,
+        num_sinusoids=batch.num_sinusoids,
+        precision=precision,
+        io128=io128,
+        sos_mode="auto",
+        omega_max=batch.omega_max,
+        tap_delay=td,
+        omega_ptr=batch.omega.data_ptr(),
+        phi_ptr=batch.phi.data_ptr(),
+        amp_ptr=batch.amp.data_ptr(),
+        spatial_ptr=batch.spatial.data_ptr(),
+    )
+    gd = np.zeros(G, dtype=np.int32)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(
+            lib.hb_fading_state(C.byref(p), h.data_ptr(), gd.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(stream))
+        )
+    del keep
+    return h, gd

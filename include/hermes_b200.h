@@ -1,0 +1,132 @@
+/* hermes_b200.h -- C-ABI of the B200-native HermesPy channel hot path.
+ *
+ * One shared library (libhermes_b200.so, sm_100a only) exposes the batched replacements of the
+ * reference's per-sample numpy routines.  Plain pointers and sizes only; no torch / numpy types.
+ * Every entry point returns an hb_status (0 == HB_OK); hb_last_error() gives the message of the
+ * last failure on the calling thread.  No exceptions cross this boundary and there is no CPU
+ * fallback: without a CUDA device every compute entry point returns HB_ERR_NO_DEVICE.
+ *
+ * Reference interfaces replaced (paths relative to the HermesPy tree, v1.6.0):
+ *   hb_fading_propagate*   <- MultipathFadingSample._propagate          hermespy/channel/fading/fading.py:371-406
+ *                             + MultipathFadingSample.__path_impulse_generator        fading.py:293-343
+ *   hb_fading_state        <- MultipathFadingSample.state (SISO tap gains)            fading.py:345-358
+ *   hb_fading_sample_params<- MultipathFadingRealization._sample                      fading.py:468-515
+ *                             (+ ConsistentUniform.sample, hermespy/channel/consistent.py:475-485)
+ *   hb_kron_mix            <- antenna-correlation mixing  R_rx @ S @ R_tx             fading.py:480-489
+ *   hb_cdl_*               <- ClusterDelayLineSample.__ray_impulse_generator / _propagate
+ *                             hermespy/channel/cdl/cluster_delay_lines.py:409-558
+ *   hb_stats_accumulate    <- ScalarEvaluationResult accumulation  hermespy/core/pymonte/scalar.py:101-125
+ *                             + BitErrorEvaluator artifact          hermespy/modem/evaluators.py:231-259
+ *
+ * Layouts (row-major, batch first):
+ *   x      [B, Ntx, T]        complex64 (float2) or complex128 (double2), read-only
+ *   y      [B, Nrx, T + D]    same element type as x, fully overwritten
+ *   omega  [B, L, N+1] f64    per-sample angular increment of every sinusoid (column 0 = LOS term)
+ *   phi    [B, L, N+1] f64    start phases
+ *   amp    [B, L, 2]   f64    (LOS amplitude, per-sinusoid NLOS amplitude) incl. sqrt(gain*power_l)
+ *   spatial[B, Nrx, Ntx] complex128
+ *   so that  h_l[n] = amp_los e^{j(omega_l0 n + phi_l0)} + amp_nlos sum_k e^{j(omega_lk n + phi_lk)}
+ *   and      y = spatial @ sum_l shift_{d_l}(x * h_l)          (d_l = tap_delay[l], ascending).
+ */
+#ifndef HERMES_B200_H
+#define HERMES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HB_API __attribute__((visibility("default")))
+#else
+#define HB_API
+#endif
+
+#define HB_VERSION 100 /* 0.1.0 */
+#define HB_MAX_TAPS 256
+#define HB_MAX_POLY_ORDER 8
+
+typedef enum hb_status {
+  HB_OK = 0,
+  HB_ERR_INVALID = 1,     /* bad argument (mirrors the reference's ValueError) */
+  HB_ERR_CUDA = 2,        /* CUDA runtime failure, see hb_last_error() */
+  HB_ERR_UNSUPPORTED = 3, /* shape outside the compiled kernel set */
+  HB_ERR_NO_DEVICE = 4    /* no sm_100 device visible; there is no CPU fallback */
+} hb_status;
+
+typedef enum hb_precision {
+  HB_F32 = 0, /* complex64 arithmetic, rel. L2 <= 1e-5 against the float64 reference */
+  HB_F64 = 1  /* float64 parity mode (bit-exact BER counts), direct evaluation only */
+} hb_precision;
+
+typedef enum hb_sos_mode {
+  HB_SOS_AUTO = 0,  /* pick POLY when the error bound allows it, else DIRECT */
+  HB_SOS_POLY = 1,  /* per-tile Taylor moments of the sum of sinusoids (FMA pipe)  */
+  HB_SOS_DIRECT = 2 /* one sincos per sinusoid per sample (MUFU pipe)              */
+} hb_sos_mode;
+
+/* Launch-uniform description of one batched fading propagation. */
+typedef struct hb_fading_problem {
+  int32_t batch;          /* B: links (drop x sweep point x direction) in this launch       */
+  int32_t num_tx;         /* Ntx streams of x                                                */
+  int32_t num_rx;         /* Nrx streams of y                                                */
+  int32_t num_samples;    /* T                                                               */
+  int32_t max_delay;      /* D = round(max(delay) * fs)  (fading.py:372); y has T + D samples */
+  int32_t num_taps;       /* L <= HB_MAX_TAPS                                                */
+  int32_t num_sinusoids;  /* N (NLOS sinusoids per tap; the LOS term is extra)               */
+  int32_t precision;      /* hb_precision                                                    */
+  int32_t io_complex128;  /* 0: x, y are complex64; 1: complex128                            */
+  int32_t sos_mode;       /* hb_sos_mode                                                     */
+  double omega_max;       /* upper bound of |omega| over the batch (rad / sample); 0 = static */
+  const int32_t* tap_delay; /* HOST int32[L]: rint(delay_l * fs) (fading.py:297), ascending   */
+  const double* omega;    /* DEVICE f64 [B, L, N+1]                                          */
+  const double* phi;      /* DEVICE f64 [B, L, N+1]                                          */
+  const double* amp;      /* DEVICE f64 [B, L, 2]                                            */
+  const void* spatial;    /* DEVICE complex128 [B, Nrx, Ntx]                                 */
+} hb_fading_problem;
+
+/* What hb_fading_plan() decided for a problem (also filled by propagate when info != NULL). */
+typedef struct hb_fading_plan_info {
+  int32_t mode;        /* HB_SOS_POLY or HB_SOS_DIRECT */
+  int32_t tile;        /* output samples per CTA */
+  int32_t poly_order;  /* number of Taylor terms P (POLY only) */
+  int32_t num_groups;  /* distinct integer delays */
+  int32_t num_tiles;   /* CTAs per link */
+  int32_t launches;    /* kernels launched per call */
+  double error_bound;  /* bound on the relative truncation error of the POLY expansion */
+} hb_fading_plan_info;
+
+HB_API int hb_version(void);
+HB_API const char* hb_last_error(void);
+/* Number of CUDA devices visible (0 when none / driver missing). */
+HB_API int hb_device_count(void);
+
+HB_API int hb_fading_plan(const hb_fading_problem* p, hb_fading_plan_info* info);
+
+/* Device-resident propagation.  x, y and all DEVICE members of p live on the current device;
+ * the work is enqueued on `stream` (a cudaStream_t; NULL = legacy default stream) and the call
+ * returns without synchronizing. */
+HB_API int hb_fading_propagate(const hb_fading_problem* p, const void* x, void* y, void* stream,
+                        hb_fading_plan_info* info);
+
+/* Host-buffer propagation (the call a drop-in plugin makes): every pointer of `p`, x and y are HOST
+ * buffers (pinned or pageable).  The library stages chunks of `chunk_links` links through its own
+ * device workspace on three streams (H2D / kernels / D2H overlapped) and returns after y is complete.
+ * chunk_links <= 0 lets the library choose. */
+HB_API int hb_fading_propagate_host(const hb_fading_problem* p, const void* x, void* y, int32_t chunk_links,
+                             hb_fading_plan_info* info);
+
+/* SISO tap gains of the channel state, h[B, G, T] complex (element type per io_complex128), one row per
+ * distinct integer delay, plus the delays themselves in group_delay_out (HOST int32[G], may be NULL).
+ * CSI[b, i, j, n, group_delay[g]] = spatial[b, i, j] * h[b, g, n]   (fading.py:351-364). */
+HB_API int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_delay_out, void* stream);
+
+/* Release cached device workspaces / streams of the calling process. */
+HB_API void hb_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HERMES_B200_H */
