@@ -1,0 +1,166 @@
+"""GPU: the channel plugin API (realize -> sample -> propagate/state) replays the reference's golden vectors and
+the property tests the reference itself uses to pin this path (tests/unit_tests/channel/test_fading.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import hermespy_b200.channel as MC
+from hermespy_b200 import config
+from hermespy_b200.core import Signal
+from oracle.golden_cases import FADING_CASES, golden_signal
+from tests.helpers import rel_l2
+from tests.test_oracle_golden import GOLDEN, mirror_device, mirror_sample
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize("ci", range(len(FADING_CASES)), ids=[c[0] for c in FADING_CASES])
+def test_plugin_propagate_matches_reference_golden(golden, ci):
+    case = FADING_CASES[ci]
+    name, _, ntx, nrx, fs, T, _, _ = case
+    real, s, tx, rx = mirror_sample(case)
+    x = Signal.Create(golden_signal(ci, ntx, T), fs, 3.5e9)
+    ref = golden[f"{name}/y"]
+    extreme = name.startswith("extreme")
+    with config.compute("f64"):
+        y64 = s.propagate(x).view(np.ndarray)
+    assert y64.shape == ref.shape and y64.dtype == np.complex128
+    # phases reach 4e3 rad in the extreme-Doppler case, where the reference's own rounding is ~1e-12
+    assert rel_l2(y64, ref) < (1e-10 if extreme else 1e-12)
+    with config.compute("f32"):
+        y32 = s.propagate(x).view(np.ndarray)
+    assert rel_l2(y32, ref) < 1e-5
+    rs = real.reciprocal_sample(s, rx, tx)
+    with config.compute("f64"):
+        yr = rs.propagate(Signal.Create(golden_signal(100 + ci, nrx, T), fs, 3.5e9)).view(np.ndarray)
+    assert rel_l2(yr, golden[f"{name}/y_reciprocal"]) < (1e-10 if extreme else 1e-12)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in FADING_CASES if c[5] <= 200])
+def test_plugin_state_matches_reference_golden(golden, name):
+    case = next(c for c in FADING_CASES if c[0] == name)
+    _, s, _, _ = mirror_sample(case)
+    csi = golden[f"{name}/csi"]
+    with config.compute("f64"):
+        st = s.state(case[5], csi.shape[3])
+    dense = st.dense_state()
+    assert dense.shape == csi.shape
+    assert np.abs(dense - csi).max() < (1e-9 if name.startswith("extreme") else 1e-12)
+
+
+def test_batched_propagate_equals_one_by_one():
+    from hermespy_b200.channel.fading import propagate_batch
+
+    rng = np.random.default_rng(0)
+    fs = 30.72e6
+    tx, rx = mirror_device(2, fs, (0, 0, 0)), mirror_device(2, fs, (10, 0, 0))
+    chans = [MC.TDL(MC.TDLType.B, rms_delay=300e-9, doppler_frequency=100, seed=1),
+             MC.Cost259(MC.Cost259Type.URBAN, doppler_frequency=20, seed=2)]
+    samples, signals = [], []
+    for i in range(9):
+        ch = chans[i % 2]
+        samples.append(ch.realize().sample(tx, rx))
+        T = 300 if i % 3 else 200
+        signals.append((rng.standard_normal((2, T)) + 1j * rng.standard_normal((2, T))))
+    ys = propagate_batch(samples, signals, precision="f64")
+    with config.compute("f64"):
+        for s, x, y in zip(samples, signals, ys):
+            one = s.propagate(Signal.Create(x, fs)).view(np.ndarray)
+            assert np.array_equal(one, y)
+
+
+# ---- property tests mirrored from the reference's own unit tests -----------------------------------------
+
+def _link(ntx=1, nrx=1, fs=1e6):
+    return mirror_device(ntx, fs, (0, 0, 0)), mirror_device(nrx, fs, (10, 0, 0))
+
+
+def test_propagation_delay_shift():
+    """test_fading.py:415-441 -- a delayed single tap equals the undelayed output shifted by int(fs * delay)."""
+    fs = 1e6
+    tx, rx = _link(fs=fs)
+    x = Signal.Create(np.exp(2j * np.pi * 0.01 * np.arange(100))[None], fs)
+    with config.compute("f64"):
+        for delay in (1e-5, 3.3e-5, 5e-5):
+            a = MC.MultipathFadingChannel([0.0], [1.0], [0.0], seed=42)
+            b = MC.MultipathFadingChannel([delay], [1.0], [0.0], seed=42)
+            ya = a.realize().sample(tx, rx).propagate(x).view(np.ndarray)
+            yb = b.realize().sample(tx, rx).propagate(x).view(np.ndarray)
+            d = int(round(fs * delay))
+            assert yb.shape[1] == ya.shape[1] + d
+            assert np.abs(yb[:, :d]).max() == 0.0
+            np.testing.assert_array_almost_equal(yb[:, d:], ya, decimal=12)
+
+
+def test_gain_scales_output():
+    """test_fading.py:560-591 -- output scales with sqrt(gain)."""
+    fs = 1e6
+    tx, rx = _link(2, 2, fs)
+    x = Signal.Create(np.ones((2, 50), complex), fs)
+    with config.compute("f64"):
+        a = MC.TDL(MC.TDLType.A, rms_delay=1e-6, seed=3, gain=1.0).realize().sample(tx, rx).propagate(x).view(np.ndarray)
+        b = MC.TDL(MC.TDLType.A, rms_delay=1e-6, seed=3, gain=0.25).realize().sample(tx, rx).propagate(x).view(np.ndarray)
+    np.testing.assert_array_almost_equal(b, 0.5 * a, decimal=12)
+
+
+def test_identity_correlation_equals_no_correlation():
+    """test_fading.py:593-614."""
+    fs = 1e6
+    tx, rx = _link(2, 2, fs)
+    x = Signal.Create(np.random.default_rng(1).standard_normal((2, 64)) + 0j, fs)
+    plain = MC.TDL(MC.TDLType.C, rms_delay=2e-6, seed=9)
+    ident = MC.TDL(MC.TDLType.C, rms_delay=2e-6, seed=9,
+                   antenna_correlation=MC.CustomAntennaCorrelation(np.eye(2, dtype=complex)))
+    with config.compute("f64"):
+        a = plain.realize().sample(tx, rx).propagate(x).view(np.ndarray)
+        b = ident.realize().sample(tx, rx).propagate(x).view(np.ndarray)
+    np.testing.assert_array_almost_equal(a, b, decimal=12)
+
+
+def test_seed_reproducibility():
+    """test_fading.py:385-396."""
+    fs = 1e6
+    tx, rx = _link(fs=fs)
+    x = Signal.Create(np.ones((1, 32), complex), fs)
+    ch = MC.Cost259(MC.Cost259Type.RURAL, seed=100)
+    a = ch.realize().sample(tx, rx).propagate(x).view(np.ndarray)
+    ch.seed = 100
+    b = ch.realize().sample(tx, rx).propagate(x).view(np.ndarray)
+    assert np.array_equal(a, b)
+
+
+def test_stream_mismatch_and_zero_energy():
+    fs = 1e6
+    tx, rx = _link(2, 2, fs)
+    s = MC.TDL(seed=1).realize().sample(tx, rx)
+    with pytest.raises(ValueError):
+        s.propagate(Signal.Create(np.ones((3, 8), complex), fs))  # channel.py:364-367
+    z = MC.TDL(seed=1, gain=0.0).realize().sample(tx, rx)
+    out = z.propagate(Signal.Create(np.ones((2, 8), complex), fs))
+    assert out.num_samples == 0 and out.num_streams == 2  # channel.py:353-361
+
+
+@pytest.mark.parametrize("build", [
+    lambda: MC.Cost259(MC.Cost259Type.HILLY, seed=42),
+    lambda: MC.TDL(MC.TDLType.E, rms_delay=1e-6, seed=42),
+    lambda: MC.Exponential(1e-6, 2e-6, seed=42),
+], ids=["cost259_hilly", "tdl_e", "exponential"])
+def test_expected_energy_scale(build):
+    """test_fading.py:712-731,780-799,836-854 -- mean propagated energy ~ expected_energy_scale over realizations."""
+    from hermespy_b200.channel.fading import propagate_batch
+
+    fs = 1e6
+    tx, rx = _link(fs=fs)
+    ch = build()
+    x = np.ones((1, 100), complex) / 10.0  # unit energy
+    samples = [ch.realize().sample(tx, rx) for _ in range(1000)]
+    ys = propagate_batch(samples, [x] * len(samples), precision="f32")
+    energy = np.mean([np.sum(np.abs(y) ** 2) for y in ys])
+    expected = np.mean([s.expected_energy_scale for s in samples])
+    assert abs(energy - expected) < 0.1
