@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the channel hot path: propagated complex samples/s per link (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--links B]
+
+A *step* is one pass of the hot path over one batch of ``--links`` synthetic links of config C2
+(BASELINE.json configs[1]: 4x4 MIMO, 5G TDL-B, rms delay 300 ns, Doppler 100, medium antenna correlation,
+T = 15 344 samples at 30.72 MHz).  The whole job (10 000 drops x 7 SNR points = 70 000 links, every one
+re-realized) is 70000 / links steps of identical shape; K steps are timed.
+
+* ``value``  device-resident throughput: inputs and parameters already in HBM, CUDA events around K steps,
+             max over ranks, aggregate over all ranks (weak scaling: same links per GPU).
+* ``e2e``    the same work through the host-buffer C-ABI (``hb_fading_propagate_host``): complex128 host
+             buffers (the reference's SignalBlock dtype) in pinned memory, H2D + kernels + D2H inside the timed
+             region.
+* ``roofline`` achieved algorithmic HBM bytes/s of the dominant kernel (tdl_poly) from per-launch CUDA events
+             recorded by the library on the launch stream during the timed region, against MEASURED_PEAKS.json.
+* ``cpu_baseline`` the numpy oracle (a restatement of the reference's CPU path) on the host cores, bounded sample.
+
+``--impl reference`` times that CPU path alone (rank 0 only).  The reference itself is Python and does not
+travel to the GPU box, so the port under ``oracle/`` stands in for it (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload: BASELINE.json configs[1] (C2) -------------------------------------------------------------
+C2 = dict(
+    name="C2: 4x4 MIMO OFDM frame (14 x (1024+72) = 15344 samples @30.72 MHz) over 5G TDL-B, rms_delay 300 ns, "
+         "doppler 100, 3GPP medium antenna correlation; 10k drops x 7 SNR points = 70000 links",
+    ntx=4, nrx=4, T=15344, fs=30.72e6, rms_delay=300e-9, doppler=100.0, total_links=70000,
+)
+UNIT = "complex samples/s per link direction"
+METRIC = "propagated complex samples/s per link"
+
+
+def make_channel(seed):
+    import hermespy_b200.channel as MC
+
+    return MC.TDL(MC.TDLType.B, rms_delay=C2["rms_delay"], doppler_frequency=C2["doppler"], seed=seed,
+                  antenna_correlation=MC.StandardAntennaCorrelation(MC.CorrelationType.MEDIUM))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- CPU baseline (oracle port of the reference path) ---------------------------------------------------------
+def _cpu_worker(args):
+    seed, n = args
+    from hermespy_b200.batch import sample_fading_links
+    from oracle import fading_oracle as fo
+
+    ch = make_channel(seed)
+    blk = None
+    rng = np.random.default_rng(seed)
+    done = 0
+    # same per-link work as the reference: realize + sample + propagate, complex128
+    import hermespy_b200.channel as MC
+    from hermespy_b200.core import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+
+    dev = lambda n_: SimulatedDevice(bandwidth=C2["fs"], antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (n_, 1, 1)))
+    tx, rx = dev(C2["ntx"]), dev(C2["nrx"])
+    for _ in range(n):
+        s = ch.realize().sample(tx, rx)
+        p = fo.FadingParams(power=s.power_profile, delay=s.delay_profile, los_gain=s.los_gains, nlos_gain=s.nlos_gains,
+                            los_angle=s.los_angles, nlos_angle=s.nlos_angles, los_phase=s.los_phases,
+                            nlos_phase=s.nlos_phases, los_doppler=s.los_doppler, nlos_doppler=s.nlos_doppler,
+                            spatial=s.spatial_response, gain=s.gain, fs=C2["fs"], num_rx=C2["nrx"], num_tx=C2["ntx"])
+        x = (rng.standard_normal((C2["ntx"], C2["T"])) + 1j * rng.standard_normal((C2["ntx"], C2["T"]))) / np.sqrt(2)
+        y = fo.propagate(p, x)
+        done += y.shape[1] > 0
+    return done
+
+
+def cpu_reference_pass(links_per_core, cores):
+    """One bounded pass of the CPU path on `cores` processes; returns (links, seconds)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(1000 + i, 1) for i in range(cores)])  # warm-up: imports, page-in
+        t0 = time.perf_counter()
+        done = pool.map(_cpu_worker, [(i, links_per_core) for i in range(cores)])
+        dt = time.perf_counter() - t0
+    return int(sum(done)), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    per_core = 2
+    vals = []
+    for _ in range(args.warmup and 1):
+        cpu_reference_pass(1, cores)
+    t_total = 0.0
+    links_total = 0
+    for _ in range(args.steps):
+        links, dt = cpu_reference_pass(per_core, cores)
+        t_total += dt
+        links_total += links
+        vals.append(links * C2["T"] / dt)
+    value = links_total * C2["T"] / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": C2["name"], "links_per_step": per_core * cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_core * cores} links of C2 per step ({per_core} per core process), "
+                                   "realize+sample+propagate in complex128 numpy (oracle port of fading.py:293-406)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from hermespy_b200 import _lib
+    from hermespy_b200.batch import sample_fading_links
+    from hermespy_b200.kernels import FadingBatch, fading_propagate, fading_propagate_host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, ntx, nrx = args.links, C2["T"], C2["ntx"], C2["nrx"]
+
+    # ---- realize + sample the step's links on the host (numpy RNG, rank-dependent seed as simulation.py:220-223)
+    ch = make_channel(42 + rank * 12345678)
+    blk = sample_fading_links(ch, B, ntx, nrx, C2["fs"])
+    fb = FadingBatch.from_numpy(device=dev, **blk)
+    D = blk["max_delay"]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(rank)
+    x = torch.view_as_complex(torch.randn((B, ntx, T, 2), device=dev, generator=gen, dtype=torch.float32) * (0.5 ** 0.5))
+    y = torch.empty((B, nrx, T + D), dtype=torch.complex64, device=dev)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)  # stand-in for evaluator statistics (sum, sum^2, count, bits)
+
+    def step():
+        fading_propagate(x, fb, precision="f32", sos_mode="auto", out=y)
+        if world > 1:
+            dist.all_reduce(stats)  # the only collective of the path: evaluator statistics
+
+    _, info = fading_propagate(x, fb, out=y, return_info=True)
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    prof = _lib.profile_end()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * T * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = 8.0 * B * (ntx * T + nrx * (T + D))  # complex64 in + out, SURVEY 8(d): 8 (Ntx + Nrx) B / sample
+    k = prof["tdl_poly"] if prof["tdl_poly"]["launches"] else prof["tdl_direct"]
+    kname = "tdl_poly_kernel" if prof["tdl_poly"]["launches"] else "tdl_direct_kernel"
+    k_ms = k["ms"] / max(1, k["launches"])
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_share_of_step": k["ms"] / ms_total if ms_total > 0 else None,
+                "other_kernels_ms": {n: v["ms"] / max(1, v["launches"]) for n, v in prof.items()
+                                     if v["launches"] and n not in ("tdl_poly", "tdl_direct")}}
+    launches = sum(v["launches"] for v in prof.values())
+
+    # ---- end to end through the host-buffer C-ABI (complex128 host buffers, as the reference's SignalBlock) ----
+    Be = min(B, args.e2e_links)
+    xh = torch.empty((Be, ntx, T), dtype=torch.complex128).pin_memory()
+    xh.copy_(x[:Be].to(torch.complex128).cpu())
+    yh = torch.empty((Be, nrx, T + D), dtype=torch.complex128).pin_memory()
+    sub = {k_: (v[:Be] if isinstance(v, np.ndarray) and v.ndim == 3 else v) for k_, v in blk.items()}
+
+    def e2e_step():
+        fading_propagate_host(xh.numpy(), out=yh.numpy(), precision="f32", **sub)
+
+    e2e_step()
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 5))
+    for _ in range(n_e2e):
+        e2e_step()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * T * n_e2e / float(t.item())
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 16 + sum(
+        sub[k_].nbytes for k_ in ("omega", "phi", "amp", "spatial"))), "d2h_bytes_per_step": int(yh.numel() * 16),
+           "links_per_step": Be, "host_dtype": "complex128", "timing": "host wall clock around the blocking C-ABI call"}
+
+    # ---- CPU baseline: rank 0, N = 1 only ---------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        per_core = 2
+        links, dtc = cpu_reference_pass(per_core, cores)
+        cpu = {"value": links * T / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{links} links of C2 ({per_core} per core process, {cores} processes), realize+sample+propagate "
+                         f"in complex128 numpy; {dtc:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": C2["name"], "links_per_step_per_gpu": B, "steps_for_whole_job": int(np.ceil(
+                C2["total_links"] / (B * world))), "l2_policy": f"inputs larger than L2 ({x.numel() * 8 / 1e6:.0f} MB in, "
+                f"{y.numel() * 8 / 1e6:.0f} MB out per step)", "plan": info},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--links", type=int, default=2048, help="links per step per GPU")
+    ap.add_argument("--e2e-links", type=int, default=512, help="links per end-to-end step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

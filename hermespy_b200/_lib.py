@@ -74,6 +74,17 @@ class FadingPlanInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+NUM_KERNEL_KINDS = 9
+KERNEL_KINDS = ("sos_poly_coef", "tdl_poly", "tdl_direct", "sos_state", "cdl_rays", "cdl_propagate", "spatial_gemm",
+                "stats", "misc")
+
+
+class ProfileReport(C.Structure):
+    """Mirror of ``hb_profile_report``."""
+
+    _fields_ = [("ms", C.c_double * NUM_KERNEL_KINDS), ("launches", C.c_int64 * NUM_KERNEL_KINDS)]
+
+
 _LIB = None
 
 
@@ -111,6 +122,12 @@ def _declare(lib: C.CDLL) -> None:
     ]
     lib.hb_fading_state.restype = C.c_int
     lib.hb_fading_state.argtypes = [C.POINTER(FadingProblem), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+    lib.hb_launch_counts.restype = None
+    lib.hb_launch_counts.argtypes = [C.POINTER(C.c_int64)]
+    lib.hb_profile_begin.restype = C.c_int
+    lib.hb_profile_begin.argtypes = []
+    lib.hb_profile_end.restype = C.c_int
+    lib.hb_profile_end.argtypes = [C.POINTER(ProfileReport)]
     lib.hb_release.restype = None
     lib.hb_release.argtypes = []
 
@@ -140,3 +157,21 @@ def check(status: int) -> None:
 
 def device_count() -> int:
     return int(load().hb_device_count())
+
+
+def launch_counts() -> dict:
+    """Kernel launches per kind since the library was loaded."""
+    arr = (C.c_int64 * NUM_KERNEL_KINDS)()
+    load().hb_launch_counts(arr)
+    return {k: int(arr[i]) for i, k in enumerate(KERNEL_KINDS)}
+
+
+def profile_begin() -> None:
+    check(load().hb_profile_begin())
+
+
+def profile_end() -> dict:
+    """Per-kind summed device time (ms) and launch counts since ``profile_begin``."""
+    rep = ProfileReport()
+    check(load().hb_profile_end(C.byref(rep)))
+    return {k: {"ms": float(rep.ms[i]), "launches": int(rep.launches[i])} for i, k in enumerate(KERNEL_KINDS)}

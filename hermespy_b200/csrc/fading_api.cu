@@ -1,6 +1,5 @@
 // C-ABI entry points of the fading hot path: planning, device-resident launch, host-buffer pipeline.
 #include <math.h>
-#include <stdarg.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -10,34 +9,6 @@
 #include "fading_kernels.cuh"
 
 namespace hb {
-
-// ---- error plumbing -----------------------------------------------------------------------------
-static thread_local char g_err[512] = "";
-
-void set_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-}
-
-int cuda_fail(cudaError_t e, const char* what) {
-  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
-  cudaGetLastError();  // clear the sticky-less error state
-  return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? HB_ERR_NO_DEVICE : HB_ERR_CUDA;
-}
-
-int require_device() {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0) {
-    cudaGetLastError();
-    set_error("no CUDA device visible (%s); libhermes_b200 has no CPU fallback",
-              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    return HB_ERR_NO_DEVICE;
-  }
-  return HB_OK;
-}
 
 // ---- problem validation / delay groups -------------------------------------------------------------
 static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
@@ -215,6 +186,7 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
 
 template <int P>
 static int launch_coef(const FadingArgs& a, const DelayTable& dt, cudaStream_t st) {
+  ProfileScope prof(KIND_SOS_COEF, st);
   sos_poly_coef_kernel<P><<<(unsigned)((size_t)a.ntiles * a.B), 128, 0, st>>>(a, dt);
   HB_CUDA(cudaGetLastError());
   return HB_OK;
@@ -235,6 +207,7 @@ static int launch_coef_any(int P, const FadingArgs& a, const DelayTable& dt, cud
 
 static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& a, const DelayTable& dt,
                         cudaStream_t st) {
+  ProfileScope prof(pl.mode == HB_SOS_POLY ? KIND_TDL_POLY : KIND_TDL_DIRECT, st);
   if (pl.mode == HB_SOS_POLY) {
     switch (pl.ntx_tpl) {
       case 1: return launch_tdl_poly<1>(pl.P, io128, a, dt, pl.smem, st);
@@ -343,19 +316,6 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 using namespace hb;
 
 extern "C" {
-
-int hb_version(void) { return HB_VERSION; }
-
-const char* hb_last_error(void) { return g_err; }
-
-int hb_device_count(void) {
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return n;
-}
 
 int hb_fading_plan(const hb_fading_problem* p, hb_fading_plan_info* info) {
   DelayTable dt;
@@ -495,6 +455,7 @@ int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_delay_ou
     return HB_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(KIND_SOS_STATE, st);
   const bool f64 = p->precision == HB_F64, io128 = p->io_complex128 != 0;
   if (f64 && io128) sos_state_kernel<double, double2><<<(unsigned)blocks, kThreads, 0, st>>>(a, dt);
   else if (f64) sos_state_kernel<double, float2><<<(unsigned)blocks, kThreads, 0, st>>>(a, dt);

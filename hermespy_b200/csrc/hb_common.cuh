@@ -22,6 +22,33 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int require_device();
 
+// ---- per-kernel accounting (hb_profile_begin/end, hb_launch_counts) -------------------------------
+enum KernelKind {
+  KIND_SOS_COEF = 0,
+  KIND_TDL_POLY = 1,
+  KIND_TDL_DIRECT = 2,
+  KIND_SOS_STATE = 3,
+  KIND_CDL_RAYS = 4,
+  KIND_CDL_PROPAGATE = 5,
+  KIND_SPATIAL_GEMM = 6,
+  KIND_STATS = 7,
+  KIND_MISC = 8,
+  KIND_COUNT = HB_NUM_KERNEL_KINDS
+};
+
+// RAII marker around ONE kernel launch on `stream`: always counts the launch; when profiling is enabled it
+// also brackets the launch with CUDA events recorded on the launching stream.
+class ProfileScope {
+ public:
+  ProfileScope(int kind, cudaStream_t stream);
+  ~ProfileScope();
+
+ private:
+  int kind_;
+  cudaStream_t stream_;
+  cudaEvent_t start_;
+};
+
 #define HB_CUDA(call)                                   \
   do {                                                  \
     cudaError_t _e = (call);                            \

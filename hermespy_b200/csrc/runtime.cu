@@ -1,0 +1,130 @@
+// Library-wide runtime: error strings, device checks, per-kernel launch accounting.
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "hb_common.cuh"
+
+namespace hb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  cudaGetLastError();
+  return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? HB_ERR_NO_DEVICE : HB_ERR_CUDA;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible (%s); libhermes_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return HB_ERR_NO_DEVICE;
+  }
+  return HB_OK;
+}
+
+// ---- accounting -----------------------------------------------------------------------------------
+static std::atomic<long long> g_counts[KIND_COUNT];
+static std::atomic<bool> g_profiling{false};
+struct Bracket {
+  int kind;
+  cudaEvent_t start, stop;
+};
+static std::mutex g_prof_mu;
+static std::vector<Bracket> g_brackets;
+
+ProfileScope::ProfileScope(int kind, cudaStream_t stream) : kind_(kind), stream_(stream), start_(nullptr) {
+  g_counts[kind_].fetch_add(1, std::memory_order_relaxed);
+  if (g_profiling.load(std::memory_order_relaxed)) {
+    if (cudaEventCreate(&start_) == cudaSuccess) {
+      cudaEventRecord(start_, stream_);
+    } else {
+      start_ = nullptr;
+      cudaGetLastError();
+    }
+  }
+}
+
+ProfileScope::~ProfileScope() {
+  if (!start_) return;
+  cudaEvent_t stop = nullptr;
+  if (cudaEventCreate(&stop) != cudaSuccess) {
+    cudaGetLastError();
+    cudaEventDestroy(start_);
+    return;
+  }
+  cudaEventRecord(stop, stream_);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_brackets.push_back({kind_, start_, stop});
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+int hb_version(void) { return HB_VERSION; }
+
+const char* hb_last_error(void) { return g_err; }
+
+int hb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void hb_launch_counts(int64_t* counts) {
+  if (!counts) return;
+  for (int k = 0; k < KIND_COUNT; ++k) counts[k] = (int64_t)g_counts[k].load();
+}
+
+int hb_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (auto& b : g_brackets) {
+    cudaEventDestroy(b.start);
+    cudaEventDestroy(b.stop);
+  }
+  g_brackets.clear();
+  g_profiling.store(true);
+  return HB_OK;
+}
+
+int hb_profile_end(hb_profile_report* report) {
+  g_profiling.store(false);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  int rc = HB_OK;
+  if (report) memset(report, 0, sizeof(*report));
+  for (auto& b : g_brackets) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(b.stop);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, b.start, b.stop);
+    if (e != cudaSuccess && rc == HB_OK) rc = cuda_fail(e, "profile event");
+    if (report && e == cudaSuccess) {
+      report->ms[b.kind] += (double)ms;
+      report->launches[b.kind] += 1;
+    }
+    cudaEventDestroy(b.start);
+    cudaEventDestroy(b.stop);
+  }
+  g_brackets.clear();
+  return rc;
+}
+
+}  // extern "C"

@@ -47,6 +47,7 @@ extern "C" {
 #define HB_VERSION 100 /* 0.1.0 */
 #define HB_MAX_TAPS 256
 #define HB_MAX_POLY_ORDER 8
+#define HB_NUM_KERNEL_KINDS 9
 
 typedef enum hb_status {
   HB_OK = 0,
@@ -122,6 +123,20 @@ HB_API int hb_fading_propagate_host(const hb_fading_problem* p, const void* x, v
  * distinct integer delay, plus the delays themselves in group_delay_out (HOST int32[G], may be NULL).
  * CSI[b, i, j, n, group_delay[g]] = spatial[b, i, j] * h[b, g, n]   (fading.py:351-364). */
 HB_API int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_delay_out, void* stream);
+
+/* Per-kernel accounting.  Kinds: 0 sos_poly_coef, 1 tdl_poly, 2 tdl_direct, 3 sos_state, 4 cdl_rays,
+ * 5 cdl_propagate, 6 spatial_gemm, 7 stats, 8 misc.
+ * hb_launch_counts: launches of each kind since load (always counted).
+ * hb_profile_begin/end: between the two calls every kernel launch is bracketed by CUDA events recorded on
+ * its own launch stream; hb_profile_end synchronizes those events and returns summed device time (ms) and
+ * launch counts per kind.  Meant for bench.py's live roofline measurement. */
+typedef struct hb_profile_report {
+  double ms[HB_NUM_KERNEL_KINDS];
+  int64_t launches[HB_NUM_KERNEL_KINDS];
+} hb_profile_report;
+HB_API void hb_launch_counts(int64_t* counts /* [HB_NUM_KERNEL_KINDS] */);
+HB_API int hb_profile_begin(void);
+HB_API int hb_profile_end(hb_profile_report* report);
 
 /* Release cached device workspaces / streams of the calling process. */
 HB_API void hb_release(void);

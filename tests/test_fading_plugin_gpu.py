@@ -128,7 +128,8 @@ def test_seed_reproducibility():
     fs = 1e6
     tx, rx = _link(fs=fs)
     x = Signal.Create(np.ones((1, 32), complex), fs)
-    ch = MC.Cost259(MC.Cost259Type.RURAL, seed=100)
+    ch = MC.Cost259(MC.Cost259Type.RURAL)
+    ch.seed = 100
     a = ch.realize().sample(tx, rx).propagate(x).view(np.ndarray)
     ch.seed = 100
     b = ch.realize().sample(tx, rx).propagate(x).view(np.ndarray)
