@@ -65,43 +65,58 @@ def measured_peaks():
 
 # ---- clocks ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons through NVML (ctypes calls release the GIL; no fork inside
+    the timed region -- spawning nvidia-smi from a thread stalled the launch loop by milliseconds)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
         self._stop_evt = threading.Event()
+        self.h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((sm, reasons, power))
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+                    "note": getattr(self, "err", "no NVML samples")}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        seen = set()
+        for _, r, _ in self.rows:
+            for bit, name in names.items():
+                if r & bit:
+                    seen.add(name)
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(seen), "samples": len(self.rows), "power_w_max": max(r[2] for r in self.rows)}
 
 
 # ---- CPU baseline (oracle port of the reference path) ---------------------------------------------------------
@@ -312,7 +327,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--links", type=int, default=2048, help="links per step per GPU")

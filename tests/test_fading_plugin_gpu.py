@@ -164,4 +164,6 @@ def test_expected_energy_scale(build):
     ys = propagate_batch(samples, [x] * len(samples), precision="f32")
     energy = np.mean([np.sum(np.abs(y) ** 2) for y in ys])
     expected = np.mean([s.expected_energy_scale for s in samples])
-    assert abs(energy - expected) < 0.1
+    # the reference asserts |E - scale^2| < 0.1 for profiles normalized to one; the exponential profile is not
+    # normalized (exponential.py:96-100), so compare relatively
+    assert abs(energy / expected - 1.0) < 0.1
