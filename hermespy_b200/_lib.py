@@ -145,6 +145,7 @@ def load() -> C.CDLL:
             )
         lib = C.CDLL(str(path))
         _declare(lib)
+        _declare_cdl(lib)
         _LIB = lib
     return _LIB
 
@@ -175,3 +176,44 @@ def profile_end() -> dict:
     rep = ProfileReport()
     check(load().hb_profile_end(C.byref(rep)))
     return {k: {"ms": float(rep.ms[i]), "launches": int(rep.launches[i])} for i, k in enumerate(KERNEL_KINDS)}
+
+
+class CdlProblem(C.Structure):
+    """Mirror of ``hb_cdl_problem``."""
+
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("num_tx", C.c_int32),
+        ("num_rx", C.c_int32),
+        ("num_samples", C.c_int32),
+        ("max_delay", C.c_int32),
+        ("num_terms", C.c_int32),
+        ("line_of_sight", C.c_int32),
+        ("los_delay", C.c_int32),
+        ("precision", C.c_int32),
+        ("io_complex128", C.c_int32),
+        ("carrier_frequency", C.c_double),
+        ("sampling_rate", C.c_double),
+        ("los_amplitude", C.c_double),
+        ("max_speed", C.c_double),
+        ("term_delay", C.POINTER(C.c_int32)),
+        ("angles", C.c_void_p),
+        ("jones", C.c_void_p),
+        ("amplitude", C.c_void_p),
+        ("tx_pose", C.c_void_p),
+        ("rx_pose", C.c_void_p),
+        ("rel_velocity", C.c_void_p),
+        ("tx_topology", C.c_void_p),
+        ("rx_topology", C.c_void_p),
+    ]
+
+
+def _declare_cdl(lib: C.CDLL) -> None:
+    lib.hb_cdl_plan.restype = C.c_int
+    lib.hb_cdl_plan.argtypes = [C.POINTER(CdlProblem), C.POINTER(FadingPlanInfo)]
+    lib.hb_cdl_propagate.restype = C.c_int
+    lib.hb_cdl_propagate.argtypes = [C.POINTER(CdlProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FadingPlanInfo)]
+    lib.hb_cdl_propagate_host.restype = C.c_int
+    lib.hb_cdl_propagate_host.argtypes = [C.POINTER(CdlProblem), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(FadingPlanInfo)]
+    lib.hb_cdl_state.restype = C.c_int
+    lib.hb_cdl_state.argtypes = [C.POINTER(CdlProblem), C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]

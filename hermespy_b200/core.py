@@ -193,10 +193,11 @@ class SimulatedIdealAntenna(object):
 
 
 class SimulatedUniformArray(object):
-    """Uniform rectangular array of identical antennas (hermespy/simulation/antennas.py uniform array).
+    """Uniform rectangular array of identical antennas (hermespy/core/antennas.py:1299-1410).
 
-    Element ``(ix, iy, iz)`` sits at ``spacing * (ix, iy, iz)`` centred on the array origin; the element
-    order is x fastest, as in the reference (``np.meshgrid`` of centred index ranges, flattened).
+    Element positions are ``spacing * (ix, iy, iz)`` -- not centred -- enumerated exactly like the reference's
+    ``np.meshgrid(arange(nx), arange(ny), arange(nz))`` (default 'xy' indexing) flattened in C order
+    (antennas.py:1344-1351): z fastest, then x, then y.
     """
 
     def __init__(self, element=SimulatedIdealAntenna, spacing: float = 1.0, dimensions: Tuple[int, ...] = (1, 1, 1)) -> None:
@@ -216,13 +217,8 @@ class SimulatedUniformArray(object):
     def topology(self) -> np.ndarray:
         """Element positions ``[M, 3]`` in the array frame."""
         nx, ny, nz = self.dimensions
-        gx = self.spacing * (np.arange(nx) - 0.5 * (nx - 1))
-        gy = self.spacing * (np.arange(ny) - 0.5 * (ny - 1))
-        gz = self.spacing * (np.arange(nz) - 0.5 * (nz - 1))
-        out = np.empty((nx * ny * nz, 3))
-        for i, (z, y, x) in enumerate(itertools.product(gz, gy, gx)):
-            out[i] = (x, y, z)
-        return out
+        grid = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz))
+        return self.spacing * np.vstack((grid[0].flat, grid[1].flat, grid[2].flat)).T.astype(np.float64)
 
     def state(self, pose: Transformation) -> "AntennaArrayState":
         return AntennaArrayState(self, pose)

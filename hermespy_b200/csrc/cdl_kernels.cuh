@@ -1,0 +1,412 @@
+// 3GPP cluster-delay-line hot path kernels (sm_100a).
+//
+//   K5  cdl_ray_kernel        per (link, ray term), FP64: polarization scalar alpha, Doppler rate w, and the
+//                             unit-modulus steering phases u[Nrx], v[Ntx] of the array responses
+//                             (cluster_delay_lines.py:409-523, core/antennas.py:138-210, 883-1000)
+//   K5b cdl_moment_kernel     per (link, tile, delay group): Taylor moments of the time-varying MIMO matrix
+//                             H_g(m) = sum_{t in g} alpha_t e^{j w_t (m - k_g)} u_t v_t^T   (FP32 output)
+//   K6  cdl_poly_kernel       y[:, m] = sum_p r^p sum_g M[g,p] x[:, m - k_g]; x tile + delay halo and the moment
+//                             matrices staged in shared memory per chunk of 8 transmit antennas
+//                             (cluster_delay_lines.py:526-558)
+//   K6' cdl_direct_f64_kernel FP64 parity mode: every ray term evaluated per sample exactly like the reference
+//   cdl_state_kernel          H_g(n) for the channel state (cluster_delay_lines.py:561-592)
+//
+// Structure exploited: for arrays of identical, identically oriented elements the per-ray matrix of the reference,
+// a_rx J a_tx^T, is rank one: H_t = alpha_t u_t v_t^T with u, v pure phases.  Terms sharing a delay index are summed
+// into one matrix per delay group before touching the signal, which removes the ray count from the per-sample cost.
+#pragma once
+#include "hb_common.cuh"
+
+namespace hb {
+
+constexpr int kCdlMaxTerms = HB_CDL_MAX_TERMS;
+constexpr int kCdlMaxGroups = HB_CDL_MAX_GROUPS;
+constexpr int kCdlTxChunk = 8;  // transmit antennas staged per pass of K6
+constexpr double kSpeedOfLight = 299792458.0;
+
+// Launch-uniform term tables, passed by value in kernel parameter space.
+struct CdlTable {
+  int32_t num_terms;   // ray terms incl. the optional line-of-sight term (always the last one)
+  int32_t num_groups;  // distinct delay indices
+  int32_t has_los;     // 1: term num_terms-1 is the line-of-sight term
+  int32_t group_delay[kCdlMaxGroups];
+  uint16_t group_start[kCdlMaxGroups + 1];  // into term_order
+  uint16_t term_order[kCdlMaxTerms];        // terms sorted by delay group
+  uint16_t term_delay[kCdlMaxTerms];        // delay index per term (original order)
+};
+
+struct CdlArgs {
+  const void* x;
+  void* y;
+  // inputs of K5
+  const double* angles;       // [B, Rn, 4] aoa, zoa, aod, zod
+  const double2* jones;       // [B, Rn, 4]
+  const double* amp;          // [B, Rn]
+  const double* tx_pose;      // [B, 12]
+  const double* rx_pose;      // [B, 12]
+  const double* rel_velocity; // [B, 3]
+  const double* tx_topology;  // [Ntx, 3]
+  const double* rx_topology;  // [Nrx, 3]
+  // ray coefficients (K5 out)
+  double2* alpha;  // [B, Rt]
+  double* w;       // [B, Rt] rad / sample
+  double2* u;      // [B, Rt, Nrx]
+  double2* v;      // [B, Rt, Ntx]
+  float2* moments; // [B, ntiles, G, P, Nrx, Ntx]
+  double wavelength_factor;  // fc / c0
+  double fs;
+  double los_amp;
+  int B, ntx, nrx, T, D, Rn, Rt;
+  int tile, ntiles, Dpad, P;
+  int rx0, nrx_chunk;
+};
+
+struct Vec3 {
+  double x, y, z;
+};
+__device__ __forceinline__ Vec3 mat_t_vec(const double* R, Vec3 a) {  // R^T a, R row-major
+  return {R[0] * a.x + R[3] * a.y + R[6] * a.z, R[1] * a.x + R[4] * a.y + R[7] * a.z,
+          R[2] * a.x + R[5] * a.y + R[8] * a.z};
+}
+__device__ __forceinline__ Vec3 mat_vec(const double* R, Vec3 a) {
+  return {R[0] * a.x + R[1] * a.y + R[2] * a.z, R[3] * a.x + R[4] * a.y + R[5] * a.z,
+          R[6] * a.x + R[7] * a.y + R[8] * a.z};
+}
+__device__ __forceinline__ double dot3(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// theta / phi unit vectors of TR 38.901 eq. 7.1-13/14 for a unit direction d (azimuth = atan2(y, x),
+// zenith = acos(z), as hermespy/core/transformation.py:66-84), formed without inverse trigonometry.
+__device__ __forceinline__ void sph_basis(Vec3 d, Vec3* th, Vec3* ph) {
+  const double rho = sqrt(d.x * d.x + d.y * d.y);
+  const double ca = rho > 0.0 ? d.x / rho : 1.0, sa = rho > 0.0 ? d.y / rho : 0.0;
+  const double cz = fmin(1.0, fmax(-1.0, d.z)), sz = sqrt(fmax(0.0, 1.0 - cz * cz));
+  *th = {cz * ca, cz * sa, -sz};
+  *ph = {-sa, ca, 0.0};
+}
+
+// Polarization of an ideal isotropic element ([2^-1/2, 2^-1/2] locally) towards global unit direction g
+// for an element whose orientation is R (core/antennas.py:138-210).
+__device__ __forceinline__ void ideal_polarization(const double* R, Vec3 g, double* f_theta, double* f_phi) {
+  Vec3 thg, phg, thl, phl;
+  sph_basis(g, &thg, &phg);
+  sph_basis(mat_t_vec(R, g), &thl, &phl);
+  const Vec3 thlt = mat_vec(R, thl), phlt = mat_vec(R, phl);
+  const double s = 0.70710678118654752440;
+  *f_theta = (dot3(thg, thlt) + dot3(thg, phlt)) * s;
+  *f_phi = (dot3(phg, thlt) + dot3(phg, phlt)) * s;
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// exp(-2j pi * turns) with the integer part of `turns` removed in FP64 first.
+__device__ __forceinline__ double2 phasor_neg_turns(double turns) {
+  const double f = turns - rint(turns);
+  double s, c;
+  sincospi(-2.0 * f, &s, &c);
+  return make_double2(c, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: one thread per (link, term).
+__global__ void __launch_bounds__(128) cdl_ray_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)a.B * a.Rt) return;
+  const int b = (int)(gid / a.Rt), t = (int)(gid - (long long)b * a.Rt);
+  const double* tp = a.tx_pose + (size_t)b * 12;
+  const double* rp = a.rx_pose + (size_t)b * 12;
+  const Vec3 ttx = {tp[9], tp[10], tp[11]}, trx = {rp[9], rp[10], rp[11]};
+  const Vec3 rv = {a.rel_velocity[b * 3 + 0], a.rel_velocity[b * 3 + 1], a.rel_velocity[b * 3 + 2]};
+  const bool los = tb.has_los && t == a.Rt - 1;
+
+  Vec3 tgt_rx, tgt_tx, wave;  // positions handed to the array responses, and the Doppler wave vector
+  double2 j00, j01, j10, j11;
+  double2 scale;
+  if (!los) {
+    const double* ang = a.angles + ((size_t)b * a.Rn + t) * 4;
+    double sa, ca, sz, cz;
+    sincos(ang[0], &sa, &ca);
+    sincos(ang[1], &sz, &cz);
+    tgt_rx = {sz * ca, sz * sa, cz};  // unit vector used as a global *position* 
+    wave = tgt_rx;
+    sincos(ang[2], &sa, &ca);
+    sincos(ang[3], &sz, &cz);
+    tgt_tx = {sz * ca, sz * sa, cz};
+    const double2* J = a.jones + ((size_t)b * a.Rn + t) * 4;
+    j00 = J[0];
+    j01 = J[1];
+    j10 = J[2];
+    j11 = J[3];
+    scale = make_double2(a.amp[(size_t)b * a.Rn + t], 0.0);
+  } else {
+    tgt_rx = ttx;  // receiver array looks at the transmitter position and vice versa
+    tgt_tx = trx;
+    const Vec3 dv = {trx.x - ttx.x, trx.y - ttx.y, trx.z - ttx.z};
+    const double dist = sqrt(dot3(dv, dv));
+    wave = {dv.x / dist, dv.y / dist, dv.z / dist};
+    j00 = make_double2(1.0, 0.0);  // [[1, 0], [-1, 0]] (sic, cluster_delay_lines.py:515)
+    j01 = make_double2(0.0, 0.0);
+    j10 = make_double2(-1.0, 0.0);
+    j11 = make_double2(0.0, 0.0);
+    const double2 ph = phasor_neg_turns(dist * a.wavelength_factor);
+    scale = make_double2(a.los_amp * ph.x, a.los_amp * ph.y);
+  }
+
+  // polarization towards normalize(target - array position)
+  Vec3 grx = {tgt_rx.x - trx.x, tgt_rx.y - trx.y, tgt_rx.z - trx.z};
+  Vec3 gtx = {tgt_tx.x - ttx.x, tgt_tx.y - ttx.y, tgt_tx.z - ttx.z};
+  const Vec3 lrx = mat_t_vec(rp, grx), ltx = mat_t_vec(tp, gtx);  // targets in array coordinates
+  double n = sqrt(dot3(grx, grx));
+  grx = {grx.x / n, grx.y / n, grx.z / n};
+  n = sqrt(dot3(gtx, gtx));
+  gtx = {gtx.x / n, gtx.y / n, gtx.z / n};
+  double frt, frp, ftt, ftp;
+  ideal_polarization(rp, grx, &frt, &frp);
+  ideal_polarization(tp, gtx, &ftt, &ftp);
+  // F_rx^T J F_tx
+  double2 jt0 = make_double2(j00.x * ftt + j01.x * ftp, j00.y * ftt + j01.y * ftp);
+  double2 jt1 = make_double2(j10.x * ftt + j11.x * ftp, j10.y * ftt + j11.y * ftp);
+  double2 pol = make_double2(frt * jt0.x + frp * jt1.x, frt * jt0.y + frp * jt1.y);
+  a.alpha[(size_t)b * a.Rt + t] = cmul(pol, scale);
+  a.w[(size_t)b * a.Rt + t] = kTwoPi * dot3(wave, rv) * a.wavelength_factor / a.fs;
+
+  double2* u = a.u + ((size_t)b * a.Rt + t) * a.nrx;
+  for (int i = 0; i < a.nrx; ++i) {
+    const double dx = a.rx_topology[i * 3] - lrx.x, dy = a.rx_topology[i * 3 + 1] - lrx.y,
+                 dz = a.rx_topology[i * 3 + 2] - lrx.z;
+    u[i] = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+  }
+  double2* v = a.v + ((size_t)b * a.Rt + t) * a.ntx;
+  for (int j = 0; j < a.ntx; ++j) {
+    const double dx = a.tx_topology[j * 3] - ltx.x, dy = a.tx_topology[j * 3 + 1] - ltx.y,
+                 dz = a.tx_topology[j * 3 + 2] - ltx.z;
+    v[j] = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b: moments of the group matrices about the tile centre.  grid = B * ntiles * G, 128 threads over (i, j).
+//   M[g][p][i][j] = sum_{t in g} alpha_t e^{j w_t (centre - k_g)} (j w_t tile)^p / p! * u_t[i] v_t[j]
+template <int P>
+__global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
+  __shared__ float2 beta[64];
+  __shared__ float ut[64];
+  const int G = tb.num_groups;
+  const int bq = blockIdx.x / G, g = blockIdx.x - bq * G;
+  const int b = bq / a.ntiles, q = bq - b * a.ntiles;
+  const int t0 = tb.group_start[g], t1 = tb.group_start[g + 1];
+  const double shift = (double)q * a.tile + 0.5 * a.tile - (double)tb.group_delay[g];
+  const int nij = a.nrx * a.ntx;
+  float2* out = a.moments + ((((size_t)b * a.ntiles + q) * G + g) * P) * nij;
+  for (int ij0 = 0; ij0 < nij; ij0 += blockDim.x) {
+    const int ij = ij0 + threadIdx.x;
+    const int i = ij / a.ntx, j = ij - i * a.ntx;
+    float accr[P], acci[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) accr[p] = acci[p] = 0.f;
+    for (int c0 = t0; c0 < t1; c0 += 64) {
+      __syncthreads();
+      if (threadIdx.x < 64 && c0 + threadIdx.x < t1) {
+        const int t = tb.term_order[c0 + threadIdx.x];
+        const double w = a.w[(size_t)b * a.Rt + t];
+        double turns = w * shift * kInvTwoPi;
+        turns -= rint(turns);
+        double s, c;
+        sincospi(2.0 * turns, &s, &c);
+        const double2 al = a.alpha[(size_t)b * a.Rt + t];
+        beta[threadIdx.x] = make_float2((float)(al.x * c - al.y * s), (float)(al.x * s + al.y * c));
+        ut[threadIdx.x] = (float)(w * (double)a.tile);
+      }
+      __syncthreads();
+      if (ij < nij) {
+        const int nc = min(64, t1 - c0);
+        for (int k = 0; k < nc; ++k) {
+          const int t = tb.term_order[c0 + k];
+          const double2 uu = a.u[((size_t)b * a.Rt + t) * a.nrx + i];
+          const double2 vv = a.v[((size_t)b * a.Rt + t) * a.ntx + j];
+          const float uvr = (float)(uu.x * vv.x - uu.y * vv.y), uvi = (float)(uu.x * vv.y + uu.y * vv.x);
+          float tr = beta[k].x * uvr - beta[k].y * uvi, ti = beta[k].x * uvi + beta[k].y * uvr;
+          accr[0] += tr;
+          acci[0] += ti;
+#pragma unroll
+          for (int p = 1; p < P; ++p) {
+            const float f = ut[k] * (1.0f / (float)p);
+            const float nr = -ti * f, ni = tr * f;
+            tr = nr;
+            ti = ni;
+            accr[p] += tr;
+            acci[p] += ti;
+          }
+        }
+      }
+    }
+    if (ij < nij) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) out[(size_t)p * nij + ij] = make_float2(accr[p], acci[p]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: grid = B * ntiles, THREADS threads, R consecutive-stride samples per thread, NRX receive rows per launch.
+//   smem: xs[kCdlTxChunk][W] | ms[G][P][NRX][kCdlTxChunk]
+template <int NRX, int P, int R, int THREADS, typename IO>
+__global__ void __launch_bounds__(THREADS) cdl_poly_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x / a.ntiles, q = blockIdx.x - b * a.ntiles, tid = threadIdx.x;
+  const int W = a.tile + a.Dpad;
+  const int G = tb.num_groups;
+  float2* xs = reinterpret_cast<float2*>(smem_raw);
+  float2* ms = xs + kCdlTxChunk * W;
+  const int Tout = a.T + a.D;
+  const int nij = a.nrx * a.ntx;
+  const IO* xb = reinterpret_cast<const IO*>(a.x) + (size_t)b * a.ntx * a.T;
+  const float2* mb = a.moments + (((size_t)b * a.ntiles + q) * G) * P * nij;
+  const int n0 = q * a.tile - a.Dpad;
+
+  float2 acc[R][P][NRX];
+#pragma unroll
+  for (int u = 0; u < R; ++u)
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int i = 0; i < NRX; ++i) acc[u][p][i] = make_float2(0.f, 0.f);
+
+  for (int j0 = 0; j0 < a.ntx; j0 += kCdlTxChunk) {
+    const int nj = min(kCdlTxChunk, a.ntx - j0);
+    __syncthreads();
+    for (int jj = 0; jj < nj; ++jj) {
+      const IO* row = xb + (size_t)(j0 + jj) * a.T;
+#pragma unroll 4
+      for (int c = tid; c < W; c += THREADS) {
+        const int n = n0 + c;
+        float2 v = make_float2(0.f, 0.f);
+        if (n >= 0 && n < a.T) v = to_c32(ldg_stream(row + n));
+        xs[jj * W + c] = v;
+      }
+    }
+    // ms[((g * P + p) * NRX + i) * chunk + jj] <- M[g][p][rx0 + i][j0 + jj]
+    for (int c = tid; c < G * P * NRX * kCdlTxChunk; c += THREADS) {
+      const int jj = c % kCdlTxChunk;
+      const int i = (c / kCdlTxChunk) % NRX;
+      const int gp = c / (kCdlTxChunk * NRX);
+      float2 v = make_float2(0.f, 0.f);
+      if (jj < nj && i < a.nrx_chunk) v = mb[(size_t)gp * nij + (size_t)(a.rx0 + i) * a.ntx + j0 + jj];
+      ms[c] = v;
+    }
+    __syncthreads();
+
+    for (int g = 0; g < G; ++g) {
+      const int off = tid + a.Dpad - tb.group_delay[g];
+      const float2* mg = ms + (size_t)g * P * NRX * kCdlTxChunk;
+      for (int jj = 0; jj < nj; ++jj) {
+        float2 xv[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) xv[u] = xs[jj * W + off + u * THREADS];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+#pragma unroll
+          for (int i = 0; i < NRX; ++i) {
+            const float2 m = mg[(p * NRX + i) * kCdlTxChunk + jj];
+#pragma unroll
+            for (int u = 0; u < R; ++u) cmac<float>(acc[u][p][i], m, xv[u]);
+          }
+        }
+      }
+    }
+  }
+
+  const float inv_tile = 1.0f / (float)a.tile, half = 0.5f * (float)a.tile;
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const int il = u * THREADS + tid;
+    const int m = q * a.tile + il;
+    if (il < a.tile && m < Tout) {
+      const float r = ((float)il - half) * inv_tile;
+#pragma unroll
+      for (int i = 0; i < NRX; ++i) {
+        if (i < a.nrx_chunk) {
+          float2 v = acc[u][P - 1][i];
+#pragma unroll
+          for (int p = P - 2; p >= 0; --p) {
+            v.x = fmaf(v.x, r, acc[u][p][i].x);
+            v.y = fmaf(v.y, r, acc[u][p][i].y);
+          }
+          IO* dst = reinterpret_cast<IO*>(a.y) + ((size_t)b * a.nrx + a.rx0 + i) * Tout + m;
+          stg_stream(dst, IoConv<IO>::make(v.x, v.y));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6' FP64 parity mode: y[b, :, m] = sum_t alpha_t e^{j w_t (m - k_t)} u_t (v_t^T x[:, m - k_t]).
+// One thread per (link, output sample); x read through L1/L2 (coalesced along time).
+template <typename IO>
+__global__ void __launch_bounds__(128) cdl_direct_f64_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
+  const int Tout = a.T + a.D;
+  const int nblk = (Tout + 127) / 128;
+  const int b = blockIdx.x / nblk;
+  const int m = (blockIdx.x - b * nblk) * 128 + threadIdx.x;
+  if (m >= Tout) return;
+  const IO* xb = reinterpret_cast<const IO*>(a.x) + (size_t)b * a.ntx * a.T;
+  IO* yb = reinterpret_cast<IO*>(a.y) + (size_t)b * a.nrx * Tout + m;
+  // accumulate receive rows in chunks of 8 to bound registers
+  for (int i0 = 0; i0 < a.nrx; i0 += 8) {
+    double2 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = make_double2(0.0, 0.0);
+    for (int t = 0; t < a.Rt; ++t) {
+      const int n = m - (int)tb.term_delay[t];
+      if (n < 0 || n >= a.T) continue;
+      const double2* v = a.v + ((size_t)b * a.Rt + t) * a.ntx;
+      double2 s = make_double2(0.0, 0.0);
+      for (int j = 0; j < a.ntx; ++j) {
+        const double2 xv = to_c64(xb[(size_t)j * a.T + n]);
+        cmac<double>(s, v[j], xv);
+      }
+      double sn, cs;
+      sincos(a.w[(size_t)b * a.Rt + t] * (double)n, &sn, &cs);
+      const double2 g = cmul(cmul(a.alpha[(size_t)b * a.Rt + t], make_double2(cs, sn)), s);
+      const double2* u = a.u + ((size_t)b * a.Rt + t) * a.nrx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i0 + i < a.nrx) cmac<double>(acc[i], u[i0 + i], g);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i0 + i < a.nrx) yb[(size_t)(i0 + i) * Tout] = IoConv<IO>::make(acc[i].x, acc[i].y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Channel state: H[b, g, i, j, n] = sum_{t in g} alpha_t e^{j w_t n} u_t[i] v_t[j]   (FP64 evaluation)
+template <typename IO>
+__global__ void __launch_bounds__(128) cdl_state_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
+  const int nblk = (a.T + 127) / 128;
+  const int nij = a.nrx * a.ntx;
+  long long blk = blockIdx.x;
+  const int nb = (int)(blk % nblk);
+  blk /= nblk;
+  const int ij = (int)(blk % nij);
+  blk /= nij;
+  const int g = (int)(blk % tb.num_groups);
+  const int b = (int)(blk / tb.num_groups);
+  const int n = nb * 128 + threadIdx.x;
+  if (n >= a.T) return;
+  const int i = ij / a.ntx, j = ij - i * a.ntx;
+  double2 h = make_double2(0.0, 0.0);
+  for (int c = tb.group_start[g]; c < tb.group_start[g + 1]; ++c) {
+    const int t = tb.term_order[c];
+    double sn, cs;
+    sincos(a.w[(size_t)b * a.Rt + t] * (double)n, &sn, &cs);
+    const double2 uv = cmul(a.u[((size_t)b * a.Rt + t) * a.nrx + i], a.v[((size_t)b * a.Rt + t) * a.ntx + j]);
+    cmac<double>(h, cmul(a.alpha[(size_t)b * a.Rt + t], make_double2(cs, sn)), uv);
+  }
+  IO* out = reinterpret_cast<IO*>(a.y) + ((((size_t)b * tb.num_groups + g) * nij + ij) * a.T) + n;
+  *out = IoConv<IO>::make(h.x, h.y);
+}
+
+}  // namespace hb

@@ -272,44 +272,6 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   return rc;
 }
 
-// ---- host-buffer pipeline ---------------------------------------------------------------------------
-constexpr int kSlots = 3;
-struct HostPipe {
-  cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
-  void* buf[kSlots] = {nullptr, nullptr, nullptr};
-  size_t cap[kSlots] = {0, 0, 0};
-  int device = -1;
-};
-static HostPipe g_pipe;
-static std::mutex g_pipe_mu;
-
-static int pipe_prepare(size_t bytes) {
-  int dev = 0;
-  HB_CUDA(cudaGetDevice(&dev));
-  if (g_pipe.device != dev) {
-    for (int s = 0; s < kSlots; ++s) {
-      if (g_pipe.buf[s]) cudaFree(g_pipe.buf[s]);
-      if (g_pipe.st[s]) cudaStreamDestroy(g_pipe.st[s]);
-      g_pipe.buf[s] = nullptr;
-      g_pipe.cap[s] = 0;
-      g_pipe.st[s] = nullptr;
-    }
-    g_pipe.device = dev;
-  }
-  for (int s = 0; s < kSlots; ++s) {
-    if (!g_pipe.st[s]) HB_CUDA(cudaStreamCreateWithFlags(&g_pipe.st[s], cudaStreamNonBlocking));
-    if (g_pipe.cap[s] < bytes) {
-      if (g_pipe.buf[s]) HB_CUDA(cudaFree(g_pipe.buf[s]));
-      g_pipe.buf[s] = nullptr;
-      g_pipe.cap[s] = 0;
-      HB_CUDA(cudaMalloc(&g_pipe.buf[s], bytes));
-      g_pipe.cap[s] = bytes;
-    }
-  }
-  return HB_OK;
-}
-
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace hb
 
@@ -379,7 +341,7 @@ int hb_fading_propagate_host(const hb_fading_problem* p, const void* x, void* y,
   const size_t off_s = align_up(off_am + am_link * chunk, 256);
   const size_t total = align_up(off_s + s_link * chunk, 256);
 
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
   if (int e = pipe_prepare(total)) return e;
   int rc = HB_OK;
   int ci = 0;
@@ -463,18 +425,6 @@ int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_delay_ou
   else sos_state_kernel<float, float2><<<(unsigned)blocks, kThreads, 0, st>>>(a, dt);
   HB_CUDA(cudaGetLastError());
   return HB_OK;
-}
-
-void hb_release(void) {
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
-  for (int s = 0; s < kSlots; ++s) {
-    if (g_pipe.buf[s]) cudaFree(g_pipe.buf[s]);
-    if (g_pipe.st[s]) cudaStreamDestroy(g_pipe.st[s]);
-    g_pipe.buf[s] = nullptr;
-    g_pipe.cap[s] = 0;
-    g_pipe.st[s] = nullptr;
-  }
-  g_pipe.device = -1;
 }
 
 }  // extern "C"

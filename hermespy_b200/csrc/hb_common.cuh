@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "hermes_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -54,6 +56,22 @@ class ProfileScope {
     cudaError_t _e = (call);                            \
     if (_e != cudaSuccess) return hb::cuda_fail(_e, #call); \
   } while (0)
+
+// ---- host-buffer pipeline shared by the *_host entry points ------------------------------------------
+// kSlots device staging buffers, each with its own non-blocking stream: chunk c uses slot c % kSlots, so the H2D
+// copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of chunk c.
+constexpr int kSlots = 3;
+struct HostPipe {
+  cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+  void* buf[kSlots] = {nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0};
+  int device = -1;
+  std::mutex mu;
+};
+extern HostPipe g_pipe;
+int pipe_prepare(size_t bytes_per_slot);  // call with g_pipe.mu held
+void pipe_release();
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Launch-uniform delay tables, passed by value in kernel parameter (constant) space so that no
 // host->device copy with lifetime concerns is needed for them.

@@ -36,6 +36,40 @@ int require_device() {
   return HB_OK;
 }
 
+// ---- host pipeline -----------------------------------------------------------------------------------
+HostPipe g_pipe;
+
+void pipe_release() {
+  for (int s = 0; s < kSlots; ++s) {
+    if (g_pipe.buf[s]) cudaFree(g_pipe.buf[s]);
+    if (g_pipe.st[s]) cudaStreamDestroy(g_pipe.st[s]);
+    g_pipe.buf[s] = nullptr;
+    g_pipe.cap[s] = 0;
+    g_pipe.st[s] = nullptr;
+  }
+  g_pipe.device = -1;
+}
+
+int pipe_prepare(size_t bytes) {
+  int dev = 0;
+  HB_CUDA(cudaGetDevice(&dev));
+  if (g_pipe.device != dev) {
+    pipe_release();
+    g_pipe.device = dev;
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    if (!g_pipe.st[s]) HB_CUDA(cudaStreamCreateWithFlags(&g_pipe.st[s], cudaStreamNonBlocking));
+    if (g_pipe.cap[s] < bytes) {
+      if (g_pipe.buf[s]) HB_CUDA(cudaFree(g_pipe.buf[s]));
+      g_pipe.buf[s] = nullptr;
+      g_pipe.cap[s] = 0;
+      HB_CUDA(cudaMalloc(&g_pipe.buf[s], bytes));
+      g_pipe.cap[s] = bytes;
+    }
+  }
+  return HB_OK;
+}
+
 // ---- accounting -----------------------------------------------------------------------------------
 static std::atomic<long long> g_counts[KIND_COUNT];
 static std::atomic<bool> g_profiling{false};
@@ -88,6 +122,11 @@ int hb_device_count(void) {
     return 0;
   }
   return n;
+}
+
+void hb_release(void) {
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  pipe_release();
 }
 
 void hb_launch_counts(int64_t* counts) {

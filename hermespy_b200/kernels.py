@@ -372,3 +372,193 @@ def fading_state(batch: FadingBatch, num_samples: int, precision="f32", io128=Tr
         )
     del keep
     return h, gd
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Cluster delay line
+
+
+@dataclass
+class CdlBlock:
+    """Host-side parameter block of B CDL links sharing one delay structure (numpy arrays, see hb_cdl_problem)."""
+
+    term_delay: np.ndarray  # int32 [Rn]
+    max_delay: int
+    angles: np.ndarray  # f64 [B, Rn, 4] aoa, zoa, aod, zod
+    jones: np.ndarray  # c128 [B, Rn, 2, 2]
+    amplitude: np.ndarray  # f64 [B, Rn]
+    tx_pose: np.ndarray  # f64 [B, 12]
+    rx_pose: np.ndarray  # f64 [B, 12]
+    rel_velocity: np.ndarray  # f64 [B, 3]
+    tx_topology: np.ndarray  # f64 [Ntx, 3]
+    rx_topology: np.ndarray  # f64 [Nrx, 3]
+    carrier_frequency: float
+    sampling_rate: float
+    line_of_sight: bool = False
+    los_delay: int = 0
+    los_amplitude: float = 0.0
+    max_speed: Optional[float] = None
+
+    def __post_init__(self):
+        self.term_delay = np.ascontiguousarray(self.term_delay, dtype=np.int32)
+        self.angles = np.ascontiguousarray(self.angles, dtype=np.float64)
+        self.jones = np.ascontiguousarray(self.jones, dtype=np.complex128)
+        self.amplitude = np.ascontiguousarray(self.amplitude, dtype=np.float64)
+        self.tx_pose = np.ascontiguousarray(self.tx_pose, dtype=np.float64)
+        self.rx_pose = np.ascontiguousarray(self.rx_pose, dtype=np.float64)
+        self.rel_velocity = np.ascontiguousarray(self.rel_velocity, dtype=np.float64)
+        self.tx_topology = np.ascontiguousarray(self.tx_topology, dtype=np.float64)
+        self.rx_topology = np.ascontiguousarray(self.rx_topology, dtype=np.float64)
+        if self.max_speed is None:
+            self.max_speed = float(np.linalg.norm(self.rel_velocity, axis=-1).max()) if self.rel_velocity.size else 0.0
+
+    @property
+    def batch(self) -> int:
+        return int(self.angles.shape[0])
+
+    @property
+    def num_tx(self) -> int:
+        return int(self.tx_topology.shape[0])
+
+    @property
+    def num_rx(self) -> int:
+        return int(self.rx_topology.shape[0])
+
+    ARRAYS = ("angles", "jones", "amplitude", "tx_pose", "rx_pose", "rel_velocity", "tx_topology", "rx_topology")
+
+    @classmethod
+    def stack(cls, blocks) -> "CdlBlock":
+        b0 = blocks[0]
+        return cls(
+            term_delay=b0.term_delay, max_delay=b0.max_delay,
+            angles=np.concatenate([b.angles for b in blocks]), jones=np.concatenate([b.jones for b in blocks]),
+            amplitude=np.concatenate([b.amplitude for b in blocks]), tx_pose=np.concatenate([b.tx_pose for b in blocks]),
+            rx_pose=np.concatenate([b.rx_pose for b in blocks]),
+            rel_velocity=np.concatenate([b.rel_velocity for b in blocks]), tx_topology=b0.tx_topology,
+            rx_topology=b0.rx_topology, carrier_frequency=b0.carrier_frequency, sampling_rate=b0.sampling_rate,
+            line_of_sight=b0.line_of_sight, los_delay=b0.los_delay, los_amplitude=b0.los_amplitude,
+            max_speed=max(b.max_speed for b in blocks))
+
+    def group_key(self):
+        return (self.term_delay.tobytes(), self.max_delay, self.tx_topology.tobytes(), self.rx_topology.tobytes(),
+                self.carrier_frequency, self.sampling_rate, self.line_of_sight, self.los_delay, self.los_amplitude)
+
+
+def _cdl_problem(blk: CdlBlock, num_samples: int, precision, io128: bool, ptrs: dict):
+    from ._lib import CdlProblem
+
+    p = CdlProblem()
+    p.batch = blk.batch
+    p.num_tx = blk.num_tx
+    p.num_rx = blk.num_rx
+    p.num_samples = int(num_samples)
+    p.max_delay = int(blk.max_delay)
+    p.num_terms = int(blk.term_delay.shape[0])
+    p.line_of_sight = 1 if blk.line_of_sight else 0
+    p.los_delay = int(blk.los_delay)
+    p.precision = _PRECISION[precision]
+    p.io_complex128 = 1 if io128 else 0
+    p.carrier_frequency = float(blk.carrier_frequency)
+    p.sampling_rate = float(blk.sampling_rate)
+    p.los_amplitude = float(blk.los_amplitude)
+    p.max_speed = float(blk.max_speed)
+    p.term_delay = blk.term_delay.ctypes.data_as(C.POINTER(C.c_int32))
+    p.angles = ptrs["angles"]
+    p.jones = ptrs["jones"]
+    p.amplitude = ptrs["amplitude"]
+    p.tx_pose = ptrs["tx_pose"]
+    p.rx_pose = ptrs["rx_pose"]
+    p.rel_velocity = ptrs["rel_velocity"]
+    p.tx_topology = ptrs["tx_topology"]
+    p.rx_topology = ptrs["rx_topology"]
+    return p
+
+
+def cdl_plan(blk: CdlBlock, num_samples: int, precision="f32") -> dict:
+    lib = _lib.load()
+    p = _cdl_problem(blk, num_samples, precision, False, {k: None for k in CdlBlock.ARRAYS})
+    info = FadingPlanInfo()
+    _lib.check(lib.hb_cdl_plan(C.byref(p), C.byref(info)))
+    return _info_dict(info)
+
+
+def cdl_propagate_host(x: np.ndarray, blk: CdlBlock, precision="f32", out: Optional[np.ndarray] = None,
+                       chunk_links: int = 0, return_info=False):
+    """Host-buffer CDL propagation: ``x[B, Ntx, T]`` numpy complex64/128 -> ``y[B, Nrx, T + D]``.
+
+    GPU counterpart of ``ClusterDelayLineSample._propagate`` (cluster_delay_lines.py:526-558) for a batch.
+    """
+    lib = _lib.load()
+    x = np.ascontiguousarray(x)
+    if x.dtype not in (np.complex64, np.complex128):
+        raise ValueError("x must be complex64 or complex128")
+    if x.ndim != 3 or x.shape[0] != blk.batch:
+        raise ValueError("x must have shape [B, Ntx, T] with B matching the parameter block")
+    if x.shape[1] != blk.num_tx:
+        raise ValueError(
+            f"Number of signal streams to be propagated does not match the number of transmitter antennas ({x.shape[1]} != {blk.num_tx}))")
+    T = x.shape[2]
+    Tout = T + blk.max_delay
+    if out is None:
+        out = np.empty((blk.batch, blk.num_rx, Tout), dtype=x.dtype)
+    elif out.shape != (blk.batch, blk.num_rx, Tout) or out.dtype != x.dtype or not out.flags.c_contiguous:
+        raise ValueError("out has the wrong shape / dtype / layout")
+    p = _cdl_problem(blk, T, precision, x.dtype == np.complex128, {k: getattr(blk, k).ctypes.data for k in CdlBlock.ARRAYS})
+    info = FadingPlanInfo()
+    _lib.check(lib.hb_cdl_propagate_host(C.byref(p), x.ctypes.data, out.ctypes.data, int(chunk_links), C.byref(info)))
+    if return_info:
+        return out, _info_dict(info)
+    return out
+
+
+class CdlDeviceBlock(object):
+    """Device-resident copy of a :class:`CdlBlock` (torch tensors) for the device-pointer entry."""
+
+    def __init__(self, blk: CdlBlock, device="cuda") -> None:
+        torch = _torch()
+        self.host = blk
+        self.tensors = {k: torch.from_numpy(getattr(blk, k)).to(device) for k in CdlBlock.ARRAYS}
+        self.device = self.tensors["angles"].device
+
+
+def cdl_propagate(x, dblk: CdlDeviceBlock, precision="f32", out=None, return_info=False):
+    """Device-resident CDL propagation on torch's current stream (no synchronization)."""
+    torch = _torch()
+    lib = _lib.load()
+    blk = dblk.host
+    if not x.is_cuda:
+        raise _lib.HermesB200Error(_lib.HB_ERR_NO_DEVICE, "x must be a CUDA tensor (no CPU fallback)")
+    if x.dim() != 3 or x.shape[0] != blk.batch or x.shape[1] != blk.num_tx:
+        raise ValueError("x must have shape [B, Ntx, T] matching the parameter block")
+    x = x.contiguous()
+    T = int(x.shape[2])
+    Tout = T + blk.max_delay
+    if out is None:
+        out = torch.empty((blk.batch, blk.num_rx, Tout), dtype=x.dtype, device=x.device)
+    p = _cdl_problem(blk, T, precision, x.dtype == torch.complex128, {k: v.data_ptr() for k, v in dblk.tensors.items()})
+    info = FadingPlanInfo()
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(lib.hb_cdl_propagate(C.byref(p), x.data_ptr(), out.data_ptr(), C.c_void_p(stream), C.byref(info)))
+    if return_info:
+        return out, _info_dict(info)
+    return out
+
+
+def cdl_state(dblk: CdlDeviceBlock, num_samples: int, io128=True):
+    """Per-delay-group MIMO impulse responses ``h[B, G, Nrx, Ntx, T]`` and the G delay indices."""
+    torch = _torch()
+    lib = _lib.load()
+    blk = dblk.host
+    p = _cdl_problem(blk, num_samples, "f64", io128, {k: v.data_ptr() for k, v in dblk.tensors.items()})
+    G = C.c_int32(0)
+    gd = np.zeros(64, dtype=np.int32)
+    _lib.check(lib.hb_cdl_state(C.byref(p), None, gd.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(G), None))
+    G = int(G.value)
+    h = torch.empty((blk.batch, G, blk.num_rx, blk.num_tx, int(num_samples)),
+                    dtype=torch.complex128 if io128 else torch.complex64, device=dblk.device)
+    with torch.cuda.device(dblk.device):
+        stream = torch.cuda.current_stream(dblk.device).cuda_stream
+        _lib.check(lib.hb_cdl_state(C.byref(p), h.data_ptr(), gd.ctypes.data_as(C.POINTER(C.c_int32)), None,
+                                    C.c_void_p(stream)))
+    return h, gd[:G].copy()

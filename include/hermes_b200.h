@@ -48,6 +48,8 @@ extern "C" {
 #define HB_MAX_TAPS 256
 #define HB_MAX_POLY_ORDER 8
 #define HB_NUM_KERNEL_KINDS 9
+#define HB_CDL_MAX_TERMS 1024
+#define HB_CDL_MAX_GROUPS 64
 
 typedef enum hb_status {
   HB_OK = 0,
@@ -123,6 +125,62 @@ HB_API int hb_fading_propagate_host(const hb_fading_problem* p, const void* x, v
  * distinct integer delay, plus the delays themselves in group_delay_out (HOST int32[G], may be NULL).
  * CSI[b, i, j, n, group_delay[g]] = spatial[b, i, j] * h[b, g, n]   (fading.py:351-364). */
 HB_API int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_delay_out, void* stream);
+
+/* ---- 3GPP cluster delay line ------------------------------------------------------------------------------
+ * Batched replacement of ClusterDelayLineSample._propagate / .state and the per-ray array responses
+ * (hermespy/channel/cdl/cluster_delay_lines.py:409-592, hermespy/core/antennas.py:138-210, 883-1000) for arrays of
+ * identical ideal elements (SimulatedIdealAntenna on a uniform array, any device orientation).
+ *
+ * A "ray term" is one iteration of the reference's ray generator: (cluster sub-partition, ray) in generator order.
+ * Per term the host supplies the four ray angles, the 2x2 Jones matrix and the real amplitude
+ * sqrt(P_c / num_rays) * nlos_scale; the delay index int((tau + offset) * fs) is launch-uniform.  The optional
+ * line-of-sight term (cluster_delay_lines.py:498-523) is synthesized by the library from the device poses.
+ */
+typedef struct hb_cdl_problem {
+  int32_t batch;            /* B links                                                              */
+  int32_t num_tx, num_rx;   /* antenna counts                                                       */
+  int32_t num_samples;      /* T                                                                    */
+  int32_t max_delay;        /* D = ceil(max_delay * fs) (cluster_delay_lines.py:528)                */
+  int32_t num_terms;        /* Rn <= HB_CDL_MAX_TERMS - 1: non-line-of-sight ray terms per link     */
+  int32_t line_of_sight;    /* 1: add the LOS term                                                  */
+  int32_t los_delay;        /* delay index of the LOS term: int((cluster_delays[0] + offset) * fs)  */
+  int32_t precision;        /* hb_precision                                                         */
+  int32_t io_complex128;    /* element type of x / y                                                */
+  double carrier_frequency; /* Hz                                                                   */
+  double sampling_rate;     /* Hz (LinkState.bandwidth)                                             */
+  double los_amplitude;     /* sqrt(K / (1 + K)), K linear (cluster_delay_lines.py:516)             */
+  double max_speed;         /* bound on |v_rx - v_tx| over the batch in m/s (0 = static links)      */
+  const int32_t* term_delay;   /* HOST int32[Rn] delay index per term                               */
+  const double* angles;        /* DEVICE f64 [B, Rn, 4]: aoa, zoa, aod, zod (radians)               */
+  const void* jones;           /* DEVICE complex128 [B, Rn, 2, 2]                                   */
+  const double* amplitude;     /* DEVICE f64 [B, Rn]                                                */
+  const double* tx_pose;       /* DEVICE f64 [B, 12]: rotation (row-major 3x3, array -> global), translation */
+  const double* rx_pose;       /* DEVICE f64 [B, 12]                                                */
+  const double* rel_velocity;  /* DEVICE f64 [B, 3]: v_rx - v_tx (global frame)                     */
+  const double* tx_topology;   /* DEVICE f64 [Ntx, 3] element positions in the array frame          */
+  const double* rx_topology;   /* DEVICE f64 [Nrx, 3]                                               */
+} hb_cdl_problem;
+
+typedef struct hb_cdl_plan_info {
+  int32_t mode;        /* HB_SOS_POLY (grouped moment path) or HB_SOS_DIRECT (per-ray FP64 path) */
+  int32_t tile;
+  int32_t poly_order;
+  int32_t num_groups;
+  int32_t num_tiles;
+  int32_t launches;
+  double error_bound;
+} hb_cdl_plan_info;
+
+HB_API int hb_cdl_plan(const hb_cdl_problem* p, hb_cdl_plan_info* info);
+/* Device-resident: x [B, Ntx, T] -> y [B, Nrx, T + D]; enqueued on `stream`, no synchronization. */
+HB_API int hb_cdl_propagate(const hb_cdl_problem* p, const void* x, void* y, void* stream, hb_cdl_plan_info* info);
+/* Host buffers for every pointer (chunked H2D / kernels / D2H pipeline). */
+HB_API int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32_t chunk_links,
+                                 hb_cdl_plan_info* info);
+/* Channel state per delay group: h [B, G, Nrx, Ntx, T] complex (io_complex128), FP64 evaluation;
+ * group_delay_out: HOST int32[G] (may be NULL); returns G through num_groups_out. */
+HB_API int hb_cdl_state(const hb_cdl_problem* p, void* h, int32_t* group_delay_out, int32_t* num_groups_out,
+                        void* stream);
 
 /* Per-kernel accounting.  Kinds: 0 sos_poly_coef, 1 tdl_poly, 2 tdl_direct, 3 sos_state, 4 cdl_rays,
  * 5 cdl_propagate, 6 spatial_gemm, 7 stats, 8 misc.

@@ -48,3 +48,27 @@ SAMPLE_FIELDS = ("power_profile delay_profile los_angles nlos_angles los_phases 
 def golden_signal(case_index: int, num_streams: int, num_samples: int) -> np.ndarray:
     rng = np.random.default_rng(1000 + case_index)
     return (rng.standard_normal((num_streams, num_samples)) + 1j * rng.standard_normal((num_streams, num_samples))) / np.sqrt(2)
+
+
+# ---- cluster delay line ------------------------------------------------------------------------------------
+# (name, channel builder, tx spec, rx spec, T); device spec = (array dims, roll-pitch-yaw, position, velocity)
+CDL_FS = 30.72e6
+CDL_FC = 3.5e9
+CDL_SPACING = 0.5 * 299792458.0 / CDL_FC
+
+CDL_CASES = [
+    ("cdl_c_8x2_moving_c3", lambda M: M.CDL(M.CDLType.C, 300e-9, seed=42),
+     ((4, 2, 1), (0, 0, 0), (0.0, 0.0, 10.0), (0, 0, 0)), ((2, 1, 1), (0, 0, 0), (100.0, 20.0, 1.5), (10.0, -3.0, 0.0)), 200),
+    ("cdl_a_4x4_rotated", lambda M: M.CDL(M.CDLType.A, 300e-9, seed=43),
+     ((2, 2, 1), (0.1, 0.2, 0.3), (0.0, 0.0, 10.0), (1.0, 2.0, 0.5)),
+     ((2, 2, 1), (-0.4, 0.1, 2.0), (100.0, 20.0, 1.5), (10.0, -3.0, 0.0)), 128),
+    ("cdl_d_los_4x2", lambda M: M.CDL(M.CDLType.D, 300e-9, rayleigh_factor=9.0, seed=44),
+     ((2, 1, 2), (0.1, 0.2, 0.3), (0.0, 0.0, 10.0), (0, 0, 0)), ((1, 2, 1), (0, 0, 0), (100.0, 20.0, 1.5), (10.0, -3.0, 0.0)), 100),
+    ("cdl_e_los_siso_static", lambda M: M.CDL(M.CDLType.E, 1e-7, rayleigh_factor=3.0, seed=45),
+     ((1, 1, 1), (0, 0, 0), (0.0, 0.0, 10.0), (0, 0, 0)), ((1, 1, 1), (0, 0, 0), (30.0, -20.0, 1.5), (0, 0, 0)), 64),
+    ("cdl_b_2x2_fast", lambda M: M.CDL(M.CDLType.B, 1e-6, seed=46),
+     ((2, 1, 1), (0, 0, 0), (0.0, 0.0, 10.0), (0, 0, 0)), ((2, 1, 1), (0, 0, 0), (30.0, -20.0, 1.5), (30.0, 0.0, 0.0)), 64),
+]
+
+CDL_SAMPLE_FIELDS = ("azimuth_of_arrival zenith_of_arrival azimuth_of_departure zenith_of_departure cluster_delays "
+                     "cluster_powers polarization_transformations").split()

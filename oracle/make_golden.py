@@ -58,3 +58,43 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def cdl_main():
+    from oracle.golden_cases import CDL_CASES, CDL_FC, CDL_FS, CDL_SAMPLE_FIELDS, CDL_SPACING
+
+    def dev(spec):
+        dims, rpy, pos, vel = spec
+        return SimulatedDevice(bandwidth=CDL_FS, oversampling_factor=1, carrier_frequency=CDL_FC,
+                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, CDL_SPACING, dims),
+                               pose=Transformation.From_RPY(np.array(rpy, float), np.array(pos, float)),
+                               velocity=np.array(vel, float))
+
+    out = {}
+    for ci, (name, build, txs, rxs, T) in enumerate(CDL_CASES):
+        ch = build(RC)
+        tx, rx = dev(txs), dev(rxs)
+        ch.realize()
+        real = ch.realize()
+        s = real.sample(tx, rx)
+        for f in CDL_SAMPLE_FIELDS:
+            out[f"{name}/{f}"] = np.asarray(getattr(s, f))
+        out[f"{name}/scalars"] = np.array([float(s.line_of_sight), s.rice_factor, s.delay_offset, s.cluster_delay_spread,
+                                           s.max_delay, s.expected_energy_scale])
+        ntx, nrx = int(np.prod(txs[0])), int(np.prod(rxs[0]))
+        x = golden_signal(200 + ci, ntx, T)
+        y = s.propagate(Signal.Create(x, CDL_FS, CDL_FC)).view(np.ndarray)
+        out[f"{name}/y"] = np.asarray(y)
+        sr = real.reciprocal_sample(s, rx, tx)
+        out[f"{name}/y_reciprocal"] = np.asarray(
+            sr.propagate(Signal.Create(golden_signal(300 + ci, nrx, T), CDL_FS, CDL_FC)).view(np.ndarray))
+        if T <= 100:
+            out[f"{name}/csi"] = np.asarray(s.state(T, 1000).dense_state()).astype(np.complex128)
+        print(f"{name}: y {y.shape}")
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cdl_golden.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    cdl_main()

@@ -31,3 +31,31 @@ def static_normals_of(realization) -> np.ndarray:
     """Private normals of a static fading realization (name-mangled)."""
     rr = realization._MultipathFadingRealization__random_realization
     return np.array(rr._StaticConsistentRealization__scalar_samples, dtype=np.float64)
+
+
+def array_geometry_from_reference(antennas_state, velocity, mode):
+    """``ArrayGeometry`` of a reference ``AntennaArrayState`` (pose = local -> global homogeneous matrix)."""
+    from .cdl_oracle import ArrayGeometry
+
+    fwd = np.asarray(antennas_state.forwards_transformation, dtype=np.float64)
+    return ArrayGeometry(rotation=fwd[:3, :3].copy(), translation=fwd[:3, 3].copy(),
+                         topology=np.asarray(antennas_state._topology(mode), dtype=np.float64).copy(),
+                         velocity=np.asarray(velocity, dtype=np.float64).copy())
+
+
+def cdl_params_from_reference_sample(sample):
+    """Read a reference ``ClusterDelayLineSample`` through its public properties (cluster_delay_lines.py:321-403)."""
+    from hermespy.core import AntennaMode
+
+    from .cdl_oracle import CdlParams
+
+    return CdlParams(
+        line_of_sight=bool(sample.line_of_sight), rice_factor_db=float(sample.rice_factor),
+        aoa=np.array(sample.azimuth_of_arrival), zoa=np.array(sample.zenith_of_arrival),
+        aod=np.array(sample.azimuth_of_departure), zod=np.array(sample.zenith_of_departure),
+        delay_offset=float(sample.delay_offset), cluster_delays=np.array(sample.cluster_delays, dtype=np.float64),
+        cluster_delay_spread=float(sample.cluster_delay_spread), cluster_powers=np.array(sample.cluster_powers),
+        jones=np.array(sample.polarization_transformations),
+        tx=array_geometry_from_reference(sample.transmitter_antennas, sample.transmitter_velocity, AntennaMode.TX),
+        rx=array_geometry_from_reference(sample.receiver_antennas, sample.receiver_velocity, AntennaMode.RX),
+        fc=float(sample.carrier_frequency), fs=float(sample.bandwidth))
