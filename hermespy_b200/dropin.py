@@ -1,0 +1,179 @@
+"""Drop-in adapter: route an installed, UNMODIFIED HermesPy's channel hot path through the B200 kernels.
+
+    import hermespy_b200.dropin as dropin
+    dropin.enable()            # raises unless libhermes_b200.so is built and a CUDA device is visible
+    ... run any Simulation script ...
+    dropin.disable()
+
+``enable()`` rebinds four methods of the reference -- nothing else is touched:
+
+* ``hermespy.channel.fading.fading.MultipathFadingSample._propagate`` (fading.py:371-406) and ``.state`` (:345-369)
+* ``hermespy.channel.cdl.cluster_delay_lines.ClusterDelayLineSample._propagate`` (cluster_delay_lines.py:526-558)
+
+The replacements read the reference sample through its public properties (fading.py:217-287,
+cluster_delay_lines.py:321-403), lay out the same kernel parameter blocks the mirror classes of this package
+use, and call the host-buffer C-ABI (``hb_fading_propagate_host`` / ``hb_cdl_propagate_host``).  Realization,
+sampling, hooks, Signal bookkeeping, serialization and the whole drop loop remain the reference's own code.
+The functions are module-level (picklable), so Ray actors that import this module inherit the patch.
+"""
+from __future__ import annotations
+
+from math import ceil
+
+import numpy as np
+
+from . import config
+
+_ORIGINALS = {}
+
+
+# ---- parameter extraction from reference objects (pure host code, testable without a GPU) --------------------
+
+def fading_block_from_reference(sample) -> dict:
+    """Kernel parameter block of a reference ``MultipathFadingSample`` (same layout as the mirror class)."""
+    from .kernels import fading_param_block
+
+    fs = sample.bandwidth
+    omega, phi, amp = fading_param_block(sample.power_profile, sample.delay_profile, sample.los_gains,
+                                         sample.nlos_gains, sample.los_angles, sample.nlos_angles, sample.los_phases,
+                                         sample.nlos_phases, sample.los_doppler, sample.nlos_doppler, sample.gain, fs)
+    spatial = np.ascontiguousarray(
+        np.asarray(sample.spatial_response)[: sample.num_receive_antennas, : sample.num_transmit_antennas],
+        dtype=np.complex128)
+    return dict(tap_delay=np.rint(np.asarray(sample.delay_profile) * fs).astype(np.int32),
+                max_delay=int(round(float(np.max(sample.delay_profile)) * fs)), omega=omega, phi=phi, amp=amp,
+                spatial=spatial, omega_max=float(max(abs(sample.los_doppler), abs(sample.nlos_doppler)) / fs))
+
+
+def _ideal_uniform(antennas_state) -> bool:
+    try:
+        from hermespy.core.antennas import IdealAntenna  # type: ignore
+
+        return all(isinstance(a, IdealAntenna) for a in antennas_state.antennas)
+    except Exception:
+        return False
+
+
+def cdl_block_from_reference(sample):
+    """``kernels.CdlBlock`` (B = 1) of a reference ``ClusterDelayLineSample``.
+
+    Raises ``NotImplementedError`` for antenna elements other than ideal isotropic ones (the CUDA ray kernel
+    implements the ideal element's polarization model, core/antennas.py:138-210 with a constant local pattern).
+    """
+    from hermespy.core import AntennaMode  # type: ignore
+
+    from .channel.cdl.cdl import SUBCLUSTER_INDICES
+    from .kernels import CdlBlock
+
+    tx_a, rx_a = sample.transmitter_antennas, sample.receiver_antennas
+    if not (_ideal_uniform(tx_a) and _ideal_uniform(rx_a)):
+        raise NotImplementedError("hermespy_b200 CDL kernels support ideal isotropic antenna elements only")
+    fs = sample.bandwidth
+    C_, R_ = sample.num_clusters, sample.num_rays
+    nsplit = min(2, C_)
+    nvirtual = 3 * nsplit + max(0, C_ - 2)
+    sub = (np.repeat(np.asarray(sample.cluster_delays)[:nsplit, None], 3, axis=1)
+           + sample.cluster_delay_spread * np.array([0.0, 1.28, 2.56]))
+    vdelays = np.concatenate((sub.flatten(), np.asarray(sample.cluster_delays)[nsplit:]))
+    cs, rs, ds = [], [], []
+    for v in range(nvirtual):
+        c = int(v / 3) if v < 6 else v - 4
+        for r in (SUBCLUSTER_INDICES[c] if c < nsplit else range(R_)):
+            cs.append(c)
+            rs.append(r)
+            ds.append(vdelays[v])
+    c, r = np.array(cs), np.array(rs)
+    rice_lin = 10.0 ** (sample.rice_factor / 10.0)
+    nlos_scale = (1.0 + rice_lin) ** -0.5 if sample.line_of_sight else 1.0
+
+    def pose12(antennas_state):
+        m = np.asarray(antennas_state.forwards_transformation, dtype=np.float64)
+        return np.concatenate([m[:3, :3].ravel(), m[:3, 3]])[None]
+
+    return CdlBlock(
+        term_delay=np.array([int((d + sample.delay_offset) * fs) for d in ds], dtype=np.int32),
+        max_delay=ceil(sample.max_delay * fs),
+        angles=np.stack([sample.azimuth_of_arrival[c, r], sample.zenith_of_arrival[c, r],
+                         sample.azimuth_of_departure[c, r], sample.zenith_of_departure[c, r]], axis=1)[None],
+        jones=np.ascontiguousarray(np.asarray(sample.polarization_transformations)[:, :, c, r].transpose(2, 0, 1))[None],
+        amplitude=(np.sqrt(np.asarray(sample.cluster_powers)[c] / R_) * nlos_scale)[None],
+        tx_pose=pose12(tx_a), rx_pose=pose12(rx_a),
+        rel_velocity=(np.asarray(sample.receiver_velocity, float) - np.asarray(sample.transmitter_velocity, float))[None],
+        tx_topology=np.asarray(tx_a._topology(AntennaMode.TX), dtype=np.float64),
+        rx_topology=np.asarray(rx_a._topology(AntennaMode.RX), dtype=np.float64),
+        carrier_frequency=sample.carrier_frequency, sampling_rate=fs, line_of_sight=bool(sample.line_of_sight),
+        los_delay=int((sample.cluster_delays[0] + sample.delay_offset) * fs),
+        los_amplitude=float((rice_lin / (1 + rice_lin)) ** 0.5))
+
+
+# ---- replacement methods (module level => picklable) ------------------------------------------------------------
+
+def _fading_propagate(self, signal, interpolation):
+    from hermespy.core.signal_model import SignalBlock  # type: ignore
+
+    from .kernels import fading_propagate_host
+
+    b = fading_block_from_reference(self)
+    T = signal.num_samples
+    nrx = b["spatial"].shape[0]
+    if T + b["max_delay"] <= 0 or nrx == 0:
+        out = np.zeros((nrx, T + b["max_delay"]), dtype=np.complex128)
+    else:
+        x = np.ascontiguousarray(np.asarray(signal, dtype=np.complex128))[None]
+        out = fading_propagate_host(x, b["tap_delay"], b["max_delay"], b["omega"][None], b["phi"][None], b["amp"][None],
+                                    b["spatial"][None], omega_max=b["omega_max"], precision=config.precision,
+                                    sos_mode=config.sos_mode)[0]
+    return SignalBlock(out.shape[0], out.shape[1], signal.offset, out.tobytes())
+
+
+def _cdl_propagate(self, signal, interpolation):
+    from hermespy.core import InterpolationMode  # type: ignore
+    from hermespy.core.signal_model import SignalBlock  # type: ignore
+
+    from .kernels import cdl_propagate_host
+
+    try:
+        blk = cdl_block_from_reference(self)
+    except NotImplementedError:
+        return _ORIGINALS["cdl_propagate"](self, signal, interpolation)  # non-ideal elements: reference code
+    if interpolation != InterpolationMode.NEAREST:
+        out = np.zeros((self.num_receive_antennas, signal.num_samples + blk.max_delay), dtype=np.complex128)
+    else:
+        x = np.ascontiguousarray(np.asarray(signal, dtype=np.complex128))[None]
+        out = cdl_propagate_host(x, blk, precision=config.precision)[0]
+    return SignalBlock(out.shape[0], out.shape[1], signal._offset, out.tobytes())
+
+
+def enable(precision: str = "f32") -> None:
+    """Patch the reference classes.  Fails loudly when the library or a CUDA device is missing."""
+    from . import _lib
+
+    if _lib.device_count() < 1:
+        raise _lib.HermesB200Error(_lib.HB_ERR_NO_DEVICE, "no CUDA device visible; hermespy_b200 has no CPU fallback")
+    if precision not in ("f32", "f64"):
+        raise ValueError("precision must be 'f32' or 'f64'")
+    config.precision = precision
+    patch_reference()
+
+
+def patch_reference() -> None:
+    """Rebind the reference methods (split from ``enable`` so host-side tests can patch without a GPU)."""
+    from hermespy.channel.cdl.cluster_delay_lines import ClusterDelayLineSample  # type: ignore
+    from hermespy.channel.fading.fading import MultipathFadingSample  # type: ignore
+
+    if not _ORIGINALS:
+        _ORIGINALS["fading_propagate"] = MultipathFadingSample._propagate
+        _ORIGINALS["cdl_propagate"] = ClusterDelayLineSample._propagate
+    MultipathFadingSample._propagate = _fading_propagate
+    ClusterDelayLineSample._propagate = _cdl_propagate
+
+
+def disable() -> None:
+    if not _ORIGINALS:
+        return
+    from hermespy.channel.cdl.cluster_delay_lines import ClusterDelayLineSample  # type: ignore
+    from hermespy.channel.fading.fading import MultipathFadingSample  # type: ignore
+
+    MultipathFadingSample._propagate = _ORIGINALS["fading_propagate"]
+    ClusterDelayLineSample._propagate = _ORIGINALS["cdl_propagate"]
+    _ORIGINALS.clear()

@@ -73,3 +73,90 @@ def test_golden_file_is_current(ref):
         s = ch.realize().sample(tx, rx)
         y = s.propagate(ref["Signal"].Create(golden_signal(ci, ntx, T), fs, 3.5e9)).view(np.ndarray)
         assert np.array_equal(np.asarray(y), g[f"{name}/y"])
+
+
+def test_cdl_oracle_matches_live_reference(ref):
+    from hermespy.core import Transformation
+    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+
+    from oracle import cdl_oracle as co
+    from oracle.golden_cases import CDL_FC, CDL_FS, CDL_SPACING
+    from oracle.ref_extract import cdl_params_from_reference_sample
+
+    RC = ref["RC"]
+    rng = np.random.default_rng(5)
+
+    def dev(dims, rpy, pos, vel):
+        return SimulatedDevice(bandwidth=CDL_FS, oversampling_factor=1, carrier_frequency=CDL_FC,
+                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, CDL_SPACING, dims),
+                               pose=Transformation.From_RPY(np.array(rpy, float), np.array(pos, float)),
+                               velocity=np.array(vel, float))
+
+    for t, K in ((RC.CDLType.B, 0.0), (RC.CDLType.D, 7.0)):
+        tx = dev((2, 2, 1), rng.uniform(-1, 1, 3), (0, 0, 20.0), (0, 0, 0))
+        rx = dev((2, 1, 1), rng.uniform(-1, 1, 3), (60.0, -30.0, 1.5), rng.uniform(-20, 20, 3))
+        s = RC.CDL(t, 200e-9, rayleigh_factor=K, seed=int(rng.integers(1 << 30))).realize().sample(tx, rx)
+        x = (rng.standard_normal((4, 90)) + 1j * rng.standard_normal((4, 90))) / np.sqrt(2)
+        y = s.propagate(ref["Signal"].Create(x, CDL_FS, CDL_FC)).view(np.ndarray)
+        yo = co.propagate(cdl_params_from_reference_sample(s), x)
+        assert np.linalg.norm(yo - y) <= 5e-12 * np.linalg.norm(y)
+
+
+def test_dropin_extraction_equals_mirror_blocks(ref):
+    """The drop-in adapter reads reference samples into the same kernel blocks the mirror classes build."""
+    import hermespy_b200.channel as MC
+    from hermespy.core import Transformation
+    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+    from hermespy_b200 import dropin
+    from oracle.golden_cases import CDL_CASES, CDL_FC, CDL_FS, CDL_SPACING, FADING_CASES
+    from tests.test_cdl_golden import mirror_cdl_sample
+    from tests.test_oracle_golden import mirror_sample
+
+    RC = ref["RC"]
+    for case in FADING_CASES[:6]:
+        name, build, ntx, nrx, fs, T, ptx, prx = case
+        ch = build(RC)
+        tx, rx = ref["device"](ntx, fs, ptx), ref["device"](nrx, fs, prx)
+        ch.realize()
+        rs = ch.realize().sample(tx, rx)
+        got = dropin.fading_block_from_reference(rs)
+        want = mirror_sample(case)[1].kernel_block()
+        for k in ("tap_delay", "omega", "phi", "amp", "spatial"):
+            assert np.array_equal(got[k], want[k]), (name, k)
+        assert got["max_delay"] == want["max_delay"] and got["omega_max"] == want["omega_max"]
+
+    def dev(spec):
+        dims, rpy, pos, vel = spec
+        return SimulatedDevice(bandwidth=CDL_FS, oversampling_factor=1, carrier_frequency=CDL_FC,
+                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, CDL_SPACING, dims),
+                               pose=Transformation.From_RPY(np.array(rpy, float), np.array(pos, float)),
+                               velocity=np.array(vel, float))
+
+    for case in CDL_CASES:
+        name, build, txs, rxs, T = case
+        ch = build(RC)
+        ch.realize()
+        rs = ch.realize().sample(dev(txs), dev(rxs))
+        got = dropin.cdl_block_from_reference(rs)
+        want = mirror_cdl_sample(case)[1].kernel_block()
+        assert np.array_equal(got.term_delay, want.term_delay) and got.max_delay == want.max_delay
+        for k in ("angles", "jones", "amplitude", "rel_velocity"):
+            assert np.array_equal(getattr(got, k), getattr(want, k)), (name, k)
+        for k in ("tx_pose", "rx_pose", "tx_topology", "rx_topology"):
+            assert np.allclose(getattr(got, k), getattr(want, k), rtol=0, atol=1e-12), (name, k)
+        assert (got.line_of_sight, got.los_delay, got.los_amplitude) == (want.line_of_sight, want.los_delay, want.los_amplitude)
+
+
+def test_dropin_patch_and_restore(ref):
+    from hermespy.channel.cdl.cluster_delay_lines import ClusterDelayLineSample
+    from hermespy.channel.fading.fading import MultipathFadingSample
+    from hermespy_b200 import dropin
+
+    orig_f, orig_c = MultipathFadingSample._propagate, ClusterDelayLineSample._propagate
+    dropin.patch_reference()
+    try:
+        assert MultipathFadingSample._propagate is dropin._fading_propagate
+        assert ClusterDelayLineSample._propagate is dropin._cdl_propagate
+    finally:
+        dropin.disable()
+    assert MultipathFadingSample._propagate is orig_f and ClusterDelayLineSample._propagate is orig_c
