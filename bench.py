@@ -225,11 +225,11 @@ def run_ours(args):
     stats = torch.zeros(4, dtype=torch.float64, device=dev)  # stand-in for evaluator statistics (sum, sum^2, count, bits)
 
     def step():
-        fading_propagate(x, fb, precision="f32", sos_mode="auto", out=y)
+        fading_propagate(x, fb, precision="f32", sos_mode=args.sos_mode, out=y)
         if world > 1:
             dist.all_reduce(stats)  # the only collective of the path: evaluator statistics
 
-    _, info = fading_propagate(x, fb, out=y, return_info=True)
+    _, info = fading_propagate(x, fb, out=y, sos_mode=args.sos_mode, return_info=True)
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
@@ -273,6 +273,8 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer C-ABI (complex128 host buffers, as the reference's SignalBlock) ----
     Be = min(B, args.e2e_links)
+    if args.no_e2e:  # profiling runs only (tools/ncu_one.sh); such a line is not a bench result
+        Be = 1
     xh = torch.empty((Be, ntx, T), dtype=torch.complex128).pin_memory()
     xh.copy_(x[:Be].to(torch.complex128).cpu())
     yh = torch.empty((Be, nrx, T + D), dtype=torch.complex128).pin_memory()
@@ -333,6 +335,9 @@ def main():
     ap.add_argument("--links", type=int, default=2048, help="links per step per GPU")
     ap.add_argument("--e2e-links", type=int, default=512, help="links per end-to-end step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: shrink the end-to-end leg to one link")
+    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_gather", "direct"],
+                    help="kernel selection (profiling / A-B runs); the default lets the planner choose")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

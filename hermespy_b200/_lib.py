@@ -22,6 +22,10 @@ HB_F64 = 1
 HB_SOS_AUTO = 0
 HB_SOS_POLY = 1
 HB_SOS_DIRECT = 2
+HB_SOS_POLY_GATHER = 3
+
+HB_VARIANT_GATHER = 0
+HB_VARIANT_WINDOW = 1
 
 HB_MAX_TAPS = 256
 
@@ -68,6 +72,8 @@ class FadingPlanInfo(C.Structure):
         ("num_tiles", C.c_int32),
         ("launches", C.c_int32),
         ("error_bound", C.c_double),
+        ("variant", C.c_int32),
+        ("poly_tile", C.c_int32),
     ]
 
     def as_dict(self) -> dict:

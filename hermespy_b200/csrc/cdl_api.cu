@@ -135,6 +135,8 @@ static void fill_cdl_info(const CdlPlan& pl, const CdlTable& tb, const hb_cdl_pr
   info->num_tiles = pl.ntiles;
   info->launches = pl.mode == HB_SOS_POLY ? 2 + (p->num_rx + pl.nrx_tpl - 1) / pl.nrx_tpl : 2;
   info->error_bound = pl.bound;
+  info->variant = 0;
+  info->poly_tile = pl.tile;
 }
 
 template <int P>

@@ -6,7 +6,7 @@
 #include <mutex>
 #include <vector>
 
-#include "fading_kernels.cuh"
+#include "fading_window.cuh"
 
 namespace hb {
 
@@ -34,7 +34,7 @@ static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
     set_error("unknown precision %d", p->precision);
     return HB_ERR_INVALID;
   }
-  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_DIRECT) {
+  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_GATHER) {
     set_error("unknown sos_mode %d", p->sos_mode);
     return HB_ERR_INVALID;
   }
@@ -67,8 +67,10 @@ static int pick_ntx_template(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 
 
 struct Plan {
   int mode, tile, P, ntiles, Dpad, ntx_tpl, taps_per_chunk;
+  int variant, poly_tile, npoly, threads;  // POLY: kernel variant, Taylor window, windows per link, CTA size
   size_t smem;
   double bound;
+  WindowPlan wp;
 };
 
 constexpr size_t kSmemSoftLimit = 72 * 1024;   // keeps >= 3 CTAs per SM
@@ -87,6 +89,48 @@ static size_t poly_smem(int ntx_tpl, int tile, int Dpad, int G, int P, int nrx) 
   return sizeof(float2) * ((size_t)ntx_tpl * (tile + Dpad) + (size_t)G * P + (size_t)nrx * ntx_tpl);
 }
 
+static int window_R(int ntx_tpl) { return ntx_tpl <= 4 ? 8 : 4; }
+
+// Sliding-window variant: eligible when the delay walk fits the masks and reads no more shared memory than the
+// gather kernel would ((dmax + R) / R loads per output and antenna against G).
+static bool window_eligible(const DelayTable& dt, int ntx_tpl) {
+  const int R = window_R(ntx_tpl);
+  const int dmax = dt.group_delay[dt.num_groups - 1];
+  return dmax <= kWindowMaxDelay && dmax + R <= dt.num_groups * R;
+}
+
+// Fill pl->wp / tile / threads / smem for the window kernel given pl->poly_tile and pl->P.
+static void plan_window(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
+  const int R = window_R(pl->ntx_tpl);
+  const int Tout = p->num_samples + p->max_delay;
+  WindowPlan& wp = pl->wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.num_groups = dt.num_groups;
+  wp.dmax = dt.group_delay[dt.num_groups - 1];
+  wp.nblk = wp.dmax / R + 1;
+  for (int g = 0; g < dt.num_groups; ++g) {
+    const int d = dt.group_delay[g];
+    wp.present[d >> 5] |= 1u << (d & 31);
+    for (int e = std::max(0, d - R + 1); e <= d; ++e) wp.load[e >> 5] |= 1u << (e & 31);
+  }
+  // CTA tile: the largest of {128, 64, 32} threads x R outputs that divides the Taylor window and is not
+  // (much) longer than the frame
+  int threads = 128;
+  while (threads > 32 && (pl->poly_tile % (threads * R) != 0 || (threads / 2) * R >= Tout)) threads /= 2;
+  pl->threads = threads;
+  pl->tile = threads * R;
+  int PL = threads + wp.nblk;
+  const int want = (16 / R) % 16;  // pitch = 16/R (mod 16): conflict-free polyphase staging writes
+  while (PL % 16 != want) ++PL;
+  wp.plane = PL;
+  wp.poly_tile = pl->poly_tile;
+  pl->npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
+  wp.npoly = pl->npoly;
+  pl->smem = sizeof(float2) * ((size_t)pl->ntx_tpl * R * PL + (size_t)dt.num_groups * pl->P +
+                               (size_t)p->num_rx * pl->ntx_tpl);
+  pl->Dpad = R * wp.nblk;
+}
+
 static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
   const int Tout = p->num_samples + p->max_delay;
   const int K = p->num_sinusoids + 1;
@@ -97,7 +141,12 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
   const int tile_cap = std::max(kThreads, ((Tout + kThreads - 1) / kThreads) * kThreads);
 
   bool poly = !f64 && p->sos_mode != HB_SOS_DIRECT;
-  if (f64 && p->sos_mode == HB_SOS_POLY) {
+  pl->variant = HB_VARIANT_GATHER;
+  pl->poly_tile = 0;
+  pl->npoly = 0;
+  pl->threads = kThreads;
+  const bool window = poly && p->sos_mode != HB_SOS_POLY_GATHER && window_eligible(dt, pl->ntx_tpl);
+  if (f64 && (p->sos_mode == HB_SOS_POLY || p->sos_mode == HB_SOS_POLY_GATHER)) {
     set_error("HB_F64 parity mode only supports direct evaluation");
     return HB_ERR_UNSUPPORTED;
   }
@@ -110,7 +159,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
     for (int P : kOrders) {
       for (int tile0 : kTiles) {
         const int tile = std::min(tile0, tile_cap);
-        if (poly_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx) > kSmemSoftLimit &&
+        if (!window && poly_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx) > kSmemSoftLimit &&
             tile > kThreads)
           continue;
         const double bnd = poly_bound(0.5 * p->omega_max * tile, P, K);
@@ -126,7 +175,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
       }
     }
     if (best_P == 0) {
-      if (p->sos_mode == HB_SOS_POLY) {
+      if (p->sos_mode == HB_SOS_POLY || p->sos_mode == HB_SOS_POLY_GATHER) {
         set_error("HB_SOS_POLY requested but omega_max=%g rad/sample cannot meet the %g bound", p->omega_max,
                   kPolyTarget);
         return HB_ERR_UNSUPPORTED;
@@ -137,8 +186,14 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
       pl->P = best_P;
       pl->tile = best_tile;
       pl->bound = best_bound;
+      pl->poly_tile = best_tile;
+      pl->npoly = std::max(1, (Tout + best_tile - 1) / best_tile);
       pl->smem = poly_smem(pl->ntx_tpl, pl->tile, pl->Dpad, dt.num_groups, pl->P, p->num_rx);
       pl->taps_per_chunk = 0;
+      if (window) {
+        pl->variant = HB_VARIANT_WINDOW;
+        plan_window(p, dt, pl);
+      }
     }
   }
   if (!poly) {
@@ -155,7 +210,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
                (size_t)tpc * K * spsz + (size_t)tpc * 2 * rsz;
   }
   // Very long delay spreads: shrink the antenna chunk before giving up.
-  while (pl->smem > kSmemHardLimit && pl->ntx_tpl > 1) {
+  while (pl->smem > kSmemHardLimit && pl->ntx_tpl > 1 && pl->variant != HB_VARIANT_WINDOW) {
     const int old = pl->ntx_tpl;
     pl->ntx_tpl = old / 2;
     const size_t per_ant = (f64 && pl->mode == HB_SOS_DIRECT ? sizeof(double2) : sizeof(float2)) *
@@ -182,6 +237,8 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
   info->num_tiles = pl.ntiles;
   info->launches = (pl.mode == HB_SOS_POLY ? 1 : 0) + chunks;
   info->error_bound = pl.bound;
+  info->variant = pl.mode == HB_SOS_POLY ? pl.variant : 0;
+  info->poly_tile = pl.mode == HB_SOS_POLY ? pl.poly_tile : pl.tile;
 }
 
 template <int P>
@@ -208,6 +265,14 @@ static int launch_coef_any(int P, const FadingArgs& a, const DelayTable& dt, cud
 static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& a, const DelayTable& dt,
                         cudaStream_t st) {
   ProfileScope prof(pl.mode == HB_SOS_POLY ? KIND_TDL_POLY : KIND_TDL_DIRECT, st);
+  if (pl.mode == HB_SOS_POLY && pl.variant == HB_VARIANT_WINDOW) {
+    switch (pl.ntx_tpl) {
+      case 1: return launch_tdl_window<1>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
+      case 2: return launch_tdl_window<2>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
+      case 4: return launch_tdl_window<4>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
+      default: return launch_tdl_window<8>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
+    }
+  }
   if (pl.mode == HB_SOS_POLY) {
     switch (pl.ntx_tpl) {
       case 1: return launch_tdl_poly<1>(pl.P, io128, a, dt, pl.smem, st);
@@ -253,10 +318,13 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   }
   float2* coef = nullptr;
   if (pl.mode == HB_SOS_POLY) {
-    const size_t bytes = sizeof(float2) * (size_t)a.B * a.ntiles * dt.num_groups * pl.P;
+    const size_t bytes = sizeof(float2) * (size_t)a.B * pl.npoly * dt.num_groups * pl.P;
     HB_CUDA(cudaMallocAsync((void**)&coef, bytes, st));
     a.coef = coef;
-    if (int e = launch_coef_any(pl.P, a, dt, st)) {
+    FadingArgs ac = a;  // K1 runs over the Taylor windows, which may span several CTA tiles
+    ac.tile = pl.poly_tile;
+    ac.ntiles = pl.npoly;
+    if (int e = launch_coef_any(pl.P, ac, dt, st)) {
       cudaFreeAsync(coef, st);
       return e;
     }

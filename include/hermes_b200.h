@@ -67,8 +67,14 @@ typedef enum hb_precision {
 typedef enum hb_sos_mode {
   HB_SOS_AUTO = 0,  /* pick POLY when the error bound allows it, else DIRECT */
   HB_SOS_POLY = 1,  /* per-tile Taylor moments of the sum of sinusoids (FMA pipe)  */
-  HB_SOS_DIRECT = 2 /* one sincos per sinusoid per sample (MUFU pipe)              */
+  HB_SOS_DIRECT = 2, /* one sincos per sinusoid per sample (MUFU pipe)             */
+  HB_SOS_POLY_GATHER = 3 /* POLY, forcing the per-group gather kernel (sparse / very long delay spreads) */
 } hb_sos_mode;
+
+typedef enum hb_poly_variant {
+  HB_VARIANT_GATHER = 0, /* tdl_poly_kernel: one shared-memory read per (delay group, antenna, output)  */
+  HB_VARIANT_WINDOW = 1  /* tdl_window_kernel: register sliding window along the delay axis            */
+} hb_poly_variant;
 
 /* Launch-uniform description of one batched fading propagation. */
 typedef struct hb_fading_problem {
@@ -99,6 +105,8 @@ typedef struct hb_fading_plan_info {
   int32_t num_tiles;   /* CTAs per link */
   int32_t launches;    /* kernels launched per call */
   double error_bound;  /* bound on the relative truncation error of the POLY expansion */
+  int32_t variant;     /* hb_poly_variant (POLY only) */
+  int32_t poly_tile;   /* samples per Taylor expansion window (POLY only; a multiple of tile) */
 } hb_fading_plan_info;
 
 HB_API int hb_version(void);
@@ -169,6 +177,8 @@ typedef struct hb_cdl_plan_info {
   int32_t num_tiles;
   int32_t launches;
   double error_bound;
+  int32_t variant;     /* reserved (0) */
+  int32_t poly_tile;   /* == tile */
 } hb_cdl_plan_info;
 
 HB_API int hb_cdl_plan(const hb_cdl_problem* p, hb_cdl_plan_info* info);

@@ -35,12 +35,42 @@ def _run_case(B, L, N, ntx, nrx, T, fs, doppler, max_delay_s, precision, sos_mod
 
 
 @pytest.mark.parametrize("ntx,nrx", [(1, 1), (2, 2), (4, 4), (4, 2), (3, 5), (8, 8), (10, 10)])
-@pytest.mark.parametrize("sos_mode", ["poly", "direct"])
+@pytest.mark.parametrize("sos_mode", ["poly", "poly_gather", "direct"])
 def test_f32_small_doppler(ntx, nrx, sos_mode):
     err, info = _run_case(B=3, L=12, N=20, ntx=ntx, nrx=nrx, T=1500, fs=30.72e6, doppler=100.0,
                           max_delay_s=1.5e-6, precision="f32", sos_mode=sos_mode, io=np.complex64)
-    assert info["mode"] == sos_mode
+    assert info["mode"] == sos_mode.split("_")[0]
+    if sos_mode != "direct":
+        # 12 taps over 46 samples: the sliding window reads less shared memory than the gather kernel
+        assert info["variant"] == ("window" if sos_mode == "poly" else "gather"), info
     assert err < F32_TOL, (err, info)
+
+
+@pytest.mark.parametrize("io", [np.complex64, np.complex128])
+@pytest.mark.parametrize("T,max_delay_s,L", [(37, 0.0, 3), (255, 2e-7, 5), (256, 2.6e-7, 9), (1023, 1e-6, 16),
+                                              (1025, 3e-6, 40), (5000, 3.3e-5, 200), (9000, 1e-5, 2)])
+@pytest.mark.parametrize("ntx,nrx", [(1, 1), (2, 3), (4, 4), (8, 8), (5, 9)])
+def test_window_variant_shapes(ntx, nrx, T, max_delay_s, L, io):
+    """Sliding-window kernel over ragged frame lengths, tile edges, dense/sparse delay sets, rx chunking."""
+    err, info = _run_case(B=2, L=L, N=8, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=300.0,
+                          max_delay_s=max_delay_s, precision="f32", sos_mode="auto", io=io, seed=T)
+    assert info["mode"] == "poly"
+    if L == 2:
+        assert info["variant"] == "gather", info  # two taps 307 samples apart: a window walk would be wasted
+    elif not (L == 200 and ntx > 4):  # 8-antenna chunks slide R = 4 outputs: 1014 delays / 4 > 183 groups
+        assert info["variant"] == "window", info
+    assert err < F32_TOL, (err, info)
+
+
+def test_window_and_gather_agree_on_c2_shape():
+    """Both POLY kernels evaluate the same Taylor model; they differ only by FP32 summation order."""
+    e1, i1 = _run_case(B=2, L=23, N=20, ntx=4, nrx=4, T=15344, fs=30.72e6, doppler=100.0, max_delay_s=1.44e-6,
+                       precision="f32", sos_mode="poly", io=np.complex64)
+    e2, i2 = _run_case(B=2, L=23, N=20, ntx=4, nrx=4, T=15344, fs=30.72e6, doppler=100.0, max_delay_s=1.44e-6,
+                       precision="f32", sos_mode="poly_gather", io=np.complex64)
+    assert i1["variant"] == "window" and i2["variant"] == "gather"
+    assert i1["poly_tile"] % i1["tile"] == 0
+    assert e1 < 1e-6 and e2 < 1e-6, (e1, e2)
 
 
 @pytest.mark.parametrize("io", [np.complex64, np.complex128])
