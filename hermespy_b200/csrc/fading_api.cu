@@ -67,7 +67,7 @@ static int pick_ntx_template(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 
 
 struct Plan {
   int mode, tile, P, ntiles, Dpad, ntx_tpl, taps_per_chunk;
-  int variant, poly_tile, npoly, threads;  // POLY: kernel variant, Taylor window, windows per link, CTA size
+  int variant, poly_tile, npoly, threads, large_halo, lin;  // POLY: kernel variant, Taylor window, windows per link, CTA size
   size_t smem;
   double bound;
   WindowPlan wp;
@@ -106,29 +106,32 @@ static void plan_window(const hb_fading_problem* p, const DelayTable& dt, Plan* 
   WindowPlan& wp = pl->wp;
   memset(&wp, 0, sizeof(wp));
   wp.num_groups = dt.num_groups;
-  wp.dmax = dt.group_delay[dt.num_groups - 1];
-  wp.nblk = wp.dmax / R + 1;
+  const int dmax = dt.group_delay[dt.num_groups - 1];
+  wp.nblk = dmax / R + 1;
   for (int g = 0; g < dt.num_groups; ++g) {
     const int d = dt.group_delay[g];
-    wp.present[d >> 5] |= 1u << (d & 31);
-    for (int e = std::max(0, d - R + 1); e <= d; ++e) wp.load[e >> 5] |= 1u << (e & 31);
+    wp.mask[d / R] |= (uint16_t)(1u << (d % R));
+    for (int e = std::max(0, d - R + 1); e <= d; ++e) wp.mask[e / R] |= (uint16_t)(0x100u << (e % R));
   }
   // CTA tile: the largest of {128, 64, 32} threads x R outputs that divides the Taylor window and is not
   // (much) longer than the frame
-  int threads = 128;
+  int threads = kWindowThreads;
   while (threads > 32 && (pl->poly_tile % (threads * R) != 0 || (threads / 2) * R >= Tout)) threads /= 2;
   pl->threads = threads;
   pl->tile = threads * R;
-  int PL = threads + wp.nblk;
-  const int want = (16 / R) % 16;  // pitch = 16/R (mod 16): conflict-free polyphase staging writes
-  while (PL % 16 != want) ++PL;
-  wp.plane = PL;
+  pl->large_halo = wp.nblk > kWindowHaloSmall;
+  const int PL = kWindowThreads + (pl->large_halo ? kWindowHaloLarge : kWindowHaloSmall);
   wp.poly_tile = pl->poly_tile;
   pl->npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
   wp.npoly = pl->npoly;
-  pl->smem = sizeof(float2) * ((size_t)pl->ntx_tpl * R * PL + (size_t)dt.num_groups * pl->P +
-                               (size_t)p->num_rx * pl->ntx_tpl);
+  pl->smem = (size_t)pl->ntx_tpl * R * PL * 8 +
+             sizeof(float2) * ((size_t)dt.num_groups * pl->P + (size_t)p->num_rx * pl->ntx_tpl);
   pl->Dpad = R * wp.nblk;
+  // linear extension of the tap gains over a thread's R outputs: neglected curvature, same normalization as
+  // poly_bound (relative to the RMS tap gain)
+  const double eps_w = 0.5 * (R - 1) * p->omega_max;
+  pl->lin = pl->P >= 3 && pl->P <= 4 && sqrt((double)(p->num_sinusoids + 1)) * eps_w * eps_w * 0.5 <= kPolyTarget;
+  if (pl->lin) pl->bound += sqrt((double)(p->num_sinusoids + 1)) * eps_w * eps_w * 0.5;
 }
 
 static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
@@ -145,6 +148,8 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
   pl->poly_tile = 0;
   pl->npoly = 0;
   pl->threads = kThreads;
+  pl->large_halo = 0;
+  pl->lin = 0;
   const bool window = poly && p->sos_mode != HB_SOS_POLY_GATHER && window_eligible(dt, pl->ntx_tpl);
   if (f64 && (p->sos_mode == HB_SOS_POLY || p->sos_mode == HB_SOS_POLY_GATHER)) {
     set_error("HB_F64 parity mode only supports direct evaluation");
@@ -267,10 +272,10 @@ static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& 
   ProfileScope prof(pl.mode == HB_SOS_POLY ? KIND_TDL_POLY : KIND_TDL_DIRECT, st);
   if (pl.mode == HB_SOS_POLY && pl.variant == HB_VARIANT_WINDOW) {
     switch (pl.ntx_tpl) {
-      case 1: return launch_tdl_window<1>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
-      case 2: return launch_tdl_window<2>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
-      case 4: return launch_tdl_window<4>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
-      default: return launch_tdl_window<8>(pl.P, io128, a, pl.wp, pl.threads, pl.smem, st);
+      case 1: return launch_tdl_window<1>(pl.P, io128, pl.large_halo != 0, pl.lin != 0, a, pl.wp, pl.threads, pl.smem, st);
+      case 2: return launch_tdl_window<2>(pl.P, io128, pl.large_halo != 0, pl.lin != 0, a, pl.wp, pl.threads, pl.smem, st);
+      case 4: return launch_tdl_window<4>(pl.P, io128, pl.large_halo != 0, pl.lin != 0, a, pl.wp, pl.threads, pl.smem, st);
+      default: return launch_tdl_window<8>(pl.P, io128, pl.large_halo != 0, pl.lin != 0, a, pl.wp, pl.threads, pl.smem, st);
     }
   }
   if (pl.mode == HB_SOS_POLY) {

@@ -4,23 +4,30 @@
 //
 // The gather kernel (tdl_poly_kernel) re-reads one x element from shared memory per (delay group, antenna,
 // output) and is bound by shared-memory wavefronts (profiles/r01_ncu_tdl_poly_ntx4_p3_r2.md).  Here every
-// thread owns R CONSECUTIVE outputs m0..m0+R-1 and walks the delay axis d = 0..Dmax once, keeping the R inputs
-// x[m0 - d .. m0 - d + R - 1] of every antenna in registers: stepping d -> d+1 shifts ONE new element in
-// (one LDS.64 per antenna).  Shared-memory reads per output drop from G to (Dmax + R) / R per antenna
-// (C2: 16 -> 6.5).  Static register indexing is obtained by unrolling the walk R-fold: at delay d = R c + s the
-// input of output u sits in window slot (u - s) mod R.
+// thread owns R CONSECUTIVE outputs m0..m0+R-1 and walks the delay axis once, keeping the R inputs
+// x[m0 - d .. m0 - d + R - 1] of every antenna in registers: stepping d -> d+1 shifts ONE new element in.
+// Shared-memory reads per output drop from G to (Dmax + R) / R per antenna (C2: 16 -> 6.5).
 //
-// Shared-memory layout ("polyphase"): element e of the staged tile [q tile - Dpad, q tile + tile) of antenna j
-// lives in plane e mod R at index e / R, so that the 32 lanes of a warp (outputs R apart) read consecutive 8-byte
-// words -- conflict-free -- and the plane pitch PL = 16/R (mod 16) keeps the coalesced staging writes
-// conflict-free as well.  The same layout, reused after the delay walk, transposes the results for fully
-// coalesced 8-byte global stores.
+// Static register indexing.  The walk is unrolled R-fold: at delay d = R c + s (c: block, s: phase) the input of
+// output u sits in window slot (u - s) mod R and the element entering (u = 0) goes to slot (R - s) mod R --
+// always the slot e mod R of its index e in the staged tile, so a slot is simply overwritten in place.
+//
+// Shared-memory layout ("polyphase planes of antenna pairs"): the staged tile holds elements e = 0 .. R (NT + Dq)
+// - 1 of every antenna, element e <-> input sample n = q tile - R Dq + e.  Row i = e / R belongs to thread i - Dq
+// (+ Dq halo rows), plane k = e mod R.  Antennas (2p, 2p+1) are interleaved, xs[p][k][i] = one float4
+// (re_2p, im_2p, re_2p+1, im_2p+1): the 32 lanes of a warp read consecutive 16-byte words (conflict-free
+// LDS.128, one per antenna pair and delay step), and a row is 64 contiguous bytes of global memory per antenna,
+// copied by its thread with 8-byte cp.async (zero-filled outside the frame) -- no index arithmetic, no
+// alignment requirement beyond the element size.  Single-antenna chunks use 8-byte planes xs[k][i].
 //
 // Arithmetic: packed FFMA2 (fma.rn.f32x2).  A complex MAC  acc += x * h  is
 //   acc(re,im) += x(re,im) * h.re            (scalar-broadcast operand)
-//   acc(re,im) += x(im,re) * (-h.im, h.im)   (ptxas folds the swap into the .LO_HI operand modifier)
-// i.e. 2 issue slots instead of 4 -- the FP32 pipe does the same flops, but the issue port is left free for the
-// shared-memory loads and the address arithmetic (measured: tools/microbench/pipes.cu, FFMA2 = 64 lanes/clk/SM).
+//   acc(re,im) += x(im,re) * (-h.im, h.im)   (ptxas folds swap and sign into the .LO_HI / .NP operand modifiers)
+// i.e. 2 issue slots instead of 4; the FP32 pipe does the same flops (tools/microbench/pipes.cu: FFMA2 issues at
+// half rate), but the issue port is left free for shared-memory loads and address arithmetic.
+//
+// Results leave the registers directly: every thread stores its R consecutive outputs of each receive stream
+// with 16-byte stores (64 contiguous bytes per thread and stream).
 #pragma once
 #include "fading_kernels.cuh"
 
@@ -28,18 +35,20 @@ namespace hb {
 
 typedef unsigned long long u64;
 
-constexpr int kWindowMaxDelay = 1023;  // delay walk masks cover d = 0..1023
+constexpr int kWindowMaxDelay = 1023;   // walk masks cover d = 0..1023
+constexpr int kWindowThreads = 128;     // maximum CTA size (32 / 64 for short frames)
+constexpr int kWindowHaloSmall = 16;    // halo rows of the small-delay instantiation (d' < 16 R)
+constexpr int kWindowHaloLarge = 1024 / 4 + 2;
 
 // Launch-uniform plan of the delay walk, by value in kernel parameter space.
 struct WindowPlan {
   int32_t num_groups;
-  int32_t dmax;       // largest group delay
-  int32_t nblk;       // dmax / R + 1 blocks of R delays
-  int32_t plane;      // plane pitch PL in elements
+  int32_t nblk;       // blocks of R delays: dmax / R + 1
   int32_t poly_tile;  // samples per Taylor expansion window (multiple of the CTA tile)
   int32_t npoly;      // expansion windows per link
-  uint32_t present[(kWindowMaxDelay + 1) / 32];  // bit d: some tap has rounded delay d
-  uint32_t load[(kWindowMaxDelay + 1) / 32];     // bit d: x[m0 - d] is needed by a present delay in [d, d+R)
+  // per block c: bits 0..R-1 "a tap has delay d = R c + s", bits 8..8+R-1 "x[m0 - d] is needed" (by a present
+  // delay in [d, d + R))
+  uint16_t mask[kWindowMaxDelay / 4 + 2];
 };
 
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
@@ -67,45 +76,107 @@ __device__ __forceinline__ void cmac2(u64& acc, u64 x, u64 hre, u64 him) {
   acc = fma2(swap2(x), him, acc);
 }
 
-__device__ __forceinline__ u64 lds_pair(const float2* p) {
-  const float2 v = *p;
-  return pk2(v.x, v.y);
+// 32-bit shared-window addressing with immediate offsets (no generic-address arithmetic in the hot loop)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int IMM>
+__device__ __forceinline__ void lds_pair(uint32_t addr, u64& lo, u64& hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2 + %3];" : "=l"(lo), "=l"(hi) : "r"(addr), "n"(IMM));
+}
+template <int IMM>
+__device__ __forceinline__ u64 lds_one(uint32_t addr) {
+  u64 v;
+  asm volatile("ld.shared.b64 %0, [%1 + %2];" : "=l"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void stg_stream4(float2* p, u64 a, u64 b) {
+  asm volatile("st.global.L1::no_allocate.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
-template <int NTX, int P, int R, typename IO>
-__global__ void __launch_bounds__(128, (NTX * R >= 32) ? 3 : 4)
+__device__ __forceinline__ void cp_async8_full(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// Stage the rows of one antenna pair (or single antenna, ES == 8) of the tile starting at sample n0.  Work item
+// = (row, antenna of the pair): consecutive lanes write consecutive 8-byte words of a plane (conflict-free) and
+// read 64-byte spans of two global rows.  `dst0` is the shared address of (plane 0, row 0) of the pair.
+template <int R, int PL, int ES, typename IO>
+__device__ __forceinline__ void stage_pair(uint32_t dst0, const IO* rowA, const IO* rowB, bool liveA, bool liveB,
+                                           int n0, int T, int nrows, int tid, int NT) {
+  constexpr int PAR = ES / 8;
+  const bool interior = n0 >= 0 && n0 + R * nrows <= T;  // CTA-uniform: no frame edge inside the tile
+  for (int it = tid; it < nrows * PAR; it += NT) {
+    const int i = PAR == 2 ? (it >> 1) : it;
+    const int par = PAR == 2 ? (it & 1) : 0;
+    const IO* row = par ? rowB : rowA;
+    const bool live = par ? liveB : liveA;
+    const int n = n0 + R * i;  // first sample of the row
+    const uint32_t dst = dst0 + (uint32_t)i * ES + par * 8;
+    if constexpr (sizeof(IO) == 8) {
+      if (interior && live) {
+        const IO* src = row + n;
+#pragma unroll
+        for (int k = 0; k < R; ++k) cp_async8_full(dst + k * PL * ES, src + k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int nn = n + k;
+          const bool ok = live && nn >= 0 && nn < T;
+          cp_async8(dst + k * PL * ES, ok ? (const void*)(row + nn) : (const void*)row, ok ? 8 : 0);
+        }
+      }
+    } else {  // complex128 host layout: convert on the way in
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int nn = n + k;
+        float2 v = make_float2(0.f, 0.f);
+        if (live && nn >= 0 && nn < T) v = to_c32(ldg_stream(row + nn));
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst + k * PL * ES), "f"(v.x), "f"(v.y) : "memory");
+      }
+    }
+  }
+}
+
+// LIN: the tap gain polynomial is evaluated once per thread and delay group (value and slope at the centre of the
+// thread's R outputs) and extended linearly over them; hb_fading_plan enables it when the neglected curvature
+// sqrt(N+1) ((R-1)/2 omega_max)^2 / 2 stays below the truncation target.
+template <int NTX, int P, int R, int HALO, bool LIN, typename IO>
+__global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
     tdl_window_kernel(const FadingArgs a, const __grid_constant__ WindowPlan wp) {
-  static_assert(R == 4 || R == 8 || R == 16, "R must divide 32");
+  static_assert(R == 4 || R == 8, "R must be 4 or 8");
+  static_assert(NTX == 1 || NTX % 2 == 0, "antennas are staged in pairs");
+  constexpr int PL = kWindowThreads + HALO;    // rows per plane
+  constexpr int ES = NTX == 1 ? 8 : 16;        // bytes per staged element (antenna pair)
+  constexpr int NP = NTX == 1 ? 1 : NTX / 2;   // antenna pairs
+  constexpr int PS = R * PL * ES;              // bytes per antenna pair
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NT = blockDim.x;
   const int tile = NT * R;
   const int b = blockIdx.x / a.ntiles, q = blockIdx.x - b * a.ntiles, tid = threadIdx.x;
-  const int G = wp.num_groups, PL = wp.plane;
-  const int Dq = wp.nblk;  // halo planes-worth: Dpad = R * nblk
-  const int W = tile + R * Dq;
+  const int G = wp.num_groups;
+  const int Dq = wp.nblk;  // halo rows: Dp = R * nblk
   const int Tout = a.T + a.D;
 
-  float2* xs = reinterpret_cast<float2*>(smem_raw);  // [NTX][R][PL]
-  float2* cs = xs + (size_t)NTX * R * PL;             // [G][P]
-  float2* Ss = cs + G * P;                            // [nrx][NTX]
+  float2* cs = reinterpret_cast<float2*>(smem_raw + NP * PS);  // [G][P]
+  float2* Ss = cs + G * P;                                      // [nrx][NTX]
+  const uint32_t xs = smem_u32(smem_raw);
 
-  // ---- stage: x tile (+ halo) into the polyphase planes, Taylor coefficients, spatial matrix ------------
+  // ---- stage: x tile (+ halo), Taylor coefficients, spatial matrix ------------------------------------------
   {
     const IO* xb = reinterpret_cast<const IO*>(a.x) + ((size_t)b * a.ntx + a.tx0) * a.T;
     const int n0 = q * tile - R * Dq;
 #pragma unroll
-    for (int j = 0; j < NTX; ++j) {
-      const bool live = j < a.ntx_chunk;
-      const IO* row = xb + (size_t)j * a.T;
-      float2* xj = xs + (size_t)j * R * PL;
-#pragma unroll 8
-      for (int e = tid; e < W; e += NT) {
-        const int n = n0 + e;
-        float2 v = make_float2(0.f, 0.f);
-        if (live && n >= 0 && n < a.T) v = to_c32(ldg_stream(row + n));
-        xj[(e & (R - 1)) * PL + (e / R)] = v;
-      }
-    }
+    for (int pr = 0; pr < NP; ++pr)
+      stage_pair<R, PL, ES, IO>(xs + pr * PS, xb + (size_t)(2 * pr) * a.T, xb + (size_t)(2 * pr + 1) * a.T,
+                                2 * pr < a.ntx_chunk, 2 * pr + 1 < a.ntx_chunk, n0, a.T, NT + Dq, tid, NT);
     const int qp = (q * tile) / wp.poly_tile;
     const float2* cb = a.coef + ((size_t)b * wp.npoly + qp) * G * P;
     for (int c = tid; c < G * P; c += NT) cs[c] = cb[c];
@@ -116,11 +187,12 @@ __global__ void __launch_bounds__(128, (NTX * R >= 32) ? 3 : 4)
       if (j < a.ntx_chunk) v = to_c32(Sb[irx * a.ntx + a.tx0 + j]);
       Ss[c] = v;
     }
+    if constexpr (sizeof(IO) == 8) cp_async_wait_all();
   }
   __syncthreads();
 
   const int m0 = q * tile + R * tid;  // first output of this thread
-  const bool active = m0 < Tout;      // warp-uniform except in one warp of the last tile
+  if (m0 >= Tout) return;             // no barrier below
 
   u64 acc[R][NTX];
 #pragma unroll
@@ -128,50 +200,84 @@ __global__ void __launch_bounds__(128, (NTX * R >= 32) ? 3 : 4)
 #pragma unroll
     for (int j = 0; j < NTX; ++j) acc[u][j] = 0ull;
 
-  if (active) {
-    // normalized expansion coordinate of each owned output
+  {
+    // normalized expansion coordinate of each owned output (LIN: offsets from the centre of the R outputs)
     float rr[R];
+    float rc;
     {
       const int qp = (q * tile) / wp.poly_tile;
       const float inv = 1.0f / (float)wp.poly_tile;
       const float r0 = ((float)(m0 - qp * wp.poly_tile) - 0.5f * (float)wp.poly_tile) * inv;
+      rc = fmaf(0.5f * (float)(R - 1), inv, r0);
 #pragma unroll
-      for (int u = 0; u < R; ++u) rr[u] = fmaf((float)u, inv, r0);
+      for (int u = 0; u < R; ++u) rr[u] = LIN ? ((float)u - 0.5f * (float)(R - 1)) * inv : fmaf((float)u, inv, r0);
     }
-    // window at d = 0: slot u holds element e = Dpad + R tid + u  (plane u, index tid + Dq)
+    // window at d = 0: slot u holds element Dp + R tid + u (plane u, row tid + Dq)
     u64 w[NTX][R];
-    const float2* xt = xs + tid + Dq;
+    uint32_t xa = xs + (uint32_t)(tid + Dq) * ES;
 #pragma unroll
-    for (int j = 0; j < NTX; ++j)
+    for (int pr = 0; pr < NP; ++pr)
 #pragma unroll
-      for (int u = 0; u < R; ++u) w[j][u] = lds_pair(xt + (j * R + u) * PL);
+      for (int u = 0; u < R; ++u) {
+        if constexpr (NTX == 1)
+          w[0][u] = lds_one<0>(xa + u * PL * ES);
+        else
+          lds_pair<0>(xa + pr * PS + u * PL * ES, w[2 * pr][u], w[2 * pr + 1][u]);
+      }
 
-    int g = 0;
-    for (int c = 0; c < wp.nblk; ++c) {
-      const int bit0 = c * R;
-      const uint32_t pm = (wp.present[bit0 >> 5] >> (bit0 & 31)) & ((1u << R) - 1u);
-      const uint32_t lm = (wp.load[bit0 >> 5] >> (bit0 & 31)) & ((1u << R) - 1u);
-      if ((pm | lm) == 0u) continue;
+    uint32_t csa = smem_u32(cs);
+    const int nblk = wp.nblk;
+    for (int c = 0; c < nblk; ++c, xa -= ES) {
+      const uint32_t mk = wp.mask[c];
+      if (mk == 0u) continue;
+      const uint32_t pm = mk & 0xffu, lm = mk >> 8;
 #pragma unroll
       for (int s = 0; s < R; ++s) {
         if (((lm >> s) & 1u) && (c | s)) {
-          // new element x[m0 - d], d = R c + s: plane (R - s) % R, index tid + Dq - c - (s > 0)
-          const int k = (R - s) % R;
-          const float2* src = xt + k * PL - c - (s > 0 ? 1 : 0);
+          // element x[m0 - d], d = R c + s: plane k = (R - s) % R, row tid + Dq - c - (s > 0)
 #pragma unroll
-          for (int j = 0; j < NTX; ++j) w[j][k] = lds_pair(src + j * R * PL);
+          for (int pr = 0; pr < NP; ++pr) {
+            const uint32_t ad = xa + pr * PS + ((R - s) % R) * PL * ES;
+            if constexpr (NTX == 1) {
+              w[0][(R - s) % R] = s > 0 ? lds_one<-ES>(ad) : lds_one<0>(ad);
+            } else {
+              if (s > 0)
+                lds_pair<-ES>(ad, w[2 * pr][(R - s) % R], w[2 * pr + 1][(R - s) % R]);
+              else
+                lds_pair<0>(ad, w[2 * pr][(R - s) % R], w[2 * pr + 1][(R - s) % R]);
+            }
+          }
         }
         if ((pm >> s) & 1u) {
           u64 cf[P];
 #pragma unroll
-          for (int p = 0; p < P; ++p) cf[p] = lds_pair(cs + g * P + p);
-          ++g;
+          for (int p = 0; p < P; ++p) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cf[p]) : "r"(csa + p * 8));
+          csa += P * 8;
+          u64 hc = cf[P - 1], hs = 0ull;
+          if constexpr (LIN) {
+            static_assert(!LIN || P >= 3, "LIN only pays for P >= 3");
+            const u64 rcb = pk2(rc, rc);
+            const float fp = (float)(P - 1);
+            hs = fma2(cf[P - 1], pk2(fp, fp), 0ull);  // derivative by Horner: sum_p p c_p r^(p-1)
+#pragma unroll
+            for (int p = P - 2; p >= 1; --p) {
+              const float fq = (float)p;
+              hs = fma2(hs, rcb, fma2(cf[p], pk2(fq, fq), 0ull));
+            }
+#pragma unroll
+            for (int p = P - 2; p >= 0; --p) hc = fma2(hc, rcb, cf[p]);
+          }
 #pragma unroll
           for (int u = 0; u < R; ++u) {
             const u64 rb = pk2(rr[u], rr[u]);
-            u64 hv = cf[P - 1];
+            u64 hv;
+            if constexpr (LIN) {
+              hv = fma2(hs, rb, hc);
+            } else {
+              hv = cf[P - 1];
 #pragma unroll
-            for (int p = P - 2; p >= 0; --p) hv = fma2(hv, rb, cf[p]);
+              for (int p = P - 2; p >= 0; --p) hv = fma2(hv, rb, cf[p]);
+            }
             const float2 h = upk2(hv);
             const u64 hre = pk2(h.x, h.x);
             const u64 him = pk2(-h.y, h.y);
@@ -182,46 +288,43 @@ __global__ void __launch_bounds__(128, (NTX * R >= 32) ? 3 : 4)
       }
     }
   }
-  __syncthreads();  // every thread is done with the x planes: reuse them for the output transpose
 
-  // ---- spatial mix  y[irx] = sum_j S[irx][j] z[j], NTX receive streams at a time, transposed through the
-  //      planes so that the global stores are coalesced 8-byte (16-byte for complex128) accesses ------------
-  IO* yb = reinterpret_cast<IO*>(a.y) + (size_t)b * a.nrx * Tout;
-  const int mbase = q * tile;
-  const int live = min(tile, Tout - mbase);
-  for (int irx0 = 0; irx0 < a.nrx; irx0 += NTX) {
-    const int nr = min(NTX, a.nrx - irx0);
-    if (irx0 > 0) __syncthreads();  // previous chunk stored
-    if (active) {
-      for (int i = 0; i < nr; ++i) {
-        u64 yv[R];
+  // ---- spatial mix  y[irx] = sum_j S[irx][j] z[j]  and direct stores of the thread's R consecutive outputs ----
+  IO* yb = reinterpret_cast<IO*>(a.y) + (size_t)b * a.nrx * Tout + m0;
+  const bool vec_ok = sizeof(IO) == 8 && ((Tout & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) &&
+                      (m0 + R <= Tout) && !a.accumulate;
+  const uint32_t ssa = smem_u32(Ss);
+  for (int irx = 0; irx < a.nrx; ++irx) {
+    u64 yv[R];
 #pragma unroll
-        for (int u = 0; u < R; ++u) yv[u] = 0ull;
+    for (int u = 0; u < R; ++u) yv[u] = 0ull;
 #pragma unroll
-        for (int j = 0; j < NTX; ++j) {
-          const float2 s = Ss[(irx0 + i) * NTX + j];
-          const u64 sre = pk2(s.x, s.x), sim = pk2(-s.y, s.y);
+    for (int j = 0; j < NTX; ++j) {
+      u64 sv;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(sv) : "r"(ssa + (irx * NTX + j) * 8));
+      const float2 s = upk2(sv);
+      const u64 sre = pk2(s.x, s.x), sim = pk2(-s.y, s.y);
 #pragma unroll
-          for (int u = 0; u < R; ++u) cmac2(yv[u], acc[u][j], sre, sim);
-        }
-        float2* yt = xs + (size_t)i * R * PL + tid;
-#pragma unroll
-        for (int u = 0; u < R; ++u) yt[u * PL] = upk2(yv[u]);
-      }
+      for (int u = 0; u < R; ++u) cmac2(yv[u], acc[u][j], sre, sim);
     }
-    __syncthreads();
-    for (int i = 0; i < nr; ++i) {
-      const float2* yr = xs + (size_t)i * R * PL;
-      IO* dst = yb + (size_t)(irx0 + i) * Tout + mbase;
-#pragma unroll 4
-      for (int e = tid; e < live; e += NT) {
-        float2 v = yr[(e & (R - 1)) * PL + (e / R)];
-        if (a.accumulate) {
-          const IO old = dst[e];
-          v.x += (float)old.x;
-          v.y += (float)old.y;
+    IO* dst = yb + (size_t)irx * Tout;
+    if (vec_ok) {
+      if constexpr (sizeof(IO) == 8) {
+#pragma unroll
+        for (int u = 0; u < R; u += 2) stg_stream4(reinterpret_cast<float2*>(dst) + u, yv[u], yv[u + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (m0 + u < Tout) {
+          float2 v = upk2(yv[u]);
+          if (a.accumulate) {
+            const IO old = dst[u];
+            v.x += (float)old.x;
+            v.y += (float)old.y;
+          }
+          stg_stream(dst + u, IoConv<IO>::make(v.x, v.y));
         }
-        stg_stream(dst + e, IoConv<IO>::make(v.x, v.y));
       }
     }
   }
@@ -230,7 +333,7 @@ __global__ void __launch_bounds__(128, (NTX * R >= 32) ? 3 : 4)
 template <int NTX> constexpr int window_samples_per_thread() { return NTX <= 4 ? 8 : 4; }
 
 template <int NTX>
-int launch_tdl_window(int P, bool io128, const FadingArgs& a, const WindowPlan& wp, int threads, size_t smem,
-                      cudaStream_t st);
+int launch_tdl_window(int P, bool io128, bool large_halo, bool lin, const FadingArgs& a, const WindowPlan& wp, int threads,
+                      size_t smem, cudaStream_t st);
 
 }  // namespace hb
