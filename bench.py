@@ -336,7 +336,7 @@ def main():
     ap.add_argument("--e2e-links", type=int, default=512, help="links per end-to-end step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: shrink the end-to-end leg to one link")
-    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_gather", "direct"],
+    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "direct"],
                     help="kernel selection (profiling / A-B runs); the default lets the planner choose")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -34,7 +34,7 @@ static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
     set_error("unknown precision %d", p->precision);
     return HB_ERR_INVALID;
   }
-  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_GATHER) {
+  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_WINDOW) {
     set_error("unknown sos_mode %d", p->sos_mode);
     return HB_ERR_INVALID;
   }
@@ -110,13 +110,19 @@ static void plan_window(const hb_fading_problem* p, const DelayTable& dt, Plan* 
   wp.nblk = dmax / R + 1;
   for (int g = 0; g < dt.num_groups; ++g) {
     const int d = dt.group_delay[g];
-    wp.mask[d / R] |= (uint16_t)(1u << (d % R));
-    for (int e = std::max(0, d - R + 1); e <= d; ++e) wp.mask[e / R] |= (uint16_t)(0x100u << (e % R));
+    wp.mask[d / R] |= 1u << (d % R);
+    for (int e = std::max(0, d - R + 1); e <= d; ++e) wp.mask[e / R] |= 0x100u << (e % R);
   }
+  for (int c = 0; c < wp.nblk; ++c)
+    if (wp.mask[c + 1] & 0x100u) wp.mask[c] |= 0x100u << R;
   // CTA tile: the largest of {128, 64, 32} threads x R outputs that divides the Taylor window and is not
   // (much) longer than the frame
   int threads = kWindowThreads;
   while (threads > 32 && (pl->poly_tile % (threads * R) != 0 || (threads / 2) * R >= Tout)) threads /= 2;
+  if (const char* ev = getenv("HB_WINDOW_THREADS")) {  // experiments only
+    const int t = atoi(ev);
+    if ((t == 32 || t == 64 || t == 128) && pl->poly_tile % (t * R) == 0) threads = t;
+  }
   pl->threads = threads;
   pl->tile = threads * R;
   pl->large_halo = wp.nblk > kWindowHaloSmall;
@@ -125,13 +131,14 @@ static void plan_window(const hb_fading_problem* p, const DelayTable& dt, Plan* 
   pl->npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
   wp.npoly = pl->npoly;
   pl->smem = (size_t)pl->ntx_tpl * R * PL * 8 +
-             sizeof(float2) * ((size_t)dt.num_groups * pl->P + (size_t)p->num_rx * pl->ntx_tpl);
+             sizeof(float2) * ((size_t)(dt.num_groups + 1) * pl->P + (size_t)p->num_rx * pl->ntx_tpl);
   pl->Dpad = R * wp.nblk;
   // linear extension of the tap gains over a thread's R outputs: neglected curvature, same normalization as
   // poly_bound (relative to the RMS tap gain)
   const double eps_w = 0.5 * (R - 1) * p->omega_max;
   pl->lin = pl->P >= 3 && pl->P <= 4 && sqrt((double)(p->num_sinusoids + 1)) * eps_w * eps_w * 0.5 <= kPolyTarget;
   if (pl->lin) pl->bound += sqrt((double)(p->num_sinusoids + 1)) * eps_w * eps_w * 0.5;
+
 }
 
 static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
@@ -163,7 +170,13 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
     double best_bound = 0;
     for (int P : kOrders) {
       for (int tile0 : kTiles) {
-        const int tile = std::min(tile0, tile_cap);
+        // window variant: CTA tiles are 32/64/128 threads x R outputs and must divide the Taylor window, so the
+        // window stays a power of two (not longer than the padded frame)
+        int tile = std::min(tile0, tile_cap);
+        if (window) {
+          tile = tile0;
+          while (tile > kThreads && tile / 2 >= Tout) tile /= 2;
+        }
         if (!window && poly_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx) > kSmemSoftLimit &&
             tile > kThreads)
           continue;
@@ -317,6 +330,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   a.tile = pl.tile;
   a.ntiles = pl.ntiles;
   a.Dpad = pl.Dpad;
+  if (const char* ev = getenv("HB_DBG")) a.dbg = atoi(ev);
   if ((size_t)a.ntiles * a.B > 0x7fffffffull) {
     set_error("grid of %zu CTAs exceeds the launch limit; split the batch", (size_t)a.ntiles * a.B);
     return HB_ERR_UNSUPPORTED;
@@ -326,6 +340,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
     const size_t bytes = sizeof(float2) * (size_t)a.B * pl.npoly * dt.num_groups * pl.P;
     HB_CUDA(cudaMallocAsync((void**)&coef, bytes, st));
     a.coef = coef;
+    a.spatial32 = nullptr;
     FadingArgs ac = a;  // K1 runs over the Taylor windows, which may span several CTA tiles
     ac.tile = pl.poly_tile;
     ac.ntiles = pl.npoly;

@@ -25,9 +25,11 @@ struct FadingArgs {
   const double* amp;       // [B, L, 2]
   const double2* spatial;  // [B, Nrx, Ntx]
   const float2* coef;      // [B, ntiles, G, P]  (poly mode)
+  float2* spatial32;       // [B, Nrx, Ntx] FP32 copy of `spatial`, written by K1 when not NULL
   int B, ntx, nrx, T, D, L, K;
   int tile, ntiles, Dpad;
   int tx0, ntx_chunk, accumulate;
+  int dbg;  // attribution experiments only (HB_DBG)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -49,6 +51,11 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
   const double* om_b = a.omega + (size_t)b * a.L * K;
   const double* ph_b = a.phi + (size_t)b * a.L * K;
   const double* am_b = a.amp + (size_t)b * a.L * 2;
+  if (q == 0 && a.spatial32 != nullptr) {  // FP32 spatial matrix for the cp.async-staged kernels
+    const int n = a.nrx * a.ntx;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      a.spatial32[(size_t)b * n + i] = to_c32(a.spatial[(size_t)b * n + i]);
+  }
   for (int g = warp; g < G; g += 4) {
     const int l0 = dt.group_start[g], l1 = dt.group_start[g + 1];
     const double shift = centre - (double)dt.group_delay[g];

@@ -46,9 +46,10 @@ struct WindowPlan {
   int32_t nblk;       // blocks of R delays: dmax / R + 1
   int32_t poly_tile;  // samples per Taylor expansion window (multiple of the CTA tile)
   int32_t npoly;      // expansion windows per link
-  // per block c: bits 0..R-1 "a tap has delay d = R c + s", bits 8..8+R-1 "x[m0 - d] is needed" (by a present
-  // delay in [d, d + R))
-  uint16_t mask[kWindowMaxDelay / 4 + 2];
+  // per block c: bits 0..R-1 "a tap has delay d = R c + s", bits 8..8+R "x[m0 - d] is needed (by a present delay in
+  // [d, d + R))" for d = R c + s, s = 0..R (bit 8+R repeats bit 8 of the next block: that element is fetched
+  // from within this block)
+  uint32_t mask[kWindowMaxDelay / 4 + 2];
 };
 
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
@@ -166,13 +167,14 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
   const int Tout = a.T + a.D;
 
   float2* cs = reinterpret_cast<float2*>(smem_raw + NP * PS);  // [G][P]
-  float2* Ss = cs + G * P;                                      // [nrx][NTX]
+  float2* Ss = cs + (G + 1) * P;                                // [nrx][NTX]; one group of padding before it
   const uint32_t xs = smem_u32(smem_raw);
 
   // ---- stage: x tile (+ halo), Taylor coefficients, spatial matrix ------------------------------------------
   {
     const IO* xb = reinterpret_cast<const IO*>(a.x) + ((size_t)b * a.ntx + a.tx0) * a.T;
     const int n0 = q * tile - R * Dq;
+    if (!(a.dbg & 1))
 #pragma unroll
     for (int pr = 0; pr < NP; ++pr)
       stage_pair<R, PL, ES, IO>(xs + pr * PS, xb + (size_t)(2 * pr) * a.T, xb + (size_t)(2 * pr + 1) * a.T,
@@ -225,65 +227,86 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
           lds_pair<0>(xa + pr * PS + u * PL * ES, w[2 * pr][u], w[2 * pr + 1][u]);
       }
 
+    // Software pipeline over the delay groups: the tap-gain polynomial of group g+1 is fetched (and, with LIN,
+    // reduced to value + slope at the thread's centre) while the MACs of group g issue, and the element entering
+    // at the next delay is loaded right after the MACs of output R-1 -- the last reader of its window slot.
+    constexpr int NH = LIN ? 2 : P;
     uint32_t csa = smem_u32(cs);
-    const int nblk = wp.nblk;
+    u64 hp[NH];
+    auto prep = [&]() {  // consume the coefficients at csa (one group past the end is padding)
+      u64 cf[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cf[p]) : "r"(csa + p * 8));
+      csa += P * 8;
+      if constexpr (LIN) {
+        static_assert(!LIN || P >= 3, "LIN only pays for P >= 3");
+        const u64 rcb = pk2(rc, rc);
+        const float fp = (float)(P - 1);
+        u64 hs = fma2(cf[P - 1], pk2(fp, fp), 0ull);  // derivative by Horner: sum_p p c_p rc^(p-1)
+#pragma unroll
+        for (int p = P - 2; p >= 1; --p) {
+          const float fq = (float)p;
+          hs = fma2(hs, rcb, fma2(cf[p], pk2(fq, fq), 0ull));
+        }
+        u64 hc = cf[P - 1];
+#pragma unroll
+        for (int p = P - 2; p >= 0; --p) hc = fma2(hc, rcb, cf[p]);
+        hp[0] = hc;
+        hp[1] = hs;
+      } else {
+#pragma unroll
+        for (int p = 0; p < P; ++p) hp[p] = cf[p];
+      }
+    };
+    prep();
+
+    const int nblk = (a.dbg & 4) ? 0 : wp.nblk;
     for (int c = 0; c < nblk; ++c, xa -= ES) {
       const uint32_t mk = wp.mask[c];
       if (mk == 0u) continue;
-      const uint32_t pm = mk & 0xffu, lm = mk >> 8;
+      const uint32_t pm = mk & 0xffu, lm = mk >> 8;  // lm bit s: the element entering at phase s is needed
 #pragma unroll
       for (int s = 0; s < R; ++s) {
-        if (((lm >> s) & 1u) && (c | s)) {
-          // element x[m0 - d], d = R c + s: plane k = (R - s) % R, row tid + Dq - c - (s > 0)
+        // element entering at the NEXT phase, x[m0 - (R c + s + 1)]: plane (R - s - 1), row tid + Dq - c - 1
+        auto load_next = [&]() {
+          if ((lm >> (s + 1)) & 1u) {
 #pragma unroll
-          for (int pr = 0; pr < NP; ++pr) {
-            const uint32_t ad = xa + pr * PS + ((R - s) % R) * PL * ES;
-            if constexpr (NTX == 1) {
-              w[0][(R - s) % R] = s > 0 ? lds_one<-ES>(ad) : lds_one<0>(ad);
-            } else {
-              if (s > 0)
-                lds_pair<-ES>(ad, w[2 * pr][(R - s) % R], w[2 * pr + 1][(R - s) % R]);
+            for (int pr = 0; pr < NP; ++pr) {
+              const uint32_t ad = xa + pr * PS + (R - s - 1) * PL * ES;
+              if constexpr (NTX == 1)
+                w[0][R - s - 1] = lds_one<-ES>(ad);
               else
-                lds_pair<0>(ad, w[2 * pr][(R - s) % R], w[2 * pr + 1][(R - s) % R]);
+                lds_pair<-ES>(ad, w[2 * pr][R - s - 1], w[2 * pr + 1][R - s - 1]);
             }
           }
-        }
+        };
         if ((pm >> s) & 1u) {
-          u64 cf[P];
+          u64 hq[NH];
 #pragma unroll
-          for (int p = 0; p < P; ++p) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cf[p]) : "r"(csa + p * 8));
-          csa += P * 8;
-          u64 hc = cf[P - 1], hs = 0ull;
-          if constexpr (LIN) {
-            static_assert(!LIN || P >= 3, "LIN only pays for P >= 3");
-            const u64 rcb = pk2(rc, rc);
-            const float fp = (float)(P - 1);
-            hs = fma2(cf[P - 1], pk2(fp, fp), 0ull);  // derivative by Horner: sum_p p c_p r^(p-1)
-#pragma unroll
-            for (int p = P - 2; p >= 1; --p) {
-              const float fq = (float)p;
-              hs = fma2(hs, rcb, fma2(cf[p], pk2(fq, fq), 0ull));
-            }
-#pragma unroll
-            for (int p = P - 2; p >= 0; --p) hc = fma2(hc, rcb, cf[p]);
-          }
-#pragma unroll
-          for (int u = 0; u < R; ++u) {
-            const u64 rb = pk2(rr[u], rr[u]);
+          for (int i = 0; i < NH; ++i) hq[i] = hp[i];
+          prep();  // next group
+          auto mac_u = [&](int u) {
             u64 hv;
             if constexpr (LIN) {
-              hv = fma2(hs, rb, hc);
+              hv = fma2(hq[1], pk2(rr[u], rr[u]), hq[0]);
             } else {
-              hv = cf[P - 1];
+              const u64 rb = pk2(rr[u], rr[u]);
+              hv = hq[P - 1];
 #pragma unroll
-              for (int p = P - 2; p >= 0; --p) hv = fma2(hv, rb, cf[p]);
+              for (int p = P - 2; p >= 0; --p) hv = fma2(hv, rb, hq[p]);
             }
             const float2 h = upk2(hv);
             const u64 hre = pk2(h.x, h.x);
             const u64 him = pk2(-h.y, h.y);
 #pragma unroll
             for (int j = 0; j < NTX; ++j) cmac2(acc[u][j], w[j][(u - s + R) % R], hre, him);
-          }
+          };
+          mac_u(R - 1);
+          load_next();
+#pragma unroll
+          for (int u = 0; u < R - 1; ++u) mac_u(u);
+        } else {
+          load_next();
         }
       }
     }
@@ -308,6 +331,7 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
       for (int u = 0; u < R; ++u) cmac2(yv[u], acc[u][j], sre, sim);
     }
     IO* dst = yb + (size_t)irx * Tout;
+    if ((a.dbg & 2) && irx + tid + m0 != -12345) continue;
     if (vec_ok) {
       if constexpr (sizeof(IO) == 8) {
 #pragma unroll

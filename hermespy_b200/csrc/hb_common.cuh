@@ -23,6 +23,7 @@ constexpr double kInvTwoPi = 0.15915494309189533576888376337251;
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int require_device();
+int device_sm_count();
 
 // ---- per-kernel accounting (hb_profile_begin/end, hb_launch_counts) -------------------------------
 enum KernelKind {

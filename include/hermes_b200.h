@@ -68,7 +68,8 @@ typedef enum hb_sos_mode {
   HB_SOS_AUTO = 0,  /* pick POLY when the error bound allows it, else DIRECT */
   HB_SOS_POLY = 1,  /* per-tile Taylor moments of the sum of sinusoids (FMA pipe)  */
   HB_SOS_DIRECT = 2, /* one sincos per sinusoid per sample (MUFU pipe)             */
-  HB_SOS_POLY_GATHER = 3 /* POLY, forcing the per-group gather kernel (sparse / very long delay spreads) */
+  HB_SOS_POLY_GATHER = 3, /* POLY, forcing the per-group gather kernel (sparse / very long delay spreads) */
+  HB_SOS_POLY_WINDOW = 4  /* POLY, forcing the sliding-window kernel where it is eligible                   */
 } hb_sos_mode;
 
 typedef enum hb_poly_variant {

@@ -35,14 +35,15 @@ def _run_case(B, L, N, ntx, nrx, T, fs, doppler, max_delay_s, precision, sos_mod
 
 
 @pytest.mark.parametrize("ntx,nrx", [(1, 1), (2, 2), (4, 4), (4, 2), (3, 5), (8, 8), (10, 10)])
-@pytest.mark.parametrize("sos_mode", ["poly", "poly_gather", "direct"])
+@pytest.mark.parametrize("sos_mode", ["poly", "poly_window", "poly_gather", "direct"])
 def test_f32_small_doppler(ntx, nrx, sos_mode):
     err, info = _run_case(B=3, L=12, N=20, ntx=ntx, nrx=nrx, T=1500, fs=30.72e6, doppler=100.0,
                           max_delay_s=1.5e-6, precision="f32", sos_mode=sos_mode, io=np.complex64)
     assert info["mode"] == sos_mode.split("_")[0]
     if sos_mode != "direct":
         # 12 taps over 46 samples: the sliding window reads less shared memory than the gather kernel
-        assert info["variant"] == ("window" if sos_mode == "poly" else "gather"), info
+        want = {"poly": "window", "poly_window": "window", "poly_gather": "gather"}[sos_mode]
+        assert info["variant"] == want, info
     assert err < F32_TOL, (err, info)
 
 
@@ -68,9 +69,23 @@ def test_window_and_gather_agree_on_c2_shape():
                        precision="f32", sos_mode="poly", io=np.complex64)
     e2, i2 = _run_case(B=2, L=23, N=20, ntx=4, nrx=4, T=15344, fs=30.72e6, doppler=100.0, max_delay_s=1.44e-6,
                        precision="f32", sos_mode="poly_gather", io=np.complex64)
-    assert i1["variant"] == "window" and i2["variant"] == "gather"
+    e3, i3 = _run_case(B=2, L=23, N=20, ntx=4, nrx=4, T=15344, fs=30.72e6, doppler=100.0, max_delay_s=1.44e-6,
+                       precision="f32", sos_mode="poly_window", io=np.complex64)
+    assert i1["variant"] == "window" and i2["variant"] == "gather" and i3["variant"] == "window"
+    assert i1["tile"] == 1024 and i1["poly_tile"] == 2048, i1
     assert i1["poly_tile"] % i1["tile"] == 0
-    assert e1 < 1e-6 and e2 < 1e-6, (e1, e2)
+    assert e1 < 1e-6 and e2 < 1e-6 and e3 < 1e-6, (e1, e2, e3)
+
+
+@pytest.mark.parametrize("ntx,nrx", [(1, 1), (2, 2), (3, 2), (4, 4), (8, 4), (6, 7)])
+@pytest.mark.parametrize("T,B", [(1024, 3), (2048, 5), (4094, 2), (15344, 3), (20000, 1)])
+def test_window_variant_tiles_and_edges(ntx, nrx, T, B):
+    """Sliding-window kernel: first / last tiles, frame lengths around tile multiples, partial antenna chunks."""
+    err, info = _run_case(B=B, L=14, N=12, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=250.0, max_delay_s=1.4e-6,
+                          precision="f32", sos_mode="auto", io=np.complex64, seed=T + ntx)
+    assert info["variant"] == "window", info
+    assert info["poly_tile"] % info["tile"] == 0 and info["tile"] in (256, 512, 1024), info
+    assert err < F32_TOL, (err, info)
 
 
 @pytest.mark.parametrize("io", [np.complex64, np.complex128])
