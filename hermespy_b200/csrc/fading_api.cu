@@ -90,6 +90,7 @@ static size_t poly_smem(int ntx_tpl, int tile, int Dpad, int G, int P, int nrx) 
 }
 
 static int window_R(int ntx_tpl) { return ntx_tpl <= 4 ? 8 : 4; }
+static int window_split_of(int) { return 1; }  // threads per output row (window_split<NTX>() in fading_window.cuh)
 
 // Sliding-window variant: eligible when the delay walk fits the masks and reads no more shared memory than the
 // gather kernel would ((dmax + R) / R loads per output and antenna against G).
@@ -117,16 +118,19 @@ static void plan_window(const hb_fading_problem* p, const DelayTable& dt, Plan* 
     if (wp.mask[c + 1] & 0x100u) wp.mask[c] |= 0x100u << R;
   // CTA tile: the largest of {128, 64, 32} threads x R outputs that divides the Taylor window and is not
   // (much) longer than the frame
+  const int split = window_split_of(pl->ntx_tpl);
   int threads = kWindowThreads;
-  while (threads > 32 && (pl->poly_tile % (threads * R) != 0 || (threads / 2) * R >= Tout)) threads /= 2;
+  while (threads > 32 && (pl->poly_tile % (threads / split * R) != 0 || (threads / 2 / split) * R >= Tout)) threads /= 2;
+#ifdef HB_ATTRIBUTION
   if (const char* ev = getenv("HB_WINDOW_THREADS")) {  // experiments only
     const int t = atoi(ev);
-    if ((t == 32 || t == 64 || t == 128) && pl->poly_tile % (t * R) == 0) threads = t;
+    if ((t == 32 || t == 64 || t == 128) && pl->poly_tile % (t / split * R) == 0) threads = t;
   }
+#endif
   pl->threads = threads;
-  pl->tile = threads * R;
+  pl->tile = threads / split * R;
   pl->large_halo = wp.nblk > kWindowHaloSmall;
-  const int PL = kWindowThreads + (pl->large_halo ? kWindowHaloLarge : kWindowHaloSmall);
+  const int PL = kWindowThreads / split + (pl->large_halo ? kWindowHaloLarge : kWindowHaloSmall);
   wp.poly_tile = pl->poly_tile;
   pl->npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
   wp.npoly = pl->npoly;
@@ -330,7 +334,9 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   a.tile = pl.tile;
   a.ntiles = pl.ntiles;
   a.Dpad = pl.Dpad;
+#ifdef HB_ATTRIBUTION
   if (const char* ev = getenv("HB_DBG")) a.dbg = atoi(ev);
+#endif
   if ((size_t)a.ntiles * a.B > 0x7fffffffull) {
     set_error("grid of %zu CTAs exceeds the launch limit; split the batch", (size_t)a.ntiles * a.B);
     return HB_ERR_UNSUPPORTED;

@@ -47,7 +47,7 @@ template <int NTX, int P, int HALO, bool LIN, typename IO>
 static int launch_window_one(const FadingArgs& a, const WindowPlan& wp, int threads, size_t smem,
                              cudaStream_t st) {
   constexpr int R = window_samples_per_thread<NTX>();
-  auto kern = tdl_window_kernel<NTX, P, R, HALO, LIN, IO>;
+  auto kern = tdl_window_kernel<NTX, P, R, HALO, LIN, window_split<NTX>(), IO>;
   if (int e = ensure_smem(kern, smem)) return e;
   dim3 grid((unsigned)((size_t)a.ntiles * a.B));
   kern<<<grid, threads, smem, st>>>(a, wp);

@@ -29,7 +29,7 @@ struct FadingArgs {
   int B, ntx, nrx, T, D, L, K;
   int tile, ntiles, Dpad;
   int tx0, ntx_chunk, accumulate;
-  int dbg;  // attribution experiments only (HB_DBG)
+  int dbg;  // attribution builds only (-DHB_ATTRIBUTION, env HB_DBG: 1 skip staging, 2 skip stores, 4 skip walk)
 };
 
 // ------------------------------------------------------------------------------------------------

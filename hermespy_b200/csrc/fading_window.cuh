@@ -149,19 +149,33 @@ __device__ __forceinline__ void stage_pair(uint32_t dst0, const IO* rowA, const 
 // LIN: the tap gain polynomial is evaluated once per thread and delay group (value and slope at the centre of the
 // thread's R outputs) and extended linearly over them; hb_fading_plan enables it when the neglected curvature
 // sqrt(N+1) ((R-1)/2 omega_max)^2 / 2 stays below the truncation target.
-template <int NTX, int P, int R, int HALO, bool LIN, typename IO>
-__global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
+//
+// SPLIT: threads per output row.  With SPLIT = 2 the two antenna pairs of a 4-antenna chunk belong to two lanes of
+// the same warp (lane, lane ^ 16): each walks the delays for its own pair with half the accumulators and half the
+// window (~100 registers instead of 160 -> 5 CTAs per SM instead of 3), forms the partial spatial mix of its pair
+// for every receive stream, and the two exchange halves with one shuffle per value (reduce-scatter: the first lane
+// finishes and stores the first half of the receive streams, its partner the second half).
+template <int NTX, int P, int R, int HALO, bool LIN, int SPLIT, typename IO>
+__global__ void __launch_bounds__(kWindowThreads, (NTX * R / SPLIT >= 32) ? 3 : (SPLIT == 2 ? 5 : 4))
     tdl_window_kernel(const FadingArgs a, const __grid_constant__ WindowPlan wp) {
   static_assert(R == 4 || R == 8, "R must be 4 or 8");
   static_assert(NTX == 1 || NTX % 2 == 0, "antennas are staged in pairs");
-  constexpr int PL = kWindowThreads + HALO;    // rows per plane
-  constexpr int ES = NTX == 1 ? 8 : 16;        // bytes per staged element (antenna pair)
-  constexpr int NP = NTX == 1 ? 1 : NTX / 2;   // antenna pairs
-  constexpr int PS = R * PL * ES;              // bytes per antenna pair
+  static_assert(SPLIT == 1 || (SPLIT == 2 && NTX == 4), "SPLIT = 2 is written for 4-antenna chunks");
+  constexpr int PL = kWindowThreads / SPLIT + HALO;  // rows per plane
+  constexpr int ES = NTX == 1 ? 8 : 16;              // bytes per staged element (antenna pair)
+  constexpr int NP = NTX == 1 ? 1 : NTX / 2;         // antenna pairs of the chunk
+  constexpr int NA = NTX / SPLIT;                    // antennas per thread
+  constexpr int NPT = NTX == 1 ? 1 : NA / 2;         // antenna pairs per thread
+  constexpr int PS = R * PL * ES;                    // bytes per antenna pair
+  constexpr int RW = 32 / SPLIT;                     // rows per warp
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NT = blockDim.x;
-  const int tile = NT * R;
+  const int NR = NT / SPLIT;  // rows (threads along time) per CTA
+  const int tile = NR * R;
   const int b = blockIdx.x / a.ntiles, q = blockIdx.x - b * a.ntiles, tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int pidx = SPLIT == 1 ? 0 : lane / RW;                         // antenna pair group of this thread
+  const int trow = SPLIT == 1 ? tid : (tid >> 5) * RW + (lane % RW);   // row of this thread
   const int G = wp.num_groups;
   const int Dq = wp.nblk;  // halo rows: Dp = R * nblk
   const int Tout = a.T + a.D;
@@ -174,14 +188,19 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
   {
     const IO* xb = reinterpret_cast<const IO*>(a.x) + ((size_t)b * a.ntx + a.tx0) * a.T;
     const int n0 = q * tile - R * Dq;
+#ifdef HB_ATTRIBUTION
     if (!(a.dbg & 1))
+#endif
 #pragma unroll
-    for (int pr = 0; pr < NP; ++pr)
-      stage_pair<R, PL, ES, IO>(xs + pr * PS, xb + (size_t)(2 * pr) * a.T, xb + (size_t)(2 * pr + 1) * a.T,
-                                2 * pr < a.ntx_chunk, 2 * pr + 1 < a.ntx_chunk, n0, a.T, NT + Dq, tid, NT);
+      for (int pr = 0; pr < NP; ++pr)
+        stage_pair<R, PL, ES, IO>(xs + pr * PS, xb + (size_t)(2 * pr) * a.T, xb + (size_t)(2 * pr + 1) * a.T,
+                                  2 * pr < a.ntx_chunk, 2 * pr + 1 < a.ntx_chunk, n0, a.T, NR + Dq, tid, NT);
+    // coefficients ride the same asynchronous copy group as the tile; the spatial matrix needs a conversion, its
+    // loads are issued before anything waits so that the CTA pays ONE memory round trip, not three
     const int qp = (q * tile) / wp.poly_tile;
     const float2* cb = a.coef + ((size_t)b * wp.npoly + qp) * G * P;
-    for (int c = tid; c < G * P; c += NT) cs[c] = cb[c];
+    const uint32_t csa0 = smem_u32(cs);
+    for (int c = tid; c < G * P; c += NT) cp_async8_full(csa0 + c * 8, cb + c);
     const double2* Sb = a.spatial + (size_t)b * a.nrx * a.ntx;
     for (int c = tid; c < a.nrx * NTX; c += NT) {
       const int irx = c / NTX, j = c - irx * NTX;
@@ -189,36 +208,36 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
       if (j < a.ntx_chunk) v = to_c32(Sb[irx * a.ntx + a.tx0 + j]);
       Ss[c] = v;
     }
-    if constexpr (sizeof(IO) == 8) cp_async_wait_all();
+    cp_async_wait_all();
   }
   __syncthreads();
 
-  const int m0 = q * tile + R * tid;  // first output of this thread
-  if (m0 >= Tout) return;             // no barrier below
+  const int m0 = q * tile + R * trow;  // first output of this thread
+  const unsigned live_mask = __ballot_sync(0xffffffffu, m0 < Tout);
+  if (m0 >= Tout) return;  // no barrier below; a row's lanes leave together
 
-  u64 acc[R][NTX];
+  u64 acc[R][NA];
 #pragma unroll
   for (int u = 0; u < R; ++u)
 #pragma unroll
-    for (int j = 0; j < NTX; ++j) acc[u][j] = 0ull;
+    for (int j = 0; j < NA; ++j) acc[u][j] = 0ull;
 
   {
-    // normalized expansion coordinate of each owned output (LIN: offsets from the centre of the R outputs)
-    float rr[R];
-    float rc;
-    {
-      const int qp = (q * tile) / wp.poly_tile;
-      const float inv = 1.0f / (float)wp.poly_tile;
-      const float r0 = ((float)(m0 - qp * wp.poly_tile) - 0.5f * (float)wp.poly_tile) * inv;
-      rc = fmaf(0.5f * (float)(R - 1), inv, r0);
+    // normalized expansion coordinate: centre of the R outputs (LIN) or every output
+    const int qp = (q * tile) / wp.poly_tile;
+    const float inv = 1.0f / (float)wp.poly_tile;
+    const float r0 = ((float)(m0 - qp * wp.poly_tile) - 0.5f * (float)wp.poly_tile) * inv;
+    const float rc = fmaf(0.5f * (float)(R - 1), inv, r0);
+    float rr[LIN ? 1 : R];
+    if constexpr (!LIN) {
 #pragma unroll
-      for (int u = 0; u < R; ++u) rr[u] = LIN ? ((float)u - 0.5f * (float)(R - 1)) * inv : fmaf((float)u, inv, r0);
+      for (int u = 0; u < R; ++u) rr[u] = fmaf((float)u, inv, r0);
     }
-    // window at d = 0: slot u holds element Dp + R tid + u (plane u, row tid + Dq)
-    u64 w[NTX][R];
-    uint32_t xa = xs + (uint32_t)(tid + Dq) * ES;
+    // window at d = 0: slot u holds element Dp + R trow + u (plane u, row trow + Dq)
+    u64 w[NA][R];
+    uint32_t xa = xs + (uint32_t)(trow + Dq) * ES + pidx * NPT * PS;
 #pragma unroll
-    for (int pr = 0; pr < NP; ++pr)
+    for (int pr = 0; pr < NPT; ++pr)
 #pragma unroll
       for (int u = 0; u < R; ++u) {
         if constexpr (NTX == 1)
@@ -241,11 +260,11 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
       if constexpr (LIN) {
         static_assert(!LIN || P >= 3, "LIN only pays for P >= 3");
         const u64 rcb = pk2(rc, rc);
-        const float fp = (float)(P - 1);
-        u64 hs = fma2(cf[P - 1], pk2(fp, fp), 0ull);  // derivative by Horner: sum_p p c_p rc^(p-1)
+        const float fp = (float)(P - 1) * inv;
+        u64 hs = fma2(cf[P - 1], pk2(fp, fp), 0ull);  // slope per output sample: inv * sum_p p c_p rc^(p-1)
 #pragma unroll
         for (int p = P - 2; p >= 1; --p) {
-          const float fq = (float)p;
+          const float fq = (float)p * inv;
           hs = fma2(hs, rcb, fma2(cf[p], pk2(fq, fq), 0ull));
         }
         u64 hc = cf[P - 1];
@@ -260,18 +279,22 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
     };
     prep();
 
+#ifdef HB_ATTRIBUTION
     const int nblk = (a.dbg & 4) ? 0 : wp.nblk;
+#else
+    const int nblk = wp.nblk;
+#endif
     for (int c = 0; c < nblk; ++c, xa -= ES) {
       const uint32_t mk = wp.mask[c];
       if (mk == 0u) continue;
       const uint32_t pm = mk & 0xffu, lm = mk >> 8;  // lm bit s: the element entering at phase s is needed
 #pragma unroll
       for (int s = 0; s < R; ++s) {
-        // element entering at the NEXT phase, x[m0 - (R c + s + 1)]: plane (R - s - 1), row tid + Dq - c - 1
+        // element entering at the NEXT phase, x[m0 - (R c + s + 1)]: plane (R - s - 1), row trow + Dq - c - 1
         auto load_next = [&]() {
           if ((lm >> (s + 1)) & 1u) {
 #pragma unroll
-            for (int pr = 0; pr < NP; ++pr) {
+            for (int pr = 0; pr < NPT; ++pr) {
               const uint32_t ad = xa + pr * PS + (R - s - 1) * PL * ES;
               if constexpr (NTX == 1)
                 w[0][R - s - 1] = lds_one<-ES>(ad);
@@ -288,7 +311,8 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
           auto mac_u = [&](int u) {
             u64 hv;
             if constexpr (LIN) {
-              hv = fma2(hq[1], pk2(rr[u], rr[u]), hq[0]);
+              const float ku = (float)u - 0.5f * (float)(R - 1);  // immediate operand of the FFMA2
+              hv = fma2(hq[1], pk2(ku, ku), hq[0]);
             } else {
               const u64 rb = pk2(rr[u], rr[u]);
               hv = hq[P - 1];
@@ -299,7 +323,7 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
             const u64 hre = pk2(h.x, h.x);
             const u64 him = pk2(-h.y, h.y);
 #pragma unroll
-            for (int j = 0; j < NTX; ++j) cmac2(acc[u][j], w[j][(u - s + R) % R], hre, him);
+            for (int j = 0; j < NA; ++j) cmac2(acc[u][j], w[j][(u - s + R) % R], hre, him);
           };
           mac_u(R - 1);
           load_next();
@@ -316,22 +340,26 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
   IO* yb = reinterpret_cast<IO*>(a.y) + (size_t)b * a.nrx * Tout + m0;
   const bool vec_ok = sizeof(IO) == 8 && ((Tout & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) &&
                       (m0 + R <= Tout) && !a.accumulate;
-  const uint32_t ssa = smem_u32(Ss);
-  for (int irx = 0; irx < a.nrx; ++irx) {
-    u64 yv[R];
+  const uint32_t ssa = smem_u32(Ss) + pidx * NA * 8;
+  // partial mix over this thread's antennas for receive stream irx
+  auto mix = [&](int irx, u64 (&yv)[R]) {
 #pragma unroll
     for (int u = 0; u < R; ++u) yv[u] = 0ull;
 #pragma unroll
-    for (int j = 0; j < NTX; ++j) {
+    for (int j = 0; j < NA; ++j) {
       u64 sv;
       asm volatile("ld.shared.b64 %0, [%1];" : "=l"(sv) : "r"(ssa + (irx * NTX + j) * 8));
-      const float2 s = upk2(sv);
-      const u64 sre = pk2(s.x, s.x), sim = pk2(-s.y, s.y);
+      const float2 sj = upk2(sv);
+      const u64 sre = pk2(sj.x, sj.x), sim = pk2(-sj.y, sj.y);
 #pragma unroll
       for (int u = 0; u < R; ++u) cmac2(yv[u], acc[u][j], sre, sim);
     }
+  };
+  auto store_row = [&](int irx, const u64 (&yv)[R]) {
     IO* dst = yb + (size_t)irx * Tout;
-    if ((a.dbg & 2) && irx + tid + m0 != -12345) continue;
+#ifdef HB_ATTRIBUTION
+    if ((a.dbg & 2) && irx + tid + m0 != -12345) return;
+#endif
     if (vec_ok) {
       if constexpr (sizeof(IO) == 8) {
 #pragma unroll
@@ -351,9 +379,43 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R >= 32) ? 3 : 4)
         }
       }
     }
+  };
+  if constexpr (SPLIT == 1) {
+    for (int irx = 0; irx < a.nrx; ++irx) {
+      u64 yv[R];
+      mix(irx, yv);
+      store_row(irx, yv);
+    }
+  } else {
+    // reduce-scatter between the two lanes of a row: lane group 0 finishes streams [0, half), group 1 the rest
+    const int half = (a.nrx + 1) >> 1;
+    for (int i = 0; i < half; ++i) {
+      const int ia = i, ib = i + half;  // ib may be past the end for odd nrx (its partial is zero work, unused)
+      u64 ya[R], yb2[R];
+      mix(ia, ya);
+      if (ib < a.nrx) {
+        mix(ib, yb2);
+      } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u) yb2[u] = 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const u64 mine = pidx == 0 ? ya[u] : yb2[u];
+        const u64 send = pidx == 0 ? yb2[u] : ya[u];
+        const u64 recv = __shfl_xor_sync(live_mask, send, RW);
+        const float2 m2 = upk2(mine), r2 = upk2(recv);
+        ya[u] = pk2(m2.x + r2.x, m2.y + r2.y);
+      }
+      const int irx = pidx == 0 ? ia : ib;
+      if (irx < a.nrx) store_row(irx, ya);
+    }
   }
 }
 
+// SPLIT = 2 measured slower on C2 (0.85 ms against 0.74 ms: the duplicated tap-gain evaluation costs more than the
+// extra warps buy -- profiles/r01_window_kernel.md), so every chunk width runs one thread per row.
+template <int NTX> constexpr int window_split() { return 1; }
 template <int NTX> constexpr int window_samples_per_thread() { return NTX <= 4 ? 8 : 4; }
 
 template <int NTX>
