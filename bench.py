@@ -260,11 +260,20 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     alg_bytes = 8.0 * B * (ntx * T + nrx * (T + D))  # complex64 in + out, SURVEY 8(d): 8 (Ntx + Nrx) B / sample
     k = prof["tdl_poly"] if prof["tdl_poly"]["launches"] else prof["tdl_direct"]
-    kname = "tdl_poly_kernel" if prof["tdl_poly"]["launches"] else "tdl_direct_kernel"
+    kname = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel"}.get(info.get("variant"), "tdl_poly_kernel") \
+        if prof["tdl_poly"]["launches"] else "tdl_direct_kernel"
+    traffic = None  # dram bytes of one launch from the committed ncu --set full capture (same kernel, same launch shape)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")) as fh:
+            tr = json.load(fh)
+        if tr["kernel"].startswith(kname) and B == 2048:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        traffic = None
     k_ms = k["ms"] / max(1, k["launches"])
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": k["ms"] / ms_total if ms_total > 0 else None,
                 "other_kernels_ms": {n: v["ms"] / max(1, v["launches"]) for n, v in prof.items()

@@ -128,6 +128,15 @@ def _declare(lib: C.CDLL) -> None:
     ]
     lib.hb_fading_state.restype = C.c_int
     lib.hb_fading_state.argtypes = [C.POINTER(FadingProblem), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+    lib.hb_bit_errors.restype = C.c_int
+    lib.hb_bit_errors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hb_stats_accumulate.restype = C.c_int
+    lib.hb_stats_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+    lib.hb_kron_mix.restype = C.c_int
+    lib.hb_kron_mix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_void_p]
     lib.hb_launch_counts.restype = None
     lib.hb_launch_counts.argtypes = [C.POINTER(C.c_int64)]
     lib.hb_profile_begin.restype = C.c_int

@@ -10,13 +10,11 @@
  *   hb_fading_propagate*   <- MultipathFadingSample._propagate          hermespy/channel/fading/fading.py:371-406
  *                             + MultipathFadingSample.__path_impulse_generator        fading.py:293-343
  *   hb_fading_state        <- MultipathFadingSample.state (SISO tap gains)            fading.py:345-358
- *   hb_fading_sample_params<- MultipathFadingRealization._sample                      fading.py:468-515
- *                             (+ ConsistentUniform.sample, hermespy/channel/consistent.py:475-485)
  *   hb_kron_mix            <- antenna-correlation mixing  R_rx @ S @ R_tx             fading.py:480-489
  *   hb_cdl_*               <- ClusterDelayLineSample.__ray_impulse_generator / _propagate
  *                             hermespy/channel/cdl/cluster_delay_lines.py:409-558
- *   hb_stats_accumulate    <- ScalarEvaluationResult accumulation  hermespy/core/pymonte/scalar.py:101-125
- *                             + BitErrorEvaluator artifact          hermespy/modem/evaluators.py:231-259
+ *   hb_stats_accumulate    <- ScalarEvaluationResult.add_artifact  hermespy/core/pymonte/scalar.py:101-125
+ *   hb_bit_errors          <- BitErrorEvaluator.evaluate/.artifact hermespy/modem/evaluators.py:231-259
  *
  * Layouts (row-major, batch first):
  *   x      [B, Ntx, T]        complex64 (float2) or complex128 (double2), read-only
@@ -192,6 +190,26 @@ HB_API int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y
  * group_delay_out: HOST int32[G] (may be NULL); returns G through num_groups_out. */
 HB_API int hb_cdl_state(const hb_cdl_problem* p, void* h, int32_t* group_delay_out, int32_t* num_groups_out,
                         void* stream);
+
+/* ---- evaluator statistics (the only data that ever crosses GPUs) and antenna-correlation mixing ---------------
+ * Bit errors of num_drops drops (BitErrorEvaluator, evaluators.py:239-259): tx_bits / rx_bits are DEVICE uint8
+ * [num_drops, num_bits] in 0/1 format, tx_len / rx_len (DEVICE int32[num_drops], may be NULL = num_bits) the valid
+ * lengths, the shorter sequence is zero-padded.  Outputs (DEVICE): errors[i] = sum |tx - rx|, bits[i] = max(len),
+ * artifact[i] = errors / bits (np.mean of the indicators; may be NULL). */
+HB_API int hb_bit_errors(const uint8_t* tx_bits, const uint8_t* rx_bits, const int32_t* tx_len, const int32_t* rx_len,
+                         int32_t num_drops, int32_t num_bits, int64_t* errors, int64_t* bits, double* artifact,
+                         void* stream);
+/* Running statistics per grid cell (ScalarEvaluationResult.add_artifact, scalar.py:109-115): for every drop i with
+ * cell[i] == c:  stats[c] += (artifact, artifact^2, 1),  counts[c] += (errors, bits).  stats: DEVICE f64
+ * [num_cells, 3], counts: DEVICE int64 [num_cells, 2] (errors / bits / counts may be NULL).  Fixed summation order.
+ * These buffers are what the evaluator all-reduce (ncclAllReduce SUM) reads. */
+HB_API int hb_stats_accumulate(const double* artifact, const int32_t* cell, const int64_t* errors, const int64_t* bits,
+                               int32_t num_drops, int32_t num_cells, double* stats, int64_t* counts, void* stream);
+/* out[b] = R_rx @ spatial[b] @ R_tx, complex128 DEVICE, FP64 (fading.py:480-489: the covariance matrices themselves,
+ * not their square roots).  r_rx [Nrx, Nrx] / r_tx [Ntx, Ntx] are shared by the batch; NULL = identity.
+ * out may alias spatial. */
+HB_API int hb_kron_mix(const void* r_rx, const void* spatial, const void* r_tx, void* out, int32_t batch,
+                       int32_t num_rx, int32_t num_tx, void* stream);
 
 /* Per-kernel accounting.  Kinds: 0 sos_poly_coef, 1 tdl_poly, 2 tdl_direct, 3 sos_state, 4 cdl_rays,
  * 5 cdl_propagate, 6 spatial_gemm, 7 stats, 8 misc.

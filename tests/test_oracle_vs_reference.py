@@ -160,3 +160,26 @@ def test_dropin_patch_and_restore(ref):
     finally:
         dropin.disable()
     assert MultipathFadingSample._propagate is orig_f and ClusterDelayLineSample._propagate is orig_c
+
+
+def test_stats_oracle_matches_reference_evaluator(ref):
+    """oracle/stats_oracle.py against BitErrorEvaluator.evaluate/.artifact (modem/evaluators.py:231-259)."""
+    from hermespy.modem.evaluators import BitErrorEvaluator
+
+    from oracle import stats_oracle as so
+
+    class _Bits:
+        def __init__(self, bits):
+            self.bits = bits
+
+    rng = np.random.default_rng(7)
+    BitErrorEvaluator.__del__ = lambda self: None  # the bare test instance never registered its hooks
+    for _ in range(20):
+        nt, nr = int(rng.integers(0, 40)), int(rng.integers(1, 40))
+        tx, rx = rng.integers(0, 2, nt), rng.integers(0, 2, nr)
+        ev = BitErrorEvaluator.__new__(BitErrorEvaluator)
+        ev._fetch_dsp_results = lambda tx=tx, rx=rx: (_Bits(tx), _Bits(rx))
+        evaluation = ev.evaluate()
+        errors, bits, artifact = so.bit_errors(tx, rx)
+        assert errors == int(np.sum(evaluation.evaluation)) and bits == len(evaluation.evaluation)
+        assert artifact == evaluation.artifact().to_scalar()
