@@ -222,12 +222,15 @@ def run_ours(args):
     gen.manual_seed(rank)
     x = torch.view_as_complex(torch.randn((B, ntx, T, 2), device=dev, generator=gen, dtype=torch.float32) * (0.5 ** 0.5))
     y = torch.empty((B, nrx, T + D), dtype=torch.complex64, device=dev)
-    stats = torch.zeros(4, dtype=torch.float64, device=dev)  # stand-in for evaluator statistics (sum, sum^2, count, bits)
+    from hermespy_b200.montecarlo import GridStatistics
+
+    # evaluator statistics of the 7 SNR points of C2: the only data that crosses GPUs
+    grid_stats = GridStatistics((7,), device=dev)
 
     def step():
         fading_propagate(x, fb, precision="f32", sos_mode=args.sos_mode, out=y)
         if world > 1:
-            dist.all_reduce(stats)  # the only collective of the path: evaluator statistics
+            grid_stats.all_reduce()  # the only collective of the path: (sum, sum^2, count) + (bit errors, bits)
 
     _, info = fading_propagate(x, fb, out=y, sos_mode=args.sos_mode, return_info=True)
     for _ in range(max(3, args.warmup)):
