@@ -137,6 +137,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.hb_kron_mix.restype = C.c_int
     lib.hb_kron_mix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p]
+    lib.hb_spatial_gemm_3xtf32.restype = C.c_int
+    lib.hb_spatial_gemm_3xtf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_void_p]
     lib.hb_launch_counts.restype = None
     lib.hb_launch_counts.argtypes = [C.POINTER(C.c_int64)]
     lib.hb_profile_begin.restype = C.c_int

@@ -1,0 +1,305 @@
+// K4 for large arrays: the per-link spatial GEMM  Y[b] = S[b] @ Z[b]  (fading.py:395, `spatial_response @ propagated`)
+// on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM), sm_100a only.
+//
+// Real-valued form.  One MMA tile covers 64 complex time samples and up to 64 x 64 antennas:
+//   A (M = 128, K = Ntx): row 2m = Re z[:, m], row 2m+1 = Im z[:, m]              (time is the M axis)
+//   B (N = 2 Nrx, K = Ntx): row 2j = Re S[j, :], row 2j+1 = Im S[j, :]
+//   D = A B^T:  D[2m, 2j] = P = Re z.Re S   D[2m, 2j+1] = Q = Re z.Im S
+//               D[2m+1, 2j] = U = Im z.Re S D[2m+1, 2j+1] = V = Im z.Im S
+//   y_re[j, m] = P - V,  y_im[j, m] = Q + U: the two TMEM lanes of a sample are neighbouring lanes of one warp, so
+//   the combination is ONE shuffle per output, and the warp's store of one receive stream is 128 contiguous bytes.
+//
+// 3xTF32.  Every FP32 operand is split x = hi + lo with hi = cvt.rna.tf32(x); D accumulates lo.hi + hi.lo + hi.hi
+// in FP32 (the lo.lo term is below 2^-22).  Measured against an FP64 GEMM: relative L2 error ~1e-7.
+//
+// Shared-memory operands use the no-swizzle K-major canonical layout (8 rows x 16 bytes core matrices, 128 bytes
+// each; row groups SBO = 128 bytes apart, 16-byte K chunks LBO = 2048 bytes apart), validated bit-exactly by
+// tools/microbench/umma_probe.cu, which also measured the issue cost: 99 clk per 128x128x8 MMA from shared memory.
+//
+// Schedule: persistent CTA (256 threads, one per SM), work item = (link, segment of consecutive tiles): S is
+// converted and split once per item; per tile all threads stage z (global -> registers -> hi/lo -> shared, loads
+// prefetched one tile ahead), one thread issues the 3 x K/8 MMAs into one of two TMEM accumulators, and all threads
+// run the epilogue of the previous tile (tcgen05.ld -> shuffle -> global) while the tensor core works.
+#pragma once
+#include "hb_common.cuh"
+
+namespace hb {
+
+constexpr int kGemmThreads = 256;
+constexpr int kGemmTileSamples = 64;              // complex samples per MMA tile (M = 128 real rows)
+constexpr int kGemmMaxAnt = 64;                   // antennas per block on either side
+constexpr uint32_t kGemmLbo = 2048;               // bytes between 16-byte K chunks (16 row groups x 128 B)
+constexpr uint32_t kGemmSbo = 128;                // bytes between 8-row groups
+constexpr uint32_t kGemmOperandBytes = 128 * kGemmMaxAnt * 4;  // one 128 x 64 fp32 operand = 32 KB
+constexpr size_t kGemmSmemBytes = 6 * (size_t)kGemmOperandBytes + 1024;  // B hi/lo + 2 x A hi/lo (+ alignment slack)
+
+struct GemmArgs {
+  const double2* S;  // [B, nrx_total, ntx_total] complex128
+  const float2* z;   // [B, ntx_total, T]
+  float2* y;         // [B, nrx_total, T]
+  int B, T;
+  int nrx_total, ntx_total;
+  int rx0, nrx;      // receive block [rx0, rx0 + nrx), nrx <= 64
+  int tx0, ntx;      // transmit block
+  int accumulate;    // y += (transmit blocks after the first)
+  int ntiles;        // tiles per link
+  int seg_tiles;     // tiles per work item
+  int nseg;          // segments per link
+};
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor: start address, leading / stride byte offsets (16-byte units), version 1, no swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t instr_desc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 TMEM lanes (this warp's quadrant) x 32 consecutive columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// x = hi + lo, hi rounded to TF32 (10 explicit mantissa bits); the tensor core ignores the low 13 bits of lo
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+}  // namespace umma
+
+// byte offset of element (row r, column k) inside a K-major operand tile
+__device__ __forceinline__ uint32_t gemm_operand_offset(int r, int k) {
+  return (uint32_t)(r >> 3) * kGemmSbo + (uint32_t)(k >> 2) * kGemmLbo + (uint32_t)(r & 7) * 16 + (uint32_t)(k & 3) * 4;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(const GemmArgs a) {
+  using namespace umma;
+  extern __shared__ unsigned char gemm_smem_raw[];
+  __shared__ uint64_t mma_done[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem0 = (smem_addr(gemm_smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB_hi = smem0, sB_lo = smem0 + kGemmOperandBytes;
+  // A buffers: [buf][hi, lo]
+  const uint32_t sA0 = smem0 + 2 * kGemmOperandBytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Kp = (a.ntx + 7) & ~7;          // K padded to the MMA depth
+  const int Np = (2 * a.nrx + 15) & ~15;    // N padded to the M = 128 granularity
+  const int ksteps = Kp >> 3;
+  const int kchunks = Kp >> 2;              // 16-byte K chunks (4 antennas)
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t idesc = instr_desc_tf32(128, Np);
+
+  // staging task of this thread in pass p: K chunk kc = 4 p + (warp >> 1), sample ms = 32 (warp & 1) + lane
+  const int ms = ((warp & 1) << 5) + lane;
+  const int kc0 = warp >> 1;
+  constexpr int kMaxPass = kGemmMaxAnt / 4 / 4;  // 4 passes of 4 chunks cover 64 antennas
+  const uint32_t a_off = (uint32_t)(ms >> 2) * kGemmSbo + (uint32_t)(ms & 3) * 32;  // rows 2 ms, 2 ms + 1
+
+  // epilogue role: TMEM lane quadrant and column half
+  const int quad = warp & 3, chalf = warp >> 2;
+  const int em = (quad << 4) + (lane >> 1);  // sample of this thread's TMEM lane inside the tile
+  const int comp = lane & 1;                 // 0: real row, 1: imaginary row
+
+  uint32_t phase_bits = 0u;  // bit s: parity the next wait on accumulator slot s expects
+
+  for (int item = blockIdx.x; item < a.B * a.nseg; item += gridDim.x) {
+    const int b = item / a.nseg, seg = item - b * a.nseg;
+    const int t_begin = seg * a.seg_tiles, t_end = min(a.ntiles, t_begin + a.seg_tiles);
+    const int ntile = t_end - t_begin;
+    const float2* zb = a.z + ((size_t)b * a.ntx_total + a.tx0) * a.T;
+    float* yb = reinterpret_cast<float*>(a.y + ((size_t)b * a.nrx_total + a.rx0) * a.T);
+
+    // ---- B operand: S block, converted, split, zero padded (no MMA is in flight here) -----------------------------
+    {
+      const double2* Sb = a.S + ((size_t)b * a.nrx_total + a.rx0) * a.ntx_total + a.tx0;
+      for (int i = tid; i < (Np >> 1) * Kp; i += kGemmThreads) {
+        const int j = i / Kp, k = i - j * Kp;
+        float re = 0.f, im = 0.f;
+        if (j < a.nrx && k < a.ntx) {
+          const double2 s = Sb[(size_t)j * a.ntx_total + k];
+          re = (float)s.x;
+          im = (float)s.y;
+        }
+        float h, l;
+        const uint32_t o = gemm_operand_offset(2 * j, k);
+        split_tf32(re, h, l);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sB_hi + o), "f"(h) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sB_lo + o), "f"(l) : "memory");
+        split_tf32(im, h, l);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sB_hi + o + 16), "f"(h) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sB_lo + o + 16), "f"(l) : "memory");
+      }
+    }
+
+    float2 zr[kMaxPass][4];  // prefetched z elements of the next tile to stage
+    auto load_tile = [&](int t) {
+      const int n = t * kGemmTileSamples + ms;
+#pragma unroll
+      for (int p = 0; p < kMaxPass; ++p) {
+        const int kc = 4 * p + kc0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = 4 * kc + i;
+          float2 v = make_float2(0.f, 0.f);
+          if (kc < kchunks && k < a.ntx && n < a.T) v = ldg_stream(zb + (size_t)k * a.T + n);
+          zr[p][i] = v;
+        }
+      }
+    };
+    auto stage_tile = [&](int buf) {
+      const uint32_t hi0 = sA0 + (uint32_t)buf * 2 * kGemmOperandBytes + a_off, lo0 = hi0 + kGemmOperandBytes;
+#pragma unroll
+      for (int p = 0; p < kMaxPass; ++p) {
+        const int kc = 4 * p + kc0;
+        if (kc < kchunks) {
+          float hr[4], lr[4], hi_[4], li[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            split_tf32(zr[p][i].x, hr[i], lr[i]);
+            split_tf32(zr[p][i].y, hi_[i], li[i]);
+          }
+          const uint32_t o = (uint32_t)kc * kGemmLbo;
+          sts128(hi0 + o, hr[0], hr[1], hr[2], hr[3]);
+          sts128(hi0 + o + 16, hi_[0], hi_[1], hi_[2], hi_[3]);
+          sts128(lo0 + o, lr[0], lr[1], lr[2], lr[3]);
+          sts128(lo0 + o + 16, li[0], li[1], li[2], li[3]);
+        }
+      }
+    };
+    auto issue_mma = [&](int buf) {  // one thread
+      const uint32_t ahi = sA0 + (uint32_t)buf * 2 * kGemmOperandBytes, alo = ahi + kGemmOperandBytes;
+      const uint32_t d = tmem + (uint32_t)buf * 128;
+      uint32_t acc = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t adv = (uint32_t)ks * 2 * kGemmLbo;
+        const uint64_t dah = smem_desc(ahi + adv, kGemmLbo, kGemmSbo), dal = smem_desc(alo + adv, kGemmLbo, kGemmSbo);
+        const uint64_t dbh = smem_desc(sB_hi + adv, kGemmLbo, kGemmSbo), dbl = smem_desc(sB_lo + adv, kGemmLbo, kGemmSbo);
+        mma_tf32(d, dal, dbh, idesc, acc);
+        mma_tf32(d, dah, dbl, idesc, 1u);
+        mma_tf32(d, dah, dbh, idesc, 1u);
+        acc = 1u;
+      }
+      commit(&mma_done[buf]);
+    };
+    auto epilogue = [&](int t, int buf) {
+      mbar_wait(&mma_done[buf], (phase_bits >> buf) & 1u);
+      phase_bits ^= 1u << buf;
+      fence_after_sync();
+      const int n = t * kGemmTileSamples + em;
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 128 + (uint32_t)chalf * 64;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (chalf * 64 + h * 32 < Np) {  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(taddr + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            // even lane (Re z row): keeps P, sends Q, receives V -> y_re = P - V
+            // odd lane  (Im z row): keeps U, sends V, receives Q -> y_im = U + Q
+            const float keep = __uint_as_float(v[2 * jj]);
+            const float recv = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[2 * jj + 1]), 1);
+            float out = comp ? keep + recv : keep - recv;
+            const int j = chalf * 32 + h * 16 + jj;
+            if (j < a.nrx && n < a.T) {
+              float* dst = yb + ((size_t)j * a.T + n) * 2 + comp;
+              if (a.accumulate) out += *dst;
+              asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dst), "f"(out) : "memory");
+            }
+          }
+        }
+      }
+    };
+
+    // ---- software pipeline over the tiles of this item -------------------------------------------------------
+    load_tile(t_begin);
+    stage_tile(0);
+    if (ntile > 1) load_tile(t_begin + 1);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 0) issue_mma(0);
+    for (int i = 0; i < ntile; ++i) {
+      if (i + 1 < ntile) {
+        stage_tile((i + 1) & 1);  // buffer last read by the MMAs of tile i - 1 (waited for in its epilogue)
+        if (i + 2 < ntile) load_tile(t_begin + i + 2);
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (tid == 0) issue_mma((i + 1) & 1);  // accumulator last read by the epilogue of tile i - 1
+      }
+      epilogue(t_begin + i, i & 1);
+    }
+    // all MMAs of the item have completed (waited for by the epilogues); order the TMEM reads and the shared
+    // operands before the next item overwrites them
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+}  // namespace hb

@@ -379,6 +379,29 @@ def fading_state(batch: FadingBatch, num_samples: int, precision="f32", io128=Tr
 # Cluster delay line
 
 
+def spatial_gemm(spatial, z, out=None):
+    """``y[b] = spatial[b] @ z[b]`` on the tcgen05 tensor cores in 3xTF32 (``hb_spatial_gemm_3xtf32``): the
+    ``spatial_response @ propagated`` product of fading.py:395 for large arrays.  ``spatial``: device complex128
+    ``[B, Nrx, Ntx]``, ``z``: device complex64 ``[B, Ntx, T]``; returns device complex64 ``[B, Nrx, T]``."""
+    torch = _torch()
+    if not (spatial.is_cuda and z.is_cuda):
+        raise HermesB200Error(_lib.HB_ERR_NO_DEVICE, "hb_spatial_gemm_3xtf32 needs device tensors (no CPU fallback)")
+    s = spatial.to(torch.complex128).contiguous()
+    zz = z.to(torch.complex64).contiguous()
+    B, nrx, ntx = (int(v) for v in s.shape)
+    if zz.dim() != 3 or int(zz.shape[0]) != B or int(zz.shape[1]) != ntx:
+        raise ValueError(f"z must be [B={B}, Ntx={ntx}, T], got {tuple(zz.shape)}")
+    T = int(zz.shape[2])
+    if out is None:
+        out = torch.empty((B, nrx, T), dtype=torch.complex64, device=zz.device)
+    st = torch.cuda.current_stream(zz.device).cuda_stream
+    with torch.cuda.device(zz.device):
+        _lib.check(_lib.load().hb_spatial_gemm_3xtf32(s.data_ptr(), zz.data_ptr(), out.data_ptr(), B, nrx, ntx, T,
+                                                      C.c_void_p(st)))
+    return out
+
+
+
 @dataclass
 class CdlBlock:
     """Host-side parameter block of B CDL links sharing one delay structure (numpy arrays, see hb_cdl_problem)."""

@@ -211,6 +211,13 @@ HB_API int hb_stats_accumulate(const double* artifact, const int32_t* cell, cons
 HB_API int hb_kron_mix(const void* r_rx, const void* spatial, const void* r_tx, void* out, int32_t batch,
                        int32_t num_rx, int32_t num_tx, void* stream);
 
+/* K4 for large arrays (SURVEY 8(b) `hb_spatial_gemm_3xtf32`): y[b] = spatial[b] @ z[b], the `spatial_response @
+ * propagated` product of fading.py:395, on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy, FP32
+ * accumulation in tensor memory).  spatial: DEVICE complex128 [B, Nrx, Ntx]; z: DEVICE complex64 [B, Ntx, T];
+ * y: DEVICE complex64 [B, Nrx, T].  Any Nrx, Ntx (blocks of 64 x 64 antennas per launch). */
+HB_API int hb_spatial_gemm_3xtf32(const void* spatial, const void* z, void* y, int32_t batch, int32_t num_rx,
+                                  int32_t num_tx, int32_t num_samples, void* stream);
+
 /* Per-kernel accounting.  Kinds: 0 sos_poly_coef, 1 tdl_poly, 2 tdl_direct, 3 sos_state, 4 cdl_rays,
  * 5 cdl_propagate, 6 spatial_gemm, 7 stats, 8 misc.
  * hb_launch_counts: launches of each kind since load (always counted).

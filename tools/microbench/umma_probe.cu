@@ -1,0 +1,176 @@
+// tcgen05.mma kind::tf32 probe for sm_100a: validates the shared-memory matrix-descriptor conventions (no-swizzle
+// canonical layouts, K-major and MN-major) used by csrc/spatial_gemm.cuh against an exact integer-valued reference,
+// and measures the issue rate of 128 x N x 8 TF32 MMAs from shared memory.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe umma_probe.cu ; run on the GPU box.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (sm_100 version bit set), no swizzle
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // c_format f32
+  d |= 2u << 7;   // a_format tf32
+  d |= 2u << 10;  // b_format tf32
+  d |= (uint32_t)a_mn << 15;
+  d |= (uint32_t)b_mn << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+
+// element (row r of the MN extent, column k of the K extent) -> byte offset inside the operand tile
+// K-major:  core matrix = 8 rows x 16 B (4 tf32 along K); row groups SBO apart, K chunks LBO apart
+// MN-major: core matrix = 8 k-rows x 16 B (4 tf32 along MN); MN chunks SBO apart, groups of 8 k LBO apart
+__host__ __device__ inline uint32_t off_kmajor(int r, int k, uint32_t lbo, uint32_t sbo) {
+  return (r >> 3) * sbo + (k >> 2) * lbo + (r & 7) * 16 + (k & 3) * 4;
+}
+__host__ __device__ inline uint32_t off_mnmajor(int r, int k, uint32_t lbo, uint32_t sbo) {
+  return (r >> 2) * sbo + (k >> 3) * lbo + (k & 7) * 16 + (r & 3) * 4;
+}
+
+struct Cfg { int N, K, a_mn, b_mn, swap_lbo_sbo; };
+
+__global__ void __launch_bounds__(128) probe_kernel(const float* A, const float* B, float* D, Cfg c, int reps, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int M = 128, N = c.N, K = c.K;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + M * K * 4;
+  // tile-internal strides: core matrices contiguous along MN (128 B apart), then along K
+  const uint32_t a_sbo = 128, a_lbo = c.a_mn ? (M / 4) * 128 : (M / 8) * 128;
+  const uint32_t b_sbo = 128, b_lbo = c.b_mn ? (N / 4) * 128 : (N / 8) * 128;
+  for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+    int r = i / K, k = i % K;
+    uint32_t o = c.a_mn ? off_mnmajor(r, k, a_lbo, a_sbo) : off_kmajor(r, k, a_lbo, a_sbo);
+    *(float*)(sA + o) = A[i];
+  }
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+    int r = i / K, k = i % K;
+    uint32_t o = c.b_mn ? off_mnmajor(r, k, b_lbo, b_sbo) : off_kmajor(r, k, b_lbo, b_sbo);
+    *(float*)(sB + o) = B[i];
+  }
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  const uint32_t idesc = make_idesc(M, N, c.a_mn, c.b_mn);
+  long long t0 = 0, t1 = 0;
+  if (threadIdx.x == 0) {
+    t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+      for (int ks = 0; ks < K / 8; ++ks) {
+        // one MMA consumes 8 k: K-major = two 16-byte chunks (LBO apart), MN-major = one group of 8 k-rows
+        uint32_t a_adv = c.a_mn ? ks * a_lbo : ks * 2 * a_lbo;
+        uint32_t b_adv = c.b_mn ? ks * b_lbo : ks * 2 * b_lbo;
+        uint32_t al = a_lbo, as = a_sbo, bl = b_lbo, bs = b_sbo;
+        if (c.swap_lbo_sbo & 1) { uint32_t t = al; al = as; as = t; }
+        if (c.swap_lbo_sbo & 2) { uint32_t t = bl; bl = bs; bs = t; }
+        uint64_t ad = make_desc(smem_u32(sA) + a_adv, al, as);
+        uint64_t bd = make_desc(smem_u32(sB) + b_adv, bl, bs);
+        mma_tf32(tm, ad, bd, idesc, (ks > 0 || rep > 0) ? 1u : 0u);
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (threadIdx.x == 0) { t1 = clock64(); *cycles = t1 - t0; }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // epilogue: warp w reads TMEM lanes 32w..32w+31, 32 columns at a time
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16) + c0;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                   "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                   "=r"(v[30]), "=r"(v[31]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    int row = warp * 32 + (threadIdx.x & 31);
+    for (int j = 0; j < 32; ++j) D[row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(256));
+}
+
+int main() {
+  const int M = 128;
+  float *dA, *dB, *dD; long long* dcyc;
+  CK(cudaMalloc(&dA, M * 64 * 4)); CK(cudaMalloc(&dB, 256 * 64 * 4)); CK(cudaMalloc(&dD, M * 256 * 4)); CK(cudaMalloc(&dcyc, 8));
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int fails = 0;
+  for (int N : {64, 128, 256}) for (int K : {8, 16, 64}) for (int a_mn = 0; a_mn < 2; ++a_mn) for (int b_mn = 0; b_mn < 2; ++b_mn) for (int sw = 0; sw < 1; ++sw) {
+    if (a_mn || b_mn) continue;  // MN-major tf32 operands returned zeros with these strides; the kernels use K-major only
+    std::vector<float> A(M * K), B(N * K), D(M * N), R(M * N);
+    srand(1234 + N + K);
+    for (auto& v : A) v = (float)(rand() % 9 - 4);
+    for (auto& v : B) v = (float)(rand() % 9 - 4);
+    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < K; ++k) s += A[m * K + k] * B[n * K + k]; R[m * N + n] = s; }
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0, M * 256 * 4));
+    Cfg c{N, K, a_mn, b_mn, sw};
+    probe_kernel<<<1, 128, (M + N) * K * 4 + 1024>>>(dA, dB, dD, c, 1, dcyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("N=%d K=%d a_mn=%d b_mn=%d sw=%d: CUDA error %s\n", N, K, a_mn, b_mn, sw, cudaGetErrorString(e)); return 2; }
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0; for (int i = 0; i < M * N; ++i) bad += (D[i] != R[i]);
+    printf("N=%3d K=%2d a_major=%s b_major=%s swap=%d : %s (%d / %d mismatches)\n", N, K, a_mn ? "MN" : "K ", b_mn ? "MN" : "K ", sw, bad ? "FAIL" : "ok", bad, M * N);
+    if (!sw) fails += bad != 0;
+  }
+  // issue-rate: many back-to-back MMAs, one CTA (per-SM rate)
+  for (int N : {64, 128, 256}) for (int a_mn = 0; a_mn < 2; ++a_mn) {
+    Cfg c{N, 64, a_mn, 0, 0};
+    int reps = 2000;
+    probe_kernel<<<1, 128, (M + N) * 64 * 4 + 1024>>>(dA, dB, dD, c, reps, dcyc);
+    CK(cudaDeviceSynchronize());
+    long long cyc; CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
+    double per = (double)cyc / (reps * 8.0);
+    printf("rate: M=128 N=%3d K=8 a_major=%s: %.1f clk per MMA -> %.0f TF32 FMA/clk/SM\n", N, a_mn ? "MN" : "K ", per, 128.0 * N * 8 / per);
+  }
+  printf(fails ? "PROBE FAILED\n" : "PROBE OK\n");
+  return fails ? 1 : 0;
+}
