@@ -263,7 +263,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     alg_bytes = 8.0 * B * (ntx * T + nrx * (T + D))  # complex64 in + out, SURVEY 8(d): 8 (Ntx + Nrx) B / sample
     k = prof["tdl_poly"] if prof["tdl_poly"]["launches"] else prof["tdl_direct"]
-    kname = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel"}.get(info.get("variant"), "tdl_poly_kernel") \
+    kname = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel", "tma": "tdl_tma_kernel"}.get(info.get("variant"), "tdl_poly_kernel") \
         if prof["tdl_poly"]["launches"] else "tdl_direct_kernel"
     traffic = None  # dram bytes of one launch from the committed ncu --set full capture (same kernel, same launch shape)
     try:
@@ -348,7 +348,7 @@ def main():
     ap.add_argument("--e2e-links", type=int, default=512, help="links per end-to-end step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: shrink the end-to-end leg to one link")
-    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "direct"],
+    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "poly_tma", "direct"],
                     help="kernel selection (profiling / A-B runs); the default lets the planner choose")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -23,9 +23,12 @@ HB_SOS_AUTO = 0
 HB_SOS_POLY = 1
 HB_SOS_DIRECT = 2
 HB_SOS_POLY_GATHER = 3
+HB_SOS_POLY_WINDOW = 4
+HB_SOS_POLY_TMA = 5
 
 HB_VARIANT_GATHER = 0
 HB_VARIANT_WINDOW = 1
+HB_VARIANT_TMA = 2
 
 HB_MAX_TAPS = 256
 

@@ -6,7 +6,7 @@
 #include <mutex>
 #include <vector>
 
-#include "fading_window.cuh"
+#include "fading_tma.cuh"
 
 namespace hb {
 
@@ -34,7 +34,7 @@ static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
     set_error("unknown precision %d", p->precision);
     return HB_ERR_INVALID;
   }
-  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_WINDOW) {
+  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_TMA) {
     set_error("unknown sos_mode %d", p->sos_mode);
     return HB_ERR_INVALID;
   }
@@ -71,6 +71,7 @@ struct Plan {
   size_t smem;
   double bound;
   WindowPlan wp;
+  TmaPlan tp;  // HB_VARIANT_TMA
 };
 
 constexpr size_t kSmemSoftLimit = 72 * 1024;   // keeps >= 3 CTAs per SM
@@ -145,7 +146,58 @@ static void plan_window(const hb_fading_problem* p, const DelayTable& dt, Plan* 
 
 }
 
-static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
+// Persistent TMA-pipelined window kernel (fading_tma.cuh): complex64 frames whose length is a multiple of 16 samples
+// (the frame is described to the copy engine as rows of 16 samples), delays below 128 samples, antenna chunks of at
+// most 4 (R = 8 outputs per thread), frames of at least two 1024-output tiles.
+static bool tma_eligible(const hb_fading_problem* p, const DelayTable& dt, const Plan& pl) {
+  const int Tout = p->num_samples + p->max_delay;
+  const int dmax = dt.group_delay[dt.num_groups - 1];
+  return !p->io_complex128 && pl.ntx_tpl <= 4 && p->num_samples % 16 == 0 && p->num_samples >= 16 &&
+         Tout >= 2 * kTmaTile && dmax / kTmaR + 1 <= kTmaMaxBlocks && pl.poly_tile % kTmaTile == 0 &&
+         p->num_rx <= 64 && (long long)p->num_samples * 8 * p->num_tx < (1ll << 40);
+}
+
+static void plan_tma(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
+  const int Tout = p->num_samples + p->max_delay;
+  TmaPlan& tp = pl->tp;
+  memset(&tp, 0, sizeof(tp));
+  const int dmax = dt.group_delay[dt.num_groups - 1];
+  tp.num_groups = dt.num_groups;
+  tp.nblk = dmax / kTmaR + 1;
+  tp.hrows = (tp.nblk + 1) / 2;
+  tp.rows = kTmaTile / 16 + tp.hrows;
+  tp.poly_tile = pl->poly_tile;
+  tp.npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
+  tp.ntiles = std::max(1, (Tout + kTmaTile - 1) / kTmaTile);
+  tp.coef_stride = (dt.num_groups * pl->P + 1) & ~1;
+  tp.s_stride = (p->num_rx * pl->ntx_tpl + 1) & ~1;
+  tp.nchunks = (p->num_tx + pl->ntx_tpl - 1) / pl->ntx_tpl;
+  tp.stage_bytes = (uint32_t)align_up((size_t)pl->ntx_tpl * tp.rows * 128, 1024);
+  tp.coef_bytes = (uint32_t)tp.coef_stride * 8u;
+  tp.s_bytes = (uint32_t)tp.s_stride * 8u;
+  tp.s_off = (uint32_t)align_up((size_t)(dt.num_groups + 1) * pl->P * 8, 16);
+  tp.aux_bytes = (uint32_t)align_up(tp.s_off + tp.s_bytes + (size_t)pl->ntx_tpl * 8, 16);  // + one row: the epilogue prefetches S
+  for (int g = 0; g < dt.num_groups; ++g) tp.mask[dt.group_delay[g] / kTmaR] |= 1u << (dt.group_delay[g] % kTmaR);
+  auto present = [&](int d) { return d >= 0 && d <= dmax && ((tp.mask[d / kTmaR] >> (d % kTmaR)) & 1u); };
+  for (int d = 1; d <= dmax; d += 2) {  // pair (x[m0-d-1], x[m0-d]) entering at odd d
+    bool need = false;
+    for (int e = d; e <= d + kTmaR; ++e) need = need || present(e);
+    if (need) tp.mask[d / kTmaR] |= 0x100u << (d % kTmaR);
+  }
+  pl->variant = HB_VARIANT_TMA;
+  pl->threads = kTmaThreads;
+  pl->tile = kTmaTile;
+  pl->large_halo = 0;
+  pl->npoly = tp.npoly;
+  pl->Dpad = 16 * tp.hrows;
+  pl->smem = 2 * (size_t)tp.stage_bytes + 3 * (size_t)tp.aux_bytes + 48;  // + two barriers, two release counters, two tile indices
+  const double eps_w = 0.5 * (kTmaR - 1) * p->omega_max;
+  const double curv = sqrt((double)(p->num_sinusoids + 1)) * eps_w * eps_w * 0.5;
+  pl->lin = pl->P >= 3 && pl->P <= 4 && curv <= kPolyTarget;
+  if (pl->lin) pl->bound += curv;
+}
+
+static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl, bool allow_tma = true) {
   const int Tout = p->num_samples + p->max_delay;
   const int K = p->num_sinusoids + 1;
   pl->Dpad = (p->max_delay + 1) & ~1;
@@ -213,8 +265,18 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
       pl->smem = poly_smem(pl->ntx_tpl, pl->tile, pl->Dpad, dt.num_groups, pl->P, p->num_rx);
       pl->taps_per_chunk = 0;
       if (window) {
+        const double bound0 = pl->bound;
         pl->variant = HB_VARIANT_WINDOW;
         plan_window(p, dt, pl);
+        if (allow_tma && p->sos_mode != HB_SOS_POLY_WINDOW && tma_eligible(p, dt, *pl) ) {
+          pl->bound = bound0;
+          plan_tma(p, dt, pl);
+          if (pl->smem > 75 * 1024) {  // would drop below 3 CTAs per SM: keep the cp.async window kernel
+            pl->bound = bound0;
+            pl->variant = HB_VARIANT_WINDOW;
+            plan_window(p, dt, pl);
+          }
+        }
       }
     }
   }
@@ -232,7 +294,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
                (size_t)tpc * K * spsz + (size_t)tpc * 2 * rsz;
   }
   // Very long delay spreads: shrink the antenna chunk before giving up.
-  while (pl->smem > kSmemHardLimit && pl->ntx_tpl > 1 && pl->variant != HB_VARIANT_WINDOW) {
+  while (pl->smem > kSmemHardLimit && pl->ntx_tpl > 1 && pl->variant == HB_VARIANT_GATHER) {
     const int old = pl->ntx_tpl;
     pl->ntx_tpl = old / 2;
     const size_t per_ant = (f64 && pl->mode == HB_SOS_DIRECT ? sizeof(double2) : sizeof(float2)) *
@@ -282,6 +344,56 @@ static int launch_coef_any(int P, const FadingArgs& a, const DelayTable& dt, cud
   }
   set_error("polynomial order %d outside the compiled set", P);
   return HB_ERR_UNSUPPORTED;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  });
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return HB_ERR_CUDA;
+  }
+  *out = fn;
+  return HB_OK;
+}
+
+// x[B, Ntx, T] complex64 as (32 floats, T / 16 rows, Ntx, B); box = one tile + halo of every antenna of a chunk.
+static int make_x_map(const void* x, int B, int ntx, int T, int rows, int ntx_box, CUtensorMap* map) {
+  EncodeTiledFn fn;
+  if (int e = encode_fn(&fn)) return e;
+  const cuuint64_t dims[4] = {32, (cuuint64_t)(T / 16), (cuuint64_t)ntx, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {128, (cuuint64_t)T * 8, (cuuint64_t)T * 8 * (cuuint64_t)ntx};
+  const cuuint32_t box[4] = {32, (cuuint32_t)rows, (cuuint32_t)ntx_box, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (T=%d Ntx=%d B=%d rows=%d)", (int)r, T, ntx, B, rows);
+    return HB_ERR_CUDA;
+  }
+  return HB_OK;
+}
+
+static int launch_chunk_tma(const Plan& pl, const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& map, int grid,
+                            cudaStream_t st) {
+  ProfileScope prof(KIND_TDL_POLY, st);
+  switch (pl.ntx_tpl) {
+    case 1: return launch_tdl_tma<1>(pl.P, pl.lin != 0, a, tp, map, grid, pl.smem, st);
+    case 2: return launch_tdl_tma<2>(pl.P, pl.lin != 0, a, tp, map, grid, pl.smem, st);
+    default: return launch_tdl_tma<4>(pl.P, pl.lin != 0, a, tp, map, grid, pl.smem, st);
+  }
 }
 
 static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& a, const DelayTable& dt,
@@ -342,11 +454,23 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
     return HB_ERR_UNSUPPORTED;
   }
   float2* coef = nullptr;
+  const bool use_tma = pl.mode == HB_SOS_POLY && pl.variant == HB_VARIANT_TMA;
+  a.coef_stride = (dt.num_groups * pl.P + 1) & ~1;
   if (pl.mode == HB_SOS_POLY) {
-    const size_t bytes = sizeof(float2) * (size_t)a.B * pl.npoly * dt.num_groups * pl.P;
-    HB_CUDA(cudaMallocAsync((void**)&coef, bytes, st));
+    // one allocation: coefficients, then (TMA variant) the chunked FP32 spatial matrices
+    const size_t coef_bytes = align_up(sizeof(float2) * (size_t)a.B * pl.npoly * a.coef_stride, 256);
+    const size_t s_bytes = use_tma ? align_up(sizeof(float2) * (size_t)a.B * pl.tp.nchunks * pl.tp.s_stride, 256) : 0;
+    const size_t c_bytes = use_tma ? sizeof(unsigned int) * (size_t)pl.tp.nchunks : 0;
+    HB_CUDA(cudaMallocAsync((void**)&coef, coef_bytes + s_bytes + c_bytes, st));
     a.coef = coef;
     a.spatial32 = nullptr;
+    if (use_tma) {
+      a.spatial32 = reinterpret_cast<float2*>(reinterpret_cast<char*>(coef) + coef_bytes);
+      a.s32_tpl = pl.ntx_tpl;
+      a.s32_stride = pl.tp.s_stride;
+      a.tile_counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(coef) + coef_bytes + s_bytes);
+      a.num_counters = pl.tp.nchunks;
+    }
     FadingArgs ac = a;  // K1 runs over the Taylor windows, which may span several CTA tiles
     ac.tile = pl.poly_tile;
     ac.ntiles = pl.npoly;
@@ -356,11 +480,26 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
     }
   }
   int rc = HB_OK;
+  CUtensorMap xmap;
+  TmaPlan tp;
+  int tma_grid = 0;
+  if (use_tma) {
+    tp = pl.tp;
+    tp.total_tiles = a.B * tp.ntiles;
+    tma_grid = std::min(tp.total_tiles, 3 * device_sm_count());
+    rc = make_x_map(x, a.B, a.ntx, a.T, tp.rows, pl.ntx_tpl, &xmap);
+  }
   for (int tx0 = 0; tx0 < p->num_tx && rc == HB_OK; tx0 += pl.ntx_tpl) {
     a.tx0 = tx0;
     a.ntx_chunk = std::min(pl.ntx_tpl, p->num_tx - tx0);
     a.accumulate = tx0 > 0;
-    rc = launch_chunk(pl, p->precision == HB_F64, p->io_complex128 != 0, a, dt, st);
+    if (use_tma) {
+      tp.chunk = tx0 / pl.ntx_tpl;
+      tp.tile_counter = a.tile_counters + tp.chunk;
+      rc = launch_chunk_tma(pl, a, tp, xmap, tma_grid, st);
+    } else {
+      rc = launch_chunk(pl, p->precision == HB_F64, p->io_complex128 != 0, a, dt, st);
+    }
   }
   if (coef) cudaFreeAsync(coef, st);
   return rc;
@@ -387,7 +526,7 @@ int hb_fading_propagate(const hb_fading_problem* p, const void* x, void* y, void
   DelayTable dt;
   if (int e = build_delay_table(p, &dt)) return e;
   Plan pl;
-  if (int e = make_plan(p, dt, &pl)) return e;
+  if (int e = make_plan(p, dt, &pl, (reinterpret_cast<uintptr_t>(x) & 15) == 0)) return e;
   fill_info(pl, dt, p, info);
   if (int e = require_device()) return e;
   if (p->batch > 0 && (!x || !y || !p->omega || !p->phi || !p->amp || !p->spatial)) {

@@ -24,8 +24,12 @@ struct FadingArgs {
   const double* phi;       // [B, L, K]
   const double* amp;       // [B, L, 2]
   const double2* spatial;  // [B, Nrx, Ntx]
-  const float2* coef;      // [B, ntiles, G, P]  (poly mode)
-  float2* spatial32;       // [B, Nrx, Ntx] FP32 copy of `spatial`, written by K1 when not NULL
+  const float2* coef;      // [B, ntiles, coef_stride >= G * P]  (poly mode)
+  float2* spatial32;       // [B, nchunks, s32_stride >= Nrx * s32_tpl] FP32 copy of `spatial` in antenna chunks of
+                           // s32_tpl transmit antennas (zero padded), written by K1 when not NULL
+  unsigned int* tile_counters;  // [num_counters] work counters of the persistent kernels, zeroed by K1 when not NULL
+  int num_counters;
+  int coef_stride, s32_tpl, s32_stride;
   int B, ntx, nrx, T, D, L, K;
   int tile, ntiles, Dpad;
   int tx0, ntx_chunk, accumulate;
@@ -51,10 +55,16 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
   const double* om_b = a.omega + (size_t)b * a.L * K;
   const double* ph_b = a.phi + (size_t)b * a.L * K;
   const double* am_b = a.amp + (size_t)b * a.L * 2;
-  if (q == 0 && a.spatial32 != nullptr) {  // FP32 spatial matrix for the cp.async-staged kernels
-    const int n = a.nrx * a.ntx;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      a.spatial32[(size_t)b * n + i] = to_c32(a.spatial[(size_t)b * n + i]);
+  if (blockIdx.x == 0 && a.tile_counters != nullptr)
+    for (int i = threadIdx.x; i < a.num_counters; i += blockDim.x) a.tile_counters[i] = 0u;
+  if (q == 0 && a.spatial32 != nullptr) {  // FP32 spatial matrix, chunked, for the bulk-copy staged kernel
+    const int tpl = a.s32_tpl, nch = (a.ntx + tpl - 1) / tpl, per = a.nrx * tpl;
+    for (int i = threadIdx.x; i < nch * per; i += blockDim.x) {
+      const int c = i / per, r = i - c * per, irx = r / tpl, j = c * tpl + (r - irx * tpl);
+      float2 v = make_float2(0.f, 0.f);
+      if (j < a.ntx) v = to_c32(a.spatial[((size_t)b * a.nrx + irx) * a.ntx + j]);
+      a.spatial32[((size_t)b * nch + c) * a.s32_stride + r] = v;
+    }
   }
   for (int g = warp; g < G; g += 4) {
     const int l0 = dt.group_start[g], l1 = dt.group_start[g + 1];
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
       }
     }
     if (lane == 0) {
-      float2* out = const_cast<float2*>(a.coef) + (((size_t)b * a.ntiles + q) * G + g) * P;
+      float2* out = const_cast<float2*>(a.coef) + ((size_t)b * a.ntiles + q) * a.coef_stride + g * P;
 #pragma unroll
       for (int p = 0; p < P; ++p) out[p] = make_float2(accr[p], acci[p]);
     }
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) tdl_poly_kernel(const FadingArgs a,
 
   stage_x_tile<NTX, float2, IO>(xs, a, b, q, W);
   {
-    const float2* cb = a.coef + ((size_t)b * a.ntiles + q) * G * P;
+    const float2* cb = a.coef + ((size_t)b * a.ntiles + q) * a.coef_stride;
     for (int c = tid; c < G * P; c += kThreads) cs[c] = cb[c];
   }
   stage_spatial<NTX, float2>(Ss, a, b);

@@ -1,0 +1,342 @@
+// K3 + K4, persistent TMA-pipelined sliding-window form (sm_100a).
+//
+//   y[:, m] = S @ sum_g h_g(m) x[:, m - d_g]        (gather form of fading.py:385-393, see fading_kernels.cuh)
+//
+// Same arithmetic as tdl_window_kernel (fading_window.cuh): every thread owns R = 8 consecutive outputs and walks
+// the delay axis once with the R inputs of every antenna in a register window.  What changes is how the signal
+// reaches shared memory and how the CTA is scheduled:
+//
+// * The x tile (+ delay halo) of ALL antennas of the chunk arrives by ONE `cp.async.bulk.tensor.4d` (TMA) per tile,
+//   in its natural time-major layout, written by the copy engine -- no LSU instructions, no shared-memory
+//   wavefronts spent on staging (the cp.async staging of the window kernel costs 2.1 of its 4.4 wavefronts per
+//   sample, profiles/r01_window_kernel.md).  The frame is described to the TMA unit as a 4-D tensor
+//   (32 floats = 16 samples, T / 16 rows, Ntx, B): a tile is the box {32, 64 + H, NTX, 1} at row 64 q - H, and the
+//   copy engine zero-fills rows before the frame start / past its end and antennas past the chunk.
+// * SWIZZLE_128B: the 16-byte chunk index of every 128-byte row is XORed with (row & 7).  A thread reads TIME
+//   PAIRS (x[e], x[e+1]) of one antenna with LDS.128; the 8 lanes of a quarter warp are 64 bytes apart in the
+//   natural layout (4-way bank conflict) and land on 8 distinct chunk positions under the swizzle: conflict-free.
+// * Persistent CTAs (3 per SM) with a two-slot ring: the next unclaimed tile (global atomic counter, so that CTAs
+//   sharing an SM unevenly still finish together) is requested right after the walk of tile i released its slot, so every walk starts on data that is already resident, and the streaming stores of
+//   the epilogue overlap the loads of the following tiles.  Taylor coefficients and the FP32 spatial matrix ride
+//   the same mbarrier as 1-D bulk copies (three aux slots: the spatial matrix is still read by the epilogue of
+//   tile i when the request for tile i+2 goes out).
+//
+// Pair walk.  Outputs m0 .. m0+7 (m0 = 8 row), window slot of x[k] = k mod 8.  Stepping to delay d needs x[m0 - d].
+// For odd d the aligned pair (x[m0-d-1], x[m0-d]) holds the elements entering at d and d+1; its slots are free
+// once output 7 of delay d has been accumulated (x[m0-d+7] shares the slot of x[m0-d-1]), and the upper element is
+// first read by output 0 of delay d.  Order at an odd delay: MAC(7), load pair, MAC(1..6), MAC(0).
+#pragma once
+#include <cuda.h>
+
+#include "fading_window.cuh"
+
+namespace hb {
+
+constexpr int kTmaThreads = 128;
+constexpr int kTmaR = 8;
+constexpr int kTmaTile = kTmaThreads * kTmaR;  // 1024 outputs per tile
+constexpr int kTmaMaxHaloRows = 8;             // 16-sample rows of delay halo: d <= 127
+constexpr int kTmaMaxBlocks = 2 * kTmaMaxHaloRows;
+
+struct TmaPlan {
+  int32_t num_groups;
+  int32_t nblk;        // blocks of 8 delays
+  int32_t hrows;       // halo rows (16 samples each) = (nblk + 1) / 2
+  int32_t rows;        // 64 + hrows
+  int32_t poly_tile, npoly;
+  int32_t ntiles;      // tiles per link
+  int32_t total_tiles; // B * ntiles
+  int32_t coef_stride; // float2 elements per (link, Taylor window) block, even
+  int32_t s_stride;    // float2 elements per (link, antenna chunk) block of the FP32 spatial matrix, even
+  int32_t chunk;       // antenna chunk index (tx0 / NTX)
+  int32_t nchunks;
+  unsigned int* tile_counter;  // zeroed by K1; tiles past the first two of every CTA are claimed from it
+  uint32_t stage_bytes;  // NTX * rows * 128 rounded up to 1024
+  uint32_t aux_bytes;    // one aux slot: coefficients (+ one group of padding) + spatial matrix, multiple of 16
+  uint32_t coef_bytes, s_bytes;  // bulk copy sizes (multiples of 16)
+  uint32_t s_off;                // offset of the spatial matrix inside an aux slot
+  // per block c: bits 0..7 "a tap has delay d = 8 c + s"; bits 8..15, odd s only: "the pair entering at d is
+  // needed by a present delay in [d, d + 8]"
+  uint32_t mask[kTmaMaxBlocks + 1];
+};
+
+namespace tma {
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// SWIZZLE_128B of an absolute shared address inside a 1024-byte aligned stage
+__device__ __forceinline__ uint32_t swz(uint32_t addr) { return addr ^ ((addr >> 3) & 0x70u); }
+__device__ __forceinline__ void lds_pair_at(uint32_t addr, u64& lo, u64& hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+}
+
+}  // namespace tma
+
+template <int NTX, int P, bool LIN>
+__global__ void __launch_bounds__(kTmaThreads, 3)
+    tdl_tma_kernel(const FadingArgs a, const __grid_constant__ TmaPlan tp, const __grid_constant__ CUtensorMap xmap) {
+  constexpr int R = kTmaR;
+  constexpr int NH = LIN ? 2 : P;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  // Output row (unit of 8 samples) of this thread.  The lanes of a quarter warp take every other row of a 16-row
+  // span: their 64-byte half rows then share a parity for EVERY block shift of the walk, which is what makes the
+  // swizzled LDS.128 conflict-free (8 consecutive half rows starting at an odd one collide: first and last lane).
+  const int trow = (tid & ~31) + ((lane >> 4) << 4) + 2 * (lane & 7) + ((lane >> 3) & 1);
+  const uint32_t xs0 = smem_u32(smem_raw);                       // two x stages
+  const uint32_t aux0 = xs0 + 2u * tp.stage_bytes;               // three aux slots
+  const uint32_t bar0 = aux0 + 3u * tp.aux_bytes;                // two full barriers, then two release counters
+  const uint32_t cnt0 = bar0 + 16u;
+  const uint32_t tid0 = bar0 + 24u;                              // tile index held by each x slot (-1: no more work)
+  const int Tout = a.T + a.D;
+  const int step = (int)gridDim.x;
+  const uint32_t plane = (uint32_t)tp.rows * 128u;
+
+  auto request = [&](int t, int i) {  // one thread: all copies of tile t (the CTA's i-th) on one barrier
+    const uint32_t bar = bar0 + 8u * (i & 1);
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(tid0 + 4u * (i & 1)), "r"(t < tp.total_tiles ? t : -1) : "memory");
+    if (t >= tp.total_tiles) {  // no more work: complete the phase so that the waiting warps see the end marker
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+      return;
+    }
+    const int b = t / tp.ntiles, q = t - b * tp.ntiles;
+    tma::mbar_expect_tx(bar, (uint32_t)NTX * plane + tp.coef_bytes + tp.s_bytes);
+    tma::load_4d(xs0 + (uint32_t)(i & 1) * tp.stage_bytes, &xmap, 0, q * (kTmaTile / 16) - tp.hrows, a.tx0, b, bar);
+    const uint32_t ax = aux0 + (uint32_t)(i % 3) * tp.aux_bytes;
+    const int qp = (q * kTmaTile) / tp.poly_tile;
+    tma::load_1d(ax, a.coef + ((size_t)b * tp.npoly + qp) * tp.coef_stride, tp.coef_bytes, bar);
+    tma::load_1d(ax + tp.s_off, a.spatial32 + ((size_t)b * tp.nchunks + tp.chunk) * tp.s_stride, tp.s_bytes, bar);
+  };
+
+  if (tid == 0) {
+    if (xs0 & 1023u) __trap();  // the swizzle phase is derived from absolute shared addresses
+    tma::prefetch_map(&xmap);
+    tma::mbar_init(bar0, 1);
+    tma::mbar_init(bar0 + 8, 1);
+    asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(cnt0), "r"(0u) : "memory");
+    tma::fence_barrier_init();
+    request((int)blockIdx.x, 0);  // the first two tiles of every CTA are static, the rest come from the counter
+    request((int)blockIdx.x + step, 1);
+  }
+  __syncthreads();
+
+  const float inv = 1.0f / (float)tp.poly_tile;
+  for (int i = 0;; ++i) {
+    tma::mbar_wait(bar0 + 8u * (i & 1), (uint32_t)(i >> 1) & 1u);
+    int t;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(tid0 + 4u * (i & 1)) : "memory");
+    if (t < 0) break;
+    const int b = t / tp.ntiles, q = t - b * tp.ntiles;
+    const int m0 = q * kTmaTile + R * trow;
+    const bool active = m0 < Tout;
+    const uint32_t xs = xs0 + (uint32_t)(i & 1) * tp.stage_bytes;
+    const uint32_t csa0 = aux0 + (uint32_t)(i % 3) * tp.aux_bytes;
+
+    u64 acc[R][NTX];
+#pragma unroll
+    for (int u = 0; u < R; ++u)
+#pragma unroll
+      for (int j = 0; j < NTX; ++j) acc[u][j] = 0ull;
+
+    if (active) {
+      const int qp = (q * kTmaTile) / tp.poly_tile;
+      const float r0 = ((float)(m0 - qp * tp.poly_tile) - 0.5f * (float)tp.poly_tile) * inv;
+      const float rc = fmaf(0.5f * (float)(R - 1), inv, r0);
+      float rr[LIN ? 1 : R];
+      if constexpr (!LIN) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) rr[u] = fmaf((float)u, inv, r0);
+      }
+      // window at d = 0: x[m0 .. m0+7] = pairs pe0 .. pe0+3, pe0 = 8 hrows + 4 trow (natural offset 16 pe0)
+      u64 w[NTX][R];
+      uint32_t nat = xs + (uint32_t)tp.hrows * 128u + 64u * (uint32_t)trow;  // antenna 0, first pair of the window
+#pragma unroll
+      for (int j = 0; j < NTX; ++j) {
+        const uint32_t sj = tma::swz(nat + (uint32_t)j * plane);
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) tma::lds_pair_at(sj ^ (16u * k), w[j][2 * k], w[j][2 * k + 1]);
+      }
+
+      uint32_t csa = csa0;
+      u64 hp[NH];
+      auto prep = [&]() {  // consume the coefficients of the next delay group (one group past the end is padding)
+        u64 cf[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(cf[p]) : "r"(csa + p * 8));
+        csa += P * 8;
+        if constexpr (LIN) {
+          const u64 rcb = pk2(rc, rc);
+          const float fp = (float)(P - 1) * inv;
+          u64 hs = fma2(cf[P - 1], pk2(fp, fp), 0ull);
+#pragma unroll
+          for (int p = P - 2; p >= 1; --p) {
+            const float fq = (float)p * inv;
+            hs = fma2(hs, rcb, fma2(cf[p], pk2(fq, fq), 0ull));
+          }
+          u64 hc = cf[P - 1];
+#pragma unroll
+          for (int p = P - 2; p >= 0; --p) hc = fma2(hc, rcb, cf[p]);
+          hp[0] = hc;
+          hp[1] = hs;
+        } else {
+#pragma unroll
+          for (int p = 0; p < P; ++p) hp[p] = cf[p];
+        }
+      };
+      prep();
+
+      for (int c = 0; c < tp.nblk; ++c) {
+        nat -= 64u;  // pairs pe0 - 4 (c + 1) .. + 3: the half row entering during this block
+        const uint32_t mk = tp.mask[c];
+        if (mk == 0u) continue;
+        const uint32_t pm = mk & 0xffu, lm = mk >> 8;
+        uint32_t sj[NTX];
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) sj[j] = tma::swz(nat + (uint32_t)j * plane);
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+          auto load_pair = [&]() {  // odd s: (x[m0-d-1], x[m0-d]) -> slots 7 - s, 8 - s; chunk 3 - (s - 1) / 2 of the half row
+            if ((lm >> s) & 1u) {
+#pragma unroll
+              for (int j = 0; j < NTX; ++j)
+                tma::lds_pair_at(sj[j] ^ (16u * (3 - (s >> 1))), w[j][7 - s], w[j][(8 - s) & 7]);
+            }
+          };
+          if ((pm >> s) & 1u) {
+            u64 hq[NH];
+#pragma unroll
+            for (int k = 0; k < NH; ++k) hq[k] = hp[k];
+            prep();
+            auto mac_u = [&](int u) {
+              u64 hv;
+              if constexpr (LIN) {
+                const float ku = (float)u - 0.5f * (float)(R - 1);
+                hv = fma2(hq[1], pk2(ku, ku), hq[0]);
+              } else {
+                const u64 rb = pk2(rr[u], rr[u]);
+                hv = hq[P - 1];
+#pragma unroll
+                for (int p = P - 2; p >= 0; --p) hv = fma2(hv, rb, hq[p]);
+              }
+              const float2 h = upk2(hv);
+              const u64 hre = pk2(h.x, h.x);
+              const u64 him = pk2(-h.y, h.y);
+#pragma unroll
+              for (int j = 0; j < NTX; ++j) cmac2(acc[u][j], w[j][(u - s + R) % R], hre, him);
+            };
+            if (s & 1) {
+              mac_u(R - 1);
+              load_pair();
+#pragma unroll
+              for (int u = 1; u < R - 1; ++u) mac_u(u);
+              mac_u(0);
+            } else {
+#pragma unroll
+              for (int u = 0; u < R; ++u) mac_u(u);
+            }
+          } else if (s & 1) {
+            load_pair();
+          }
+        }
+      }
+    }
+
+    // Release: the LAST warp to finish the walk of this tile requests the tile after next into the slot just
+    // freed.  No CTA-wide barrier: warps drift apart by up to one tile, which overlaps one warp's epilogue
+    // (stores) with the others' walks.  Every warp that counted has finished the epilogue of the previous tile, so
+    // the aux slot (i + 2) % 3 == (i - 1) % 3 is free as well.
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt0 + 4u * (i & 1)) : "memory");
+      if (old == kTmaThreads / 32 - 1) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * (i & 1)), "r"(0u) : "memory");
+        request((int)atomicAdd(tp.tile_counter, 1u) + 2 * step, i + 2);  // dynamic schedule: no tail imbalance
+      }
+    }
+
+    if (active) {
+      // ---- spatial mix  y[irx] = sum_j S[irx][j] z[j]  and direct stores of the thread's R consecutive outputs ----
+      float2* yb = reinterpret_cast<float2*>(a.y) + (size_t)b * a.nrx * Tout + m0;
+      const bool vec_ok = ((Tout & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && (m0 + R <= Tout) &&
+                          !a.accumulate;
+      const uint32_t ssa = csa0 + tp.s_off;
+      u64 snext[NTX];  // row irx + 1 of S is fetched while row irx is applied (the aux slot has padding past the end)
+#pragma unroll
+      for (int j = 0; j < NTX; ++j) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(snext[j]) : "r"(ssa + j * 8));
+      for (int irx = 0; irx < a.nrx; ++irx) {
+        u64 yv[R], scur[NTX];
+#pragma unroll
+        for (int u = 0; u < R; ++u) yv[u] = 0ull;
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) {
+          scur[j] = snext[j];
+          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(snext[j]) : "r"(ssa + ((irx + 1) * NTX + j) * 8));
+        }
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) {
+          const float2 sc = upk2(scur[j]);
+          const u64 sre = pk2(sc.x, sc.x), sim = pk2(-sc.y, sc.y);
+#pragma unroll
+          for (int u = 0; u < R; ++u) cmac2(yv[u], acc[u][j], sre, sim);
+        }
+        float2* dst = yb + (size_t)irx * Tout;
+        if (vec_ok) {
+#pragma unroll
+          for (int u = 0; u < R; u += 2) stg_stream4(dst + u, yv[u], yv[u + 1]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            if (m0 + u < Tout) {
+              float2 v = upk2(yv[u]);
+              if (a.accumulate) {
+                const float2 old = dst[u];
+                v.x += old.x;
+                v.y += old.y;
+              }
+              stg_stream(dst + u, v);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NTX>
+int launch_tdl_tma(int P, bool lin, const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid,
+                   size_t smem, cudaStream_t st);
+
+}  // namespace hb

@@ -1,0 +1,39 @@
+// Explicit instantiations of the TMA-pipelined window kernel for one NTX (separate TUs compile in parallel).
+#pragma once
+#include "fading_inst.cuh"
+#include "fading_tma.cuh"
+
+namespace hb {
+
+template <int NTX, int P, bool LIN>
+static int launch_tma_one(const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid, size_t smem,
+                          cudaStream_t st) {
+  auto kern = tdl_tma_kernel<NTX, P, LIN>;
+  if (int e = ensure_smem(kern, smem)) return e;
+  kern<<<grid, kTmaThreads, smem, st>>>(a, tp, xmap);
+  HB_CUDA(cudaGetLastError());
+  return HB_OK;
+}
+
+template <int NTX>
+int launch_tdl_tma(int P, bool lin, const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid,
+                   size_t smem, cudaStream_t st) {
+  switch (P) {
+    case 1: return launch_tma_one<NTX, 1, false>(a, tp, xmap, grid, smem, st);
+    case 2: return launch_tma_one<NTX, 2, false>(a, tp, xmap, grid, smem, st);
+    case 3:
+      return lin ? launch_tma_one<NTX, 3, true>(a, tp, xmap, grid, smem, st)
+                 : launch_tma_one<NTX, 3, false>(a, tp, xmap, grid, smem, st);
+    case 4:
+      return lin ? launch_tma_one<NTX, 4, true>(a, tp, xmap, grid, smem, st)
+                 : launch_tma_one<NTX, 4, false>(a, tp, xmap, grid, smem, st);
+    case 5: case 6: return launch_tma_one<NTX, 6, false>(a, tp, xmap, grid, smem, st);
+    case 7: case 8: return launch_tma_one<NTX, 8, false>(a, tp, xmap, grid, smem, st);
+    default: set_error("polynomial order %d outside the compiled set", P); return HB_ERR_UNSUPPORTED;
+  }
+}
+
+#define HB_INSTANTIATE_FADING_TMA(NTX) \
+  template int launch_tdl_tma<NTX>(int, bool, const FadingArgs&, const TmaPlan&, const CUtensorMap&, int, size_t, cudaStream_t);
+
+}  // namespace hb

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kWindowThreads, (NTX * R / SPLIT >= 32) ? 3 : 
     // coefficients ride the same asynchronous copy group as the tile; the spatial matrix needs a conversion, its
     // loads are issued before anything waits so that the CTA pays ONE memory round trip, not three
     const int qp = (q * tile) / wp.poly_tile;
-    const float2* cb = a.coef + ((size_t)b * wp.npoly + qp) * G * P;
+    const float2* cb = a.coef + ((size_t)b * wp.npoly + qp) * a.coef_stride;
     const uint32_t csa0 = smem_u32(cs);
     for (int c = tid; c < G * P; c += NT) cp_async8_full(csa0 + c * 8, cb + c);
     const double2* Sb = a.spatial + (size_t)b * a.nrx * a.ntx;

@@ -67,12 +67,15 @@ typedef enum hb_sos_mode {
   HB_SOS_POLY = 1,  /* per-tile Taylor moments of the sum of sinusoids (FMA pipe)  */
   HB_SOS_DIRECT = 2, /* one sincos per sinusoid per sample (MUFU pipe)             */
   HB_SOS_POLY_GATHER = 3, /* POLY, forcing the per-group gather kernel (sparse / very long delay spreads) */
-  HB_SOS_POLY_WINDOW = 4  /* POLY, forcing the sliding-window kernel where it is eligible                   */
+  HB_SOS_POLY_WINDOW = 4, /* POLY, forcing the cp.async-staged sliding-window kernel where it is eligible  */
+  HB_SOS_POLY_TMA = 5     /* POLY, preferring the persistent TMA-pipelined window kernel (what AUTO/POLY pick
+                             for complex64 frames with T % 16 == 0, T + D >= 2048 and delays below 128 samples) */
 } hb_sos_mode;
 
 typedef enum hb_poly_variant {
   HB_VARIANT_GATHER = 0, /* tdl_poly_kernel: one shared-memory read per (delay group, antenna, output)  */
-  HB_VARIANT_WINDOW = 1  /* tdl_window_kernel: register sliding window along the delay axis            */
+  HB_VARIANT_WINDOW = 1, /* tdl_window_kernel: register sliding window along the delay axis            */
+  HB_VARIANT_TMA = 2     /* tdl_tma_kernel: the same walk, persistent CTAs fed by TMA (swizzled time-pair loads) */
 } hb_poly_variant;
 
 /* Launch-uniform description of one batched fading propagation. */

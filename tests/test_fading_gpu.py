@@ -43,7 +43,7 @@ def test_f32_small_doppler(ntx, nrx, sos_mode):
     if sos_mode != "direct":
         # 12 taps over 46 samples: the sliding window reads less shared memory than the gather kernel
         want = {"poly": "window", "poly_window": "window", "poly_gather": "gather"}[sos_mode]
-        assert info["variant"] == want, info
+        assert info["variant"] == want, info  # T + D < 2048: too short for the persistent TMA kernel
     assert err < F32_TOL, (err, info)
 
 
@@ -71,7 +71,7 @@ def test_window_and_gather_agree_on_c2_shape():
                        precision="f32", sos_mode="poly_gather", io=np.complex64)
     e3, i3 = _run_case(B=2, L=23, N=20, ntx=4, nrx=4, T=15344, fs=30.72e6, doppler=100.0, max_delay_s=1.44e-6,
                        precision="f32", sos_mode="poly_window", io=np.complex64)
-    assert i1["variant"] == "window" and i2["variant"] == "gather" and i3["variant"] == "window"
+    assert i1["variant"] == "tma" and i2["variant"] == "gather" and i3["variant"] == "window"
     assert i1["tile"] == 1024 and i1["poly_tile"] == 2048, i1
     assert i1["poly_tile"] % i1["tile"] == 0
     assert e1 < 1e-6 and e2 < 1e-6 and e3 < 1e-6, (e1, e2, e3)
@@ -83,9 +83,50 @@ def test_window_variant_tiles_and_edges(ntx, nrx, T, B):
     """Sliding-window kernel: first / last tiles, frame lengths around tile multiples, partial antenna chunks."""
     err, info = _run_case(B=B, L=14, N=12, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=250.0, max_delay_s=1.4e-6,
                           precision="f32", sos_mode="auto", io=np.complex64, seed=T + ntx)
-    assert info["variant"] == "window", info
+    tma_shape = ntx <= 4 and T % 16 == 0 and T + 43 >= 2048
+    assert info["variant"] == ("tma" if tma_shape else "window"), info
     assert info["poly_tile"] % info["tile"] == 0 and info["tile"] in (256, 512, 1024), info
     assert err < F32_TOL, (err, info)
+
+
+@pytest.mark.parametrize("ntx,nrx", [(1, 1), (2, 2), (3, 2), (4, 4), (4, 9), (2, 64)])
+@pytest.mark.parametrize("T,B,max_delay_s,doppler", [(2048, 5, 1.4e-6, 250.0), (4096, 3, 4.1e-6, 2e3), (15344, 40, 1.44e-6, 100.0),
+                                                      (3056, 7, 0.0, 50.0), (20000, 2, 2.0e-6, 2e4), (16384, 150, 3.0e-7, 0.0)])
+def test_tma_variant(ntx, nrx, T, B, max_delay_s, doppler):
+    """Persistent TMA-pipelined window kernel: ring reuse over many tiles per CTA (B x tiles > 2 x 444 CTAs), halo
+    sizes from 0 to 126 samples, first / last tiles, partial antenna chunks, every compiled Taylor order."""
+    if B >= 40 and ntx * nrx > 16:
+        pytest.skip("oracle time")
+    err, info = _run_case(B=B, L=20, N=12, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=doppler, max_delay_s=max_delay_s,
+                          precision="f32", sos_mode="poly_tma", io=np.complex64, seed=T + ntx)
+    if info["poly_tile"] % 1024 == 0:
+        assert info["variant"] == "tma" and info["tile"] == 1024, info
+    else:  # fast fading: Taylor windows shorter than the 1024-output tile of the persistent kernel
+        assert info["variant"] == "window", info
+    assert err < F32_TOL, (err, info)
+
+
+def test_tma_matches_window_kernel_bitwise_model():
+    """The TMA and cp.async window kernels evaluate the same Taylor model in the same summation order."""
+    import torch
+    from hermespy_b200.kernels import FadingBatch, fading_propagate
+
+    rng = np.random.default_rng(5)
+    p0 = random_fading_params(rng, 23, 20, 4, 4, 30.72e6, 100.0, 1.44e-6, None, None)
+    blk = stack_param_blocks([p0] * 3)
+    fb = FadingBatch.from_numpy(**blk)
+    x = torch.from_numpy(np.stack([random_signal(rng, 4, 15344) for _ in range(3)]).astype(np.complex64)).cuda()
+    y1, i1 = fading_propagate(x, fb, sos_mode="poly_tma", return_info=True)
+    y2, i2 = fading_propagate(x, fb, sos_mode="poly_window", return_info=True)
+    assert i1["variant"] == "tma" and i2["variant"] == "window"
+    assert torch.equal(y1, y2)
+
+
+def test_tma_falls_back_for_unaligned_frames():
+    err, info = _run_case(B=2, L=14, N=12, ntx=4, nrx=4, T=4100, fs=30.72e6, doppler=100.0, max_delay_s=1.4e-6,
+                          precision="f32", sos_mode="poly_tma", io=np.complex64)
+    assert info["variant"] == "window", info  # T % 16 != 0
+    assert err < F32_TOL
 
 
 @pytest.mark.parametrize("io", [np.complex64, np.complex128])

@@ -82,6 +82,8 @@ __global__ void k_lds(float* out, int shift, int stride) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+
+
 template <typename F>
 float timeit(F f) {
   cudaEvent_t e0, e1;
@@ -92,6 +94,42 @@ float timeit(F f) {
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   return ms / 5;
+}
+
+// Mixed issue: NF2 packed FFMA2 and NF1 scalar FFMA per iteration on independent accumulators.  Answers whether the
+// scalar FFMA can use FMA-pipe capacity that FFMA2 leaves idle (total lane-FMAs/clk/SM above 128 would say yes).
+template <int NF2, int NF1>
+__global__ void k_mix(float* out, float a, float b) {
+  u64 acc2[NF2 > 0 ? NF2 : 1];
+  float acc1[NF1 > 0 ? NF1 : 1];
+#pragma unroll
+  for (int i = 0; i < NF2; ++i) acc2[i] = pk(threadIdx.x + i, i);
+#pragma unroll
+  for (int i = 0; i < NF1; ++i) acc1[i] = threadIdx.x + i;
+  u64 x2 = pk(a + threadIdx.x, b + threadIdx.x), h2 = pk(b, b);
+  float x1 = a + threadIdx.x, h1 = b;
+  constexpr int M = NF2 > NF1 ? NF2 : NF1;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      if (i < NF2) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i]) : "l"(x2), "l"(h2));
+      if (i < NF1) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc1[i]) : "f"(x1), "f"(h1));
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < NF2; ++i) { float2 v = upk(acc2[i]); s += v.x + v.y; }
+#pragma unroll
+  for (int i = 0; i < NF1; ++i) s += acc1[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int NF2, int NF1>
+void run_mix(float* out, int clk, int blocks, int thr) {
+  float ms = timeit([&] { k_mix<NF2, NF1><<<blocks, thr>>>(out, 1.0001f, 0.5f); });
+  const double fmas = (double)blocks * thr * ITERS * (2.0 * NF2 + NF1);
+  const double instr = (double)blocks * thr * ITERS * (NF2 + NF1);
+  printf("mix FFMA2 x%2d + FFMA x%2d, %d x %d thr: %.3f ms  %.1f lane-FMA/clk/SM, %.1f instr-lanes/clk/SM\n", NF2, NF1, blocks, thr, ms,
+         fmas / (ms * 1e-3) / 148 / (clk * 1e3), instr / (ms * 1e-3) / 148 / (clk * 1e3));
 }
 
 int main() {
@@ -106,6 +144,17 @@ int main() {
   printf("FFMA2 bcast   : %.3f ms  %.1f instr-lanes/clk/SM -> %.1f TFLOP/s\n", ms, lanes / (ms * 1e-3) / 148 / (clk * 1e3), 4 * lanes / ms * 1e-9);
   ms = timeit([&] { k_ffma2_packed<<<blocks, thr>>>(out, 1.0001f, 0.5f); });
   printf("FFMA2 packed  : %.3f ms  %.1f instr-lanes/clk/SM -> %.1f TFLOP/s\n", ms, lanes / (ms * 1e-3) / 148 / (clk * 1e3), 4 * lanes / ms * 1e-9);
+  run_mix<16, 0>(out, clk, 148 * 4, 512);
+  run_mix<0, 16>(out, clk, 148 * 4, 512);
+  run_mix<8, 8>(out, clk, 148 * 4, 512);
+  run_mix<12, 6>(out, clk, 148 * 4, 512);
+  run_mix<8, 16>(out, clk, 148 * 4, 512);
+  run_mix<16, 8>(out, clk, 148 * 4, 512);
+  // the window kernels' occupancy: 12 warps per SM
+  run_mix<16, 0>(out, clk, 148 * 3, 128);
+  run_mix<32, 0>(out, clk, 148 * 3, 128);
+  run_mix<16, 8>(out, clk, 148 * 3, 128);
+  run_mix<24, 12>(out, clk, 148 * 3, 128);
   cudaFuncSetAttribute(k_lds<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_lds<float4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_lds<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
