@@ -17,8 +17,9 @@ re-realized) is 70000 / links steps of identical shape; K steps are 
              recorded by the library on the launch stream during the timed region, against MEASURED_PEAKS.json.
 * ``cpu_baseline`` the numpy oracle (a restatement of the reference's CPU path) on the host cores, bounded sample.
 
-``--impl reference`` times that CPU path alone (rank 0 only).  The reference itself is Python and does not
-travel to the GPU box, so the port under ``oracle/`` stands in for it (kind "port").
+``--impl reference`` times that CPU path alone (rank 0 only): the UNMODIFIED reference classes when the pip install
+``baseline/_ref`` (tools/install_reference.py, git-ignored, travels with the snapshot) is present (kind
+"reference"), else the numpy port under ``oracle/`` (kind "port").
 """
 from __future__ import annotations
 
@@ -119,18 +120,52 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(seen), "samples": len(self.rows), "power_w_max": max(r[2] for r in self.rows)}
 
 
-# ---- CPU baseline (oracle port of the reference path) ---------------------------------------------------------
-def _cpu_worker(args):
+# ---- CPU baseline: the reference's own code when its install travelled (baseline/_ref), else the oracle port ----
+def cpu_kind():
+    from oracle.refload import REFERENCE_ROOT, reference_available
+
+    # /root/reference is never read at run time on the GPU box; only the pip install under baseline/_ref counts
+    if reference_available() and os.path.realpath(REFERENCE_ROOT).startswith(os.path.realpath(os.path.join(ROOT, "baseline"))):
+        return "reference"
+    return "port"
+
+
+def _cpu_worker_reference(args):
+    """realize + sample + propagate of ONE C2 link per iteration through the unmodified reference classes
+    (hermespy/channel/fading/fading.py:371-406 and its generator :293-343), complex128."""
     seed, n = args
-    from hermespy_b200.batch import sample_fading_links
+    from oracle.refload import load_reference
+
+    load_reference()
+    from hermespy.channel import TDL, CorrelationType, StandardAntennaCorrelation, TDLType
+    from hermespy.core import Signal
+    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+
+    ch = TDL(TDLType.B, rms_delay=C2["rms_delay"], doppler_frequency=C2["doppler"], seed=seed,
+             antenna_correlation=StandardAntennaCorrelation(CorrelationType.MEDIUM))
+    dev = lambda n_: SimulatedDevice(bandwidth=C2["fs"], oversampling_factor=1, carrier_frequency=3.5e9,
+                                     antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (n_, 1, 1)))
+    tx, rx = dev(C2["ntx"]), dev(C2["nrx"])
+    rng = np.random.default_rng(seed)
+    done = 0
+    for _ in range(n):
+        s = ch.realize().sample(tx, rx)
+        x = (rng.standard_normal((C2["ntx"], C2["T"])) + 1j * rng.standard_normal((C2["ntx"], C2["T"]))) / np.sqrt(2)
+        y = s.propagate(Signal.Create(x, C2["fs"], 3.5e9))
+        done += y.num_samples > 0
+    return done
+
+
+def _cpu_worker(args):
+    if cpu_kind() == "reference":
+        return _cpu_worker_reference(args)
+    seed, n = args
     from oracle import fading_oracle as fo
 
     ch = make_channel(seed)
-    blk = None
     rng = np.random.default_rng(seed)
     done = 0
     # same per-link work as the reference: realize + sample + propagate, complex128
-    import hermespy_b200.channel as MC
     from hermespy_b200.core import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
 
     dev = lambda n_: SimulatedDevice(bandwidth=C2["fs"], antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (n_, 1, 1)))
@@ -147,17 +182,37 @@ def _cpu_worker(args):
     return done
 
 
+class CpuPool:
+    """`cores` worker processes (one per host core, as Ray's one actor per core, monte_carlo.py:176,621), warmed up
+    once (imports, page-in); every pass maps a bounded number of links onto them."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores)
+        self.pool.map(_cpu_worker, [(1000 + i, 1) for i in range(cores)])
+        self.seed = 0
+
+    def run(self, links_per_core):
+        t0 = time.perf_counter()
+        done = self.pool.map(_cpu_worker, [(self.seed + i, links_per_core) for i in range(self.cores)])
+        dt = time.perf_counter() - t0
+        self.seed += self.cores
+        return int(sum(done)), dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
 def cpu_reference_pass(links_per_core, cores):
     """One bounded pass of the CPU path on `cores` processes; returns (links, seconds)."""
-    import multiprocessing as mp
-
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(1000 + i, 1) for i in range(cores)])  # warm-up: imports, page-in
-        t0 = time.perf_counter()
-        done = pool.map(_cpu_worker, [(i, links_per_core) for i in range(cores)])
-        dt = time.perf_counter() - t0
-    return int(sum(done)), dt
+    pool = CpuPool(cores)
+    try:
+        return pool.run(links_per_core)
+    finally:
+        pool.close()
 
 
 def run_reference(args):
@@ -166,26 +221,31 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    per_core = 2
-    vals = []
-    for _ in range(args.warmup and 1):
-        cpu_reference_pass(1, cores)
+    # a step = a bounded sample of the C2 workload: per_core links on every host core, sized so that K steps end
+    # within a few minutes (one reference link costs ~0.7 s of one core)
+    per_core = max(1, min(8, 240 // max(1, args.steps + args.warmup)))
+    pool = CpuPool(cores)
+    for _ in range(args.warmup):
+        pool.run(per_core)
     t_total = 0.0
     links_total = 0
     for _ in range(args.steps):
-        links, dt = cpu_reference_pass(per_core, cores)
+        links, dt = pool.run(per_core)
         t_total += dt
         links_total += links
-        vals.append(links * C2["T"] / dt)
+    pool.close()
     value = links_total * C2["T"] / t_total
+    kind = cpu_kind()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": C2["name"], "links_per_step": per_core * cores},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{per_core * cores} links of C2 per step ({per_core} per core process), "
-                                   "realize+sample+propagate in complex128 numpy (oracle port of fading.py:293-406)"},
+                                   "realize+sample+propagate in complex128 numpy (" + (
+                                       "the unmodified reference classes from baseline/_ref" if kind == "reference"
+                                       else "oracle port of fading.py:293-406") + ")"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -316,11 +376,11 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        per_core = 2
+        per_core = 16 if cpu_kind() == "reference" else 4  # 10-30 s of host work
         links, dtc = cpu_reference_pass(per_core, cores)
-        cpu = {"value": links * T / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": links * T / dtc, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
                "sample": f"{links} links of C2 ({per_core} per core process, {cores} processes), realize+sample+propagate "
-                         f"in complex128 numpy; {dtc:.1f} s"}
+                         f"in complex128 numpy ({'unmodified reference from baseline/_ref' if cpu_kind() == 'reference' else 'oracle port'}); {dtc:.1f} s"}
 
     if rank == 0:
         line = {

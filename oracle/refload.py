@@ -1,10 +1,12 @@
 """Loader for the UNMODIFIED HermesPy reference (test infrastructure only).
 
-Only usable where ``/root/reference`` exists (the build container); the GPU box has no
-reference, so nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports this module.
+Usable where ``/root/reference`` exists (the build container) or where its pip install
+``baseline/_ref/`` travelled with the snapshot (the GPU box; made by ``tools/install_reference.py``).
 It is used (a) by ``oracle/make_golden.py`` to generate the committed golden vectors under
-``tests/golden/`` and (b) by CPU tests that pin the numpy restatement in ``oracle/`` against
-the live reference code.
+``tests/golden/``, (b) by CPU tests that pin the numpy restatement in ``oracle/`` against the live
+reference code, (c) by ``tests/test_dropin_gpu.py`` -- the unmodified reference drop loop with the CUDA
+path patched in -- and (d) by ``bench.py --impl reference``.  Everything that uses it skips / falls back
+to the numpy port when no reference is present.
 
 The reference imports ``matplotlib``, ``h5py``, ``ray`` and ``sparse`` at module import time
 and none of them is installed here.  They are replaced by inert stub modules; ``sparse`` gets
@@ -21,7 +23,11 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("HERMES_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the source tree in the build container, else the pip install made from it (`tools/install_reference.py`,
+# git-ignored `baseline/_ref/`, the only form of the reference that travels to the GPU box)
+_CANDIDATES = [os.environ.get("HERMES_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "hermespy"))), "/root/reference")
 
 
 def reference_available() -> bool:

@@ -1,0 +1,219 @@
+"""The UNMODIFIED reference drop loop with the CUDA channel path patched in (north_star acceptance test).
+
+Needs the reference install ``baseline/_ref`` (``tools/install_reference.py``; travels to the GPU box with the
+snapshot, git-ignored) -- skipped where it is absent.  Every scenario is run twice from the same seed: once with
+the reference's own numpy ``_propagate`` and once with ``hermespy_b200.dropin`` enabled.  Realization, sampling,
+modems, noise, synchronization, equalization and ``BitErrorEvaluator`` are reference code in both runs.
+
+* float64 parity mode: received signals agree to <= 1e-12 relative L2 and the per-drop bit-error vectors are
+  IDENTICAL (bit-exact BER counts).
+* float32 mode: propagated signals within the stated 1e-5 relative L2; bit-error totals are reported and may differ
+  by isolated decisions, bounded here.
+"""
+import numpy as np
+import pytest
+
+from oracle.golden_cases import CDL_CASES, CDL_FC, CDL_FS, CDL_SPACING, FADING_CASES, golden_signal
+from oracle.refload import load_reference, reference_available
+from tests.helpers import rel_l2
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not reference_available(), reason="no reference install (baseline/_ref)")]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    load_reference()
+    import hermespy_b200.dropin as dropin
+
+    yield dropin
+    dropin.disable()
+
+
+# ---- scenarios (reference API only) ---------------------------------------------------------------------------
+
+def _siso_rrc_tdl_a(seed):
+    """BASELINE config C1: SISO RRC modem over TDL-A (getting_started/simulation.py)."""
+    from hermespy.channel import TDL, TDLType
+    from hermespy.modem import (BitErrorEvaluator, RootRaisedCosineWaveform, SimplexLink,
+                                SingleCarrierLeastSquaresChannelEstimation, SingleCarrierZeroForcingChannelEqualization)
+    from hermespy.simulation import SimulationScenario
+
+    sc = SimulationScenario(seed=seed)
+    tx = sc.new_device(oversampling_factor=4)
+    rx = sc.new_device(oversampling_factor=4)
+    sc.set_channel(tx, rx, TDL(TDLType.A, doppler_frequency=100.0))
+    link = SimplexLink(seed=seed + 1)
+    tx.transmitters.add(link)
+    rx.receivers.add(link)
+    link.waveform = RootRaisedCosineWaveform(num_preamble_symbols=10, num_data_symbols=100, roll_off=0.9)
+    link.waveform.channel_estimation = SingleCarrierLeastSquaresChannelEstimation()
+    link.waveform.channel_equalization = SingleCarrierZeroForcingChannelEqualization()
+    return _seeded(sc, tx, rx, seed), tx, rx, BitErrorEvaluator(link, link)
+
+
+def _seeded(sc, tx, rx, seed):
+    """The reference leaves the modem and the devices' noise models (re-parented to an unseeded RF block,
+    simulation/rf/block.py:102-106) as independent random roots; pin them so that two runs of the reference itself
+    are reproducible."""
+    tx.noise_model.seed = seed + 2
+    rx.noise_model.seed = seed + 3
+    return sc
+
+
+def _ofdm_link(seed, channel_builder, ntx, nrx, coding=None, carrier=3.5e9, ideal_csi=False):
+    from hermespy.core import Transformation
+    from hermespy.modem import (BitErrorEvaluator, ElementType, GridElement, GridResource, OFDMWaveform,
+                                OrthogonalLeastSquaresChannelEstimation, OrthogonalZeroForcingChannelEqualization,
+                                SimplexLink, SymbolSection)
+    from hermespy.simulation import SimulatedIdealAntenna, SimulatedUniformArray, SimulationScenario
+
+    sc = SimulationScenario(seed=seed)
+    bw = 128 * 240e3  # 30.72 MHz
+    lam = 299792458.0 / carrier
+
+    def dev(n, pos, vel):
+        return sc.new_device(carrier_frequency=carrier, bandwidth=bw, oversampling_factor=1,
+                             pose=Transformation.From_Translation(np.array(pos, float)), velocity=np.array(vel, float),
+                             antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.5 * lam, [n, 1, 1]))
+
+    tx, rx = dev(ntx, (0.0, 0.0, 25.0), (0, 0, 0)), dev(nrx, (100.0, 20.0, 1.5), (10.0, -3.0, 0.0))
+    channel = channel_builder()
+    sc.set_channel(tx, rx, channel)
+    link = SimplexLink(seed=seed + 1)
+    tx.transmitters.add(link)
+    rx.receivers.add(link)
+    res = [GridResource(128 // 5, prefix_ratio=0.0703, elements=[GridElement(ElementType.REFERENCE, 1), GridElement(ElementType.DATA, 4)]),
+           GridResource(128 // 5, prefix_ratio=0.0703, elements=[GridElement(ElementType.DATA, 2), GridElement(ElementType.REFERENCE, 1),
+                                                                  GridElement(ElementType.DATA, 2)])]
+    link.waveform = OFDMWaveform(num_subcarriers=128, dc_suppression=True, grid_resources=res,
+                                 grid_structure=[SymbolSection(64, [0, 1], 5)], modulation_order=4)
+    if ideal_csi:  # MIMO: the reference's least-squares estimator is SISO only; ideal CSI calls sample.state()
+        from hermespy.simulation import OFDMIdealChannelEstimation
+
+        link.waveform.channel_estimation = OFDMIdealChannelEstimation(channel, tx, rx)
+    else:
+        link.waveform.channel_estimation = OrthogonalLeastSquaresChannelEstimation()
+    link.waveform.channel_equalization = OrthogonalZeroForcingChannelEqualization()
+    if coding is not None:  # as tests/integration_tests/test_mimo.py:130-143: the space-time decoder consumes the CSI itself
+        from hermespy.modem import ChannelEqualization
+
+        link.transmit_symbol_coding[0] = coding()
+        link.receive_symbol_coding[0] = coding()
+        link.waveform.channel_equalization = ChannelEqualization()
+    return _seeded(sc, tx, rx, seed), tx, rx, BitErrorEvaluator(link, link)
+
+
+def _ofdm_2x1_alamouti_tdl_b(seed):
+    from hermespy.channel import TDL, TDLType
+    from hermespy.modem import Alamouti
+
+    return _ofdm_link(seed, lambda: TDL(TDLType.B, rms_delay=300e-9, doppler_frequency=100.0), 2, 1, Alamouti, ideal_csi=True)
+
+
+def _ofdm_siso_cdl_c(seed):
+    from hermespy.channel import CDL, CDLType
+
+    return _ofdm_link(seed, lambda: CDL(CDLType.C, 300e-9), 1, 1)
+
+
+def _run(build, seed, snrs_db, drops):
+    """Drop loop over an SNR sweep: per-drop bit-error vectors and received device signals."""
+    from hermespy.core import dB
+    from hermespy.simulation import SNR
+
+    sc, tx, rx, ber = build(seed)
+    errors, received = [], []
+    for snr in snrs_db:
+        rx.noise_level = SNR(dB(snr), tx)
+        for _ in range(drops):
+            drop = sc.drop()
+            errors.append(np.asarray(ber.evaluate().evaluation).copy())
+            received.append(np.asarray(drop.device_receptions[1].impinging_signals[0].view(np.ndarray)).copy())
+    return errors, received
+
+
+# f64 tolerance: 1e-12 for fading; 1e-10 for CDL, whose distance / Doppler phases reach 1e3..1e4 rad (the reference's own
+# rounding there is ~1e-12)
+@pytest.mark.parametrize("build,snrs,drops,tol64", [(_siso_rrc_tdl_a, (0, 4, 8, 12, 16, 20), 25, 1e-12),
+                                                     (_ofdm_2x1_alamouti_tdl_b, (0, 10, 20), 8, 1e-12),
+                                                     (_ofdm_siso_cdl_c, (5, 15), 5, 1e-10)],
+                         ids=["c1_siso_rrc_tdl_a", "ofdm_2x1_alamouti_tdl_b", "ofdm_siso_cdl_c"])
+def test_simulation_drop_loop_bit_exact_ber(ref, build, snrs, drops, tol64):
+    from hermespy_b200 import _lib
+
+    ref.disable()
+    e_ref, r_ref = _run(build, 42, snrs, drops)
+    before = sum(_lib.launch_counts().values())
+    ref.enable(precision="f64")
+    e_64, r_64 = _run(build, 42, snrs, drops)
+    ref.enable(precision="f32")
+    e_32, r_32 = _run(build, 42, snrs, drops)
+    ref.disable()
+    assert sum(_lib.launch_counts().values()) - before >= 2 * len(snrs) * drops  # the CUDA path really ran
+    assert len(e_ref) == len(e_64) == len(snrs) * drops
+    for a, b in zip(r_ref, r_64):
+        assert a.shape == b.shape and rel_l2(b, a) < tol64
+    for a, b in zip(e_ref, e_64):
+        assert np.array_equal(a, b)  # bit-exact per drop, not only in total
+    for a, b in zip(r_ref, r_32):
+        assert rel_l2(b, a) < 1e-5
+    tot_ref, tot_32 = sum(int(e.sum()) for e in e_ref), sum(int(e.sum()) for e in e_32)
+    bits = sum(e.size for e in e_ref)
+    print(f"bits {bits}, errors: reference {tot_ref}, f64 {sum(int(e.sum()) for e in e_64)}, f32 {tot_32}")
+    assert abs(tot_32 - tot_ref) <= max(3, tot_ref // 200)
+
+
+@pytest.mark.parametrize("ci", range(len(FADING_CASES)), ids=[c[0] for c in FADING_CASES])
+def test_reference_fading_samples_propagate_through_dropin(ref, ci):
+    """Every golden fading configuration, built from the REFERENCE classes, propagated by both implementations."""
+    import hermespy.channel as RC
+    from hermespy.core import Signal, Transformation
+    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+
+    name, build, ntx, nrx, fs, T, ptx, prx = FADING_CASES[ci]
+
+    def device(n, pos):
+        return SimulatedDevice(bandwidth=fs, oversampling_factor=1, carrier_frequency=3.5e9,
+                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (n, 1, 1)),
+                               pose=Transformation.From_Translation(np.array(pos, dtype=float)))
+
+    s = build(RC).realize().sample(device(ntx, ptx), device(nrx, prx))
+    sig = Signal.Create(golden_signal(ci, ntx, max(T, 2100)), fs, 3.5e9)
+    ref.disable()
+    y0 = np.asarray(s.propagate(sig).view(np.ndarray))
+    ref.enable(precision="f64")
+    y64 = np.asarray(s.propagate(sig).view(np.ndarray))
+    ref.enable(precision="f32")
+    y32 = np.asarray(s.propagate(sig).view(np.ndarray))
+    ref.disable()
+    assert y0.shape == y64.shape == y32.shape
+    assert rel_l2(y64, y0) < (1e-10 if "extreme" in name else 1e-12)
+    assert rel_l2(y32, y0) < 1e-5
+
+
+@pytest.mark.parametrize("ci", range(len(CDL_CASES)), ids=[c[0] for c in CDL_CASES])
+def test_reference_cdl_samples_propagate_through_dropin(ref, ci):
+    import hermespy.channel as RC
+    from hermespy.core import Signal, Transformation
+    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+
+    name, build, txs, rxs, T = CDL_CASES[ci]
+
+    def dev(spec):
+        dims, rpy, pos, vel = spec
+        return SimulatedDevice(bandwidth=CDL_FS, oversampling_factor=1, carrier_frequency=CDL_FC,
+                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, CDL_SPACING, dims),
+                               pose=Transformation.From_RPY(np.array(rpy, float), np.array(pos, float)),
+                               velocity=np.array(vel, float))
+
+    s = build(RC).realize().sample(dev(txs), dev(rxs))
+    sig = Signal.Create(golden_signal(200 + ci, int(np.prod(txs[0])), T), CDL_FS, CDL_FC)
+    ref.disable()
+    y0 = np.asarray(s.propagate(sig).view(np.ndarray))
+    ref.enable(precision="f64")
+    y64 = np.asarray(s.propagate(sig).view(np.ndarray))
+    ref.enable(precision="f32")
+    y32 = np.asarray(s.propagate(sig).view(np.ndarray))
+    ref.disable()
+    assert rel_l2(y64, y0) < 1e-10
+    assert rel_l2(y32, y0) < 1e-5
