@@ -10,6 +10,9 @@
 
 namespace hb {
 
+// tensor-core spatial product of the large-array path (spatial_gemm.cu)
+int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int nrx, int ntx, int T, cudaStream_t st);
+
 // ---- problem validation / delay groups -------------------------------------------------------------
 static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
   if (!p) {
@@ -67,6 +70,7 @@ static int pick_ntx_template(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 
 
 struct Plan {
   int mode, tile, P, ntiles, Dpad, ntx_tpl, taps_per_chunk;
+  int large_array;  // TMA variant only: z = tap delay lines per transmit antenna, then y = S z on the tensor cores
   int variant, poly_tile, npoly, threads, large_halo, lin;  // POLY: kernel variant, Taylor window, windows per link, CTA size
   size_t smem;
   double bound;
@@ -148,13 +152,15 @@ static void plan_window(const hb_fading_problem* p, const DelayTable& dt, Plan* 
 
 // Persistent TMA-pipelined window kernel (fading_tma.cuh): complex64 frames whose length is a multiple of 16 samples
 // (the frame is described to the copy engine as rows of 16 samples), delays below 128 samples, antenna chunks of at
-// most 4 (R = 8 outputs per thread), frames of at least two 1024-output tiles.
-static bool tma_eligible(const hb_fading_problem* p, const DelayTable& dt, const Plan& pl) {
+// most 4 (R = 8 outputs per thread), frames of at least two 1024-output tiles.  Sparse delay sets are fine: the walk
+// skips empty blocks of 8 delays and loads only the pairs a present delay reads (never more than the gather kernel).
+static bool tma_shape_ok(const hb_fading_problem* p, const DelayTable& dt, int ntx_tpl) {
   const int Tout = p->num_samples + p->max_delay;
   const int dmax = dt.group_delay[dt.num_groups - 1];
-  return !p->io_complex128 && pl.ntx_tpl <= 4 && p->num_samples % 16 == 0 && p->num_samples >= 16 &&
-         Tout >= 2 * kTmaTile && dmax / kTmaR + 1 <= kTmaMaxBlocks && pl.poly_tile % kTmaTile == 0 &&
-         p->num_rx <= 64 && (long long)p->num_samples * 8 * p->num_tx < (1ll << 40);
+  const bool zmode = p->num_tx >= 16 && p->num_rx >= 16;
+  return !p->io_complex128 && ntx_tpl <= 4 && p->num_samples % 16 == 0 && p->num_samples >= 16 &&
+         Tout >= 2 * kTmaTile && dmax / kTmaR + 1 <= kTmaMaxBlocks && (p->num_rx <= 64 || zmode) &&
+         (long long)p->num_samples * 8 * p->num_tx < (1ll << 40);
 }
 
 static void plan_tma(const hb_fading_problem* p, const DelayTable& dt, Plan* pl) {
@@ -170,7 +176,8 @@ static void plan_tma(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
   tp.npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
   tp.ntiles = std::max(1, (Tout + kTmaTile - 1) / kTmaTile);
   tp.coef_stride = (dt.num_groups * pl->P + 1) & ~1;
-  tp.s_stride = (p->num_rx * pl->ntx_tpl + 1) & ~1;
+  const bool zmode = p->num_tx >= 16 && p->num_rx >= 16;  // large arrays: no spatial matrix in the kernel
+  tp.s_stride = zmode ? 2 : (p->num_rx * pl->ntx_tpl + 1) & ~1;
   tp.nchunks = (p->num_tx + pl->ntx_tpl - 1) / pl->ntx_tpl;
   tp.stage_bytes = (uint32_t)align_up((size_t)pl->ntx_tpl * tp.rows * 128, 1024);
   tp.coef_bytes = (uint32_t)tp.coef_stride * 8u;
@@ -208,12 +215,17 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
 
   bool poly = !f64 && p->sos_mode != HB_SOS_DIRECT;
   pl->variant = HB_VARIANT_GATHER;
+  pl->large_array = 0;
   pl->poly_tile = 0;
   pl->npoly = 0;
   pl->threads = kThreads;
   pl->large_halo = 0;
   pl->lin = 0;
   const bool window = poly && p->sos_mode != HB_SOS_POLY_GATHER && window_eligible(dt, pl->ntx_tpl);
+  // large arrays (16 x 16 and more) run the persistent kernel in z mode, chunks of 4 antennas, then the tensor-core GEMM
+  const int tpl_tma = (p->num_tx >= 16 && p->num_rx >= 16) ? 4 : pl->ntx_tpl;
+  const bool tma_shape = poly && allow_tma && p->sos_mode != HB_SOS_POLY_GATHER && p->sos_mode != HB_SOS_POLY_WINDOW &&
+                         tma_shape_ok(p, dt, tpl_tma);
   if (f64 && (p->sos_mode == HB_SOS_POLY || p->sos_mode == HB_SOS_POLY_GATHER)) {
     set_error("HB_F64 parity mode only supports direct evaluation");
     return HB_ERR_UNSUPPORTED;
@@ -229,11 +241,11 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
         // window variant: CTA tiles are 32/64/128 threads x R outputs and must divide the Taylor window, so the
         // window stays a power of two (not longer than the padded frame)
         int tile = std::min(tile0, tile_cap);
-        if (window) {
+        if (window || tma_shape) {
           tile = tile0;
           while (tile > kThreads && tile / 2 >= Tout) tile /= 2;
         }
-        if (!window && poly_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx) > kSmemSoftLimit &&
+        if (!window && !tma_shape && poly_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx) > kSmemSoftLimit &&
             tile > kThreads)
           continue;
         const double bnd = poly_bound(0.5 * p->omega_max * tile, P, K);
@@ -264,19 +276,29 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
       pl->npoly = std::max(1, (Tout + best_tile - 1) / best_tile);
       pl->smem = poly_smem(pl->ntx_tpl, pl->tile, pl->Dpad, dt.num_groups, pl->P, p->num_rx);
       pl->taps_per_chunk = 0;
-      if (window) {
-        const double bound0 = pl->bound;
+      const double bound0 = pl->bound;
+      if (tma_shape && pl->poly_tile % kTmaTile == 0) {
+        const int tpl0 = pl->ntx_tpl;
+        pl->ntx_tpl = tpl_tma;
+        plan_tma(p, dt, pl);
+        if (pl->smem > 75 * 1024) {  // would drop below 3 CTAs per SM: keep the other kernels
+          pl->bound = bound0;
+          pl->variant = HB_VARIANT_GATHER;
+          pl->ntx_tpl = tpl0;
+          pl->tile = pl->poly_tile;
+          pl->npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
+          pl->threads = kThreads;
+          pl->lin = 0;
+          pl->Dpad = (p->max_delay + 1) & ~1;
+          pl->smem = poly_smem(pl->ntx_tpl, pl->tile, pl->Dpad, dt.num_groups, pl->P, p->num_rx);
+        } else {
+          // 16 x 16 antennas and more: 8 Nrx Ntx flop per sample are tensor-core work
+          pl->large_array = p->num_tx >= 16 && p->num_rx >= 16;
+        }
+      }
+      if (pl->variant == HB_VARIANT_GATHER && window) {
         pl->variant = HB_VARIANT_WINDOW;
         plan_window(p, dt, pl);
-        if (allow_tma && p->sos_mode != HB_SOS_POLY_WINDOW && tma_eligible(p, dt, *pl) ) {
-          pl->bound = bound0;
-          plan_tma(p, dt, pl);
-          if (pl->smem > 75 * 1024) {  // would drop below 3 CTAs per SM: keep the cp.async window kernel
-            pl->bound = bound0;
-            pl->variant = HB_VARIANT_WINDOW;
-            plan_window(p, dt, pl);
-          }
-        }
       }
     }
   }
@@ -319,7 +341,8 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
   info->poly_order = pl.P;
   info->num_groups = dt.num_groups;
   info->num_tiles = pl.ntiles;
-  info->launches = (pl.mode == HB_SOS_POLY ? 1 : 0) + chunks;
+  info->launches = (pl.mode == HB_SOS_POLY ? 1 : 0) + chunks +
+                   (pl.large_array ? ((p->num_rx + 63) / 64) * ((p->num_tx + 63) / 64) : 0);
   info->error_bound = pl.bound;
   info->variant = pl.mode == HB_SOS_POLY ? pl.variant : 0;
   info->poly_tile = pl.mode == HB_SOS_POLY ? pl.poly_tile : pl.tile;
@@ -390,9 +413,9 @@ static int launch_chunk_tma(const Plan& pl, const FadingArgs& a, const TmaPlan& 
                             cudaStream_t st) {
   ProfileScope prof(KIND_TDL_POLY, st);
   switch (pl.ntx_tpl) {
-    case 1: return launch_tdl_tma<1>(pl.P, pl.lin != 0, a, tp, map, grid, pl.smem, st);
-    case 2: return launch_tdl_tma<2>(pl.P, pl.lin != 0, a, tp, map, grid, pl.smem, st);
-    default: return launch_tdl_tma<4>(pl.P, pl.lin != 0, a, tp, map, grid, pl.smem, st);
+    case 1: return launch_tdl_tma<1>(pl.P, pl.lin != 0, a.z_mode != 0, a, tp, map, grid, pl.smem, st);
+    case 2: return launch_tdl_tma<2>(pl.P, pl.lin != 0, a.z_mode != 0, a, tp, map, grid, pl.smem, st);
+    default: return launch_tdl_tma<4>(pl.P, pl.lin != 0, a.z_mode != 0, a, tp, map, grid, pl.smem, st);
   }
 }
 
@@ -466,7 +489,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
     a.spatial32 = nullptr;
     if (use_tma) {
       a.spatial32 = reinterpret_cast<float2*>(reinterpret_cast<char*>(coef) + coef_bytes);
-      a.s32_tpl = pl.ntx_tpl;
+      a.s32_tpl = pl.large_array ? 0 : pl.ntx_tpl;  // z mode: the slot is copied but never read, K1 leaves it alone
       a.s32_stride = pl.tp.s_stride;
       a.tile_counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(coef) + coef_bytes + s_bytes);
       a.num_counters = pl.tp.nchunks;
@@ -483,6 +506,16 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   CUtensorMap xmap;
   TmaPlan tp;
   int tma_grid = 0;
+  float2* zbuf = nullptr;
+  if (use_tma && pl.large_array) {
+    const cudaError_t ce = cudaMallocAsync((void**)&zbuf, sizeof(float2) * (size_t)a.B * a.ntx * Tout, st);
+    if (ce != cudaSuccess) {
+      if (coef) cudaFreeAsync(coef, st);
+      return cuda_fail(ce, "cudaMallocAsync(z workspace of the large-array path)");
+    }
+    a.y = zbuf;
+    a.z_mode = 1;
+  }
   if (use_tma) {
     tp = pl.tp;
     tp.total_tiles = a.B * tp.ntiles;
@@ -492,7 +525,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   for (int tx0 = 0; tx0 < p->num_tx && rc == HB_OK; tx0 += pl.ntx_tpl) {
     a.tx0 = tx0;
     a.ntx_chunk = std::min(pl.ntx_tpl, p->num_tx - tx0);
-    a.accumulate = tx0 > 0;
+    a.accumulate = tx0 > 0 && !a.z_mode;
     if (use_tma) {
       tp.chunk = tx0 / pl.ntx_tpl;
       tp.tile_counter = a.tile_counters + tp.chunk;
@@ -500,6 +533,11 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
     } else {
       rc = launch_chunk(pl, p->precision == HB_F64, p->io_complex128 != 0, a, dt, st);
     }
+  }
+  if (zbuf) {
+    if (rc == HB_OK)
+      rc = launch_spatial_gemm(a.spatial, zbuf, reinterpret_cast<float2*>(y), a.B, a.nrx, a.ntx, Tout, st);
+    cudaFreeAsync(zbuf, st);
   }
   if (coef) cudaFreeAsync(coef, st);
   return rc;

@@ -33,6 +33,7 @@ struct FadingArgs {
   int B, ntx, nrx, T, D, L, K;
   int tile, ntiles, Dpad;
   int tx0, ntx_chunk, accumulate;
+  int z_mode;   // large arrays: skip the spatial mix, store the chunk's tap-delay-line outputs z[b, tx0 + j, :] (y has ntx rows)
   int dbg;  // attribution builds only (-DHB_ATTRIBUTION, env HB_DBG: 1 skip staging, 2 skip stores, 4 skip walk)
 };
 
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
   const double* am_b = a.amp + (size_t)b * a.L * 2;
   if (blockIdx.x == 0 && a.tile_counters != nullptr)
     for (int i = threadIdx.x; i < a.num_counters; i += blockDim.x) a.tile_counters[i] = 0u;
-  if (q == 0 && a.spatial32 != nullptr) {  // FP32 spatial matrix, chunked, for the bulk-copy staged kernel
+  if (q == 0 && a.spatial32 != nullptr && a.s32_tpl > 0) {  // FP32 spatial matrix, chunked, for the bulk-copy staged kernel
     const int tpl = a.s32_tpl, nch = (a.ntx + tpl - 1) / tpl, per = a.nrx * tpl;
     for (int i = threadIdx.x; i < nch * per; i += blockDim.x) {
       const int c = i / per, r = i - c * per, irx = r / tpl, j = c * tpl + (r - irx * tpl);

@@ -103,7 +103,7 @@ __device__ __forceinline__ void lds_pair_at(uint32_t addr, u64& lo, u64& hi) {
 
 }  // namespace tma
 
-template <int NTX, int P, bool LIN>
+template <int NTX, int P, bool LIN, bool ZMODE>
 __global__ void __launch_bounds__(kTmaThreads, 3)
     tdl_tma_kernel(const FadingArgs a, const __grid_constant__ TmaPlan tp, const __grid_constant__ CUtensorMap xmap) {
   constexpr int R = kTmaR;
@@ -288,31 +288,9 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
     }
 
     if (active) {
-      // ---- spatial mix  y[irx] = sum_j S[irx][j] z[j]  and direct stores of the thread's R consecutive outputs ----
-      float2* yb = reinterpret_cast<float2*>(a.y) + (size_t)b * a.nrx * Tout + m0;
       const bool vec_ok = ((Tout & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && (m0 + R <= Tout) &&
                           !a.accumulate;
-      const uint32_t ssa = csa0 + tp.s_off;
-      u64 snext[NTX];  // row irx + 1 of S is fetched while row irx is applied (the aux slot has padding past the end)
-#pragma unroll
-      for (int j = 0; j < NTX; ++j) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(snext[j]) : "r"(ssa + j * 8));
-      for (int irx = 0; irx < a.nrx; ++irx) {
-        u64 yv[R], scur[NTX];
-#pragma unroll
-        for (int u = 0; u < R; ++u) yv[u] = 0ull;
-#pragma unroll
-        for (int j = 0; j < NTX; ++j) {
-          scur[j] = snext[j];
-          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(snext[j]) : "r"(ssa + ((irx + 1) * NTX + j) * 8));
-        }
-#pragma unroll
-        for (int j = 0; j < NTX; ++j) {
-          const float2 sc = upk2(scur[j]);
-          const u64 sre = pk2(sc.x, sc.x), sim = pk2(-sc.y, sc.y);
-#pragma unroll
-          for (int u = 0; u < R; ++u) cmac2(yv[u], acc[u][j], sre, sim);
-        }
-        float2* dst = yb + (size_t)irx * Tout;
+      auto store_row = [&](float2* dst, const u64 (&yv)[R]) {
         if (vec_ok) {
 #pragma unroll
           for (int u = 0; u < R; u += 2) stg_stream4(dst + u, yv[u], yv[u + 1]);
@@ -330,13 +308,51 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
             }
           }
         }
+      };
+      if constexpr (ZMODE) {
+        // ---- large arrays: the spatial product runs on the tensor cores (spatial_gemm.cuh); store z itself ----------
+        float2* zb = reinterpret_cast<float2*>(a.y) + ((size_t)b * a.ntx + a.tx0) * Tout + m0;
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) {
+          if (j < a.ntx_chunk) {
+            u64 yv[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) yv[u] = acc[u][j];
+            store_row(zb + (size_t)j * Tout, yv);
+          }
+        }
+      } else {
+        // ---- spatial mix  y[irx] = sum_j S[irx][j] z[j]  and direct stores of the thread's R consecutive outputs ----
+        float2* yb = reinterpret_cast<float2*>(a.y) + (size_t)b * a.nrx * Tout + m0;
+        const uint32_t ssa = csa0 + tp.s_off;
+        u64 snext[NTX];  // row irx + 1 of S is fetched while row irx is applied (the aux slot has padding past the end)
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(snext[j]) : "r"(ssa + j * 8));
+        for (int irx = 0; irx < a.nrx; ++irx) {
+          u64 yv[R], scur[NTX];
+#pragma unroll
+          for (int u = 0; u < R; ++u) yv[u] = 0ull;
+#pragma unroll
+          for (int j = 0; j < NTX; ++j) {
+            scur[j] = snext[j];
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(snext[j]) : "r"(ssa + ((irx + 1) * NTX + j) * 8));
+          }
+#pragma unroll
+          for (int j = 0; j < NTX; ++j) {
+            const float2 sc = upk2(scur[j]);
+            const u64 sre = pk2(sc.x, sc.x), sim = pk2(-sc.y, sc.y);
+#pragma unroll
+            for (int u = 0; u < R; ++u) cmac2(yv[u], acc[u][j], sre, sim);
+          }
+          store_row(yb + (size_t)irx * Tout, yv);
+        }
       }
     }
   }
 }
 
 template <int NTX>
-int launch_tdl_tma(int P, bool lin, const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid,
+int launch_tdl_tma(int P, bool lin, bool zmode, const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid,
                    size_t smem, cudaStream_t st);
 
 }  // namespace hb

@@ -5,18 +5,32 @@
 
 namespace hb {
 
-template <int NTX, int P, bool LIN>
-static int launch_tma_one(const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid, size_t smem,
-                          cudaStream_t st) {
-  auto kern = tdl_tma_kernel<NTX, P, LIN>;
+template <int NTX, int P, bool LIN, bool ZMODE>
+static int launch_tma_z(const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid, size_t smem,
+                        cudaStream_t st) {
+  auto kern = tdl_tma_kernel<NTX, P, LIN, ZMODE>;
   if (int e = ensure_smem(kern, smem)) return e;
   kern<<<grid, kTmaThreads, smem, st>>>(a, tp, xmap);
   HB_CUDA(cudaGetLastError());
   return HB_OK;
 }
 
+// z mode (large arrays, spatial product on the tensor cores) always runs in chunks of 4 antennas
+template <int NTX, int P, bool LIN>
+static int launch_tma_one(const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid, size_t smem,
+                          cudaStream_t st) {
+  if constexpr (NTX == 4) {
+    if (a.z_mode) return launch_tma_z<NTX, P, LIN, true>(a, tp, xmap, grid, smem, st);
+  }
+  if (a.z_mode) {
+    set_error("z mode is compiled for 4-antenna chunks only");
+    return HB_ERR_UNSUPPORTED;
+  }
+  return launch_tma_z<NTX, P, LIN, false>(a, tp, xmap, grid, smem, st);
+}
+
 template <int NTX>
-int launch_tdl_tma(int P, bool lin, const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid,
+int launch_tdl_tma(int P, bool lin, bool /*zmode: carried by a.z_mode*/, const FadingArgs& a, const TmaPlan& tp, const CUtensorMap& xmap, int grid,
                    size_t smem, cudaStream_t st) {
   switch (P) {
     case 1: return launch_tma_one<NTX, 1, false>(a, tp, xmap, grid, smem, st);
@@ -34,6 +48,6 @@ int launch_tdl_tma(int P, bool lin, const FadingArgs& a, const TmaPlan& tp, cons
 }
 
 #define HB_INSTANTIATE_FADING_TMA(NTX) \
-  template int launch_tdl_tma<NTX>(int, bool, const FadingArgs&, const TmaPlan&, const CUtensorMap&, int, size_t, cudaStream_t);
+  template int launch_tdl_tma<NTX>(int, bool, bool, const FadingArgs&, const TmaPlan&, const CUtensorMap&, int, size_t, cudaStream_t);
 
 }  // namespace hb

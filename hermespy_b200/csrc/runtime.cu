@@ -33,6 +33,19 @@ int require_device() {
               e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     return HB_ERR_NO_DEVICE;
   }
+  // Workspaces come from the stream-ordered pool (cudaMallocAsync).  Its default release threshold is 0: every
+  // synchronization hands the memory back to the driver and the next call pays a fresh ~1 ms allocation.  Keep it.
+  static bool pool_kept[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_kept[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    pool_kept[dev] = true;
+  }
   return HB_OK;
 }
 

@@ -12,7 +12,7 @@ F64_TOL = 1e-12  # parity mode
 
 
 def _run_case(B, L, N, ntx, nrx, T, fs, doppler, max_delay_s, precision, sos_mode, io, seed=0, los_doppler=None,
-              rice=None, same_profile=True):
+              rice=None, same_profile=True, large=False):
     import torch
     from hermespy_b200.kernels import FadingBatch, fading_propagate
 
@@ -22,6 +22,11 @@ def _run_case(B, L, N, ntx, nrx, T, fs, doppler, max_delay_s, precision, sos_mod
     for _ in range(B - 1):
         plist.append(random_fading_params(rng, L, N, ntx, nrx, fs, doppler, max_delay_s, los_doppler, rice,
                                           delays=p0.delay, powers=p0.power))
+    if large:  # beyond the reference's 10 x 10 antenna variable: a dense random spatial response per link
+        import dataclasses
+
+        plist = [dataclasses.replace(p, spatial=(rng.standard_normal((nrx, ntx)) + 1j * rng.standard_normal((nrx, ntx))) / np.sqrt(2 * ntx))
+                 for p in plist]
     xs = [random_signal(rng, ntx, T) for _ in range(B)]
     ref = np.stack([fo.propagate(p, x) for p, x in zip(plist, xs)])
     blk = stack_param_blocks(plist)
@@ -104,6 +109,23 @@ def test_tma_variant(ntx, nrx, T, B, max_delay_s, doppler):
     else:  # fast fading: Taylor windows shorter than the 1024-output tile of the persistent kernel
         assert info["variant"] == "window", info
     assert err < F32_TOL, (err, info)
+
+
+@pytest.mark.parametrize("ntx,nrx,T,B", [(16, 16, 2048, 2), (64, 64, 4096, 2), (24, 40, 2048, 1), (33, 17, 3072, 1), (70, 66, 2048, 1)])
+def test_large_array_tensor_core_path(ntx, nrx, T, B):
+    """Config C4 shape and friends: tap delay lines per transmit antenna (z mode of the TMA kernel, chunks of 4), then
+    the spatial product on the tcgen05 tensor cores in 3xTF32 -- one fused C-ABI call, same tolerance."""
+    err, info = _run_case(B=B, L=12, N=20, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=100.0, max_delay_s=1.5e-6,
+                          precision="f32", sos_mode="auto", io=np.complex64, seed=ntx, rice=np.r_[3.0, np.zeros(11)], large=True)
+    assert info["variant"] == "tma", info
+    gemms = ((nrx + 63) // 64) * ((ntx + 63) // 64)
+    assert info["launches"] == 1 + (ntx + 3) // 4 + gemms, info
+    assert err < F32_TOL, (err, info)
+    # the same problem through the chunked fused kernels (no tensor cores)
+    err2, info2 = _run_case(B=B, L=12, N=20, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=100.0, max_delay_s=1.5e-6,
+                            precision="f32", sos_mode="poly_window", io=np.complex64, seed=ntx, rice=np.r_[3.0, np.zeros(11)],
+                            large=True)
+    assert info2["variant"] in ("window", "gather") and err2 < F32_TOL
 
 
 def test_tma_matches_window_kernel_bitwise_model():
