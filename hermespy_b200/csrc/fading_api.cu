@@ -78,6 +78,7 @@ struct Plan {
   TmaPlan tp;  // HB_VARIANT_TMA
 };
 
+constexpr size_t kTmaSmemBudget = 226 * 1024;  // dynamic shared memory of the one persistent TMA CTA per SM
 constexpr size_t kSmemSoftLimit = 72 * 1024;   // keeps >= 3 CTAs per SM
 constexpr size_t kSmemHardLimit = 200 * 1024;  // below the 227 KB per-CTA maximum
 constexpr double kPolyTarget = 5e-8;           // truncation bound, relative to the RMS tap gain
@@ -197,7 +198,11 @@ static void plan_tma(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
   pl->large_halo = 0;
   pl->npoly = tp.npoly;
   pl->Dpad = 16 * tp.hrows;
-  pl->smem = 2 * (size_t)tp.stage_bytes + 3 * (size_t)tp.aux_bytes + 48;  // + two barriers, two release counters, two tile indices
+  tp.slot_bytes = (uint32_t)align_up((size_t)tp.stage_bytes + tp.aux_bytes, 1024);
+  // ring depth: as many slots as fit the 227 KB of one SM (one CTA per SM), at most kTmaMaxSlots
+  const size_t ctl = 16 * kTmaMaxSlots + 16;  // barriers, release counters, tile indices, ticket counter
+  tp.num_slots = (int)std::min<size_t>(kTmaMaxSlots, (kTmaSmemBudget - ctl) / tp.slot_bytes);
+  pl->smem = (size_t)tp.num_slots * tp.slot_bytes + ctl;
   const double eps_w = 0.5 * (kTmaR - 1) * p->omega_max;
   const double curv = sqrt((double)(p->num_sinusoids + 1)) * eps_w * eps_w * 0.5;
   pl->lin = pl->P >= 3 && pl->P <= 4 && curv <= kPolyTarget;
@@ -281,7 +286,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
         const int tpl0 = pl->ntx_tpl;
         pl->ntx_tpl = tpl_tma;
         plan_tma(p, dt, pl);
-        if (pl->smem > 75 * 1024) {  // would drop below 3 CTAs per SM: keep the other kernels
+        if (pl->tp.num_slots < 4) {  // ring too shallow to hide the loads: keep the other kernels
           pl->bound = bound0;
           pl->variant = HB_VARIANT_GATHER;
           pl->ntx_tpl = tpl0;
@@ -323,7 +328,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
                            ((size_t)(pl->tile + pl->Dpad) + p->num_rx);
     pl->smem -= per_ant * (old - pl->ntx_tpl);
   }
-  if (pl->smem > kSmemHardLimit) {
+  if (pl->variant != HB_VARIANT_TMA && pl->smem > kSmemHardLimit) {
     set_error("delay spread of %d samples needs %zu bytes of shared memory per CTA (limit %zu)", p->max_delay,
               pl->smem, kSmemHardLimit);
     return HB_ERR_UNSUPPORTED;
@@ -341,7 +346,7 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
   info->poly_order = pl.P;
   info->num_groups = dt.num_groups;
   info->num_tiles = pl.ntiles;
-  info->launches = (pl.mode == HB_SOS_POLY ? 1 : 0) + chunks +
+  info->launches = (pl.mode == HB_SOS_POLY ? 1 : 0) + (pl.large_array ? 1 : chunks) +
                    (pl.large_array ? ((p->num_rx + 63) / 64) * ((p->num_tx + 63) / 64) : 0);
   info->error_bound = pl.bound;
   info->variant = pl.mode == HB_SOS_POLY ? pl.variant : 0;
@@ -518,11 +523,11 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   }
   if (use_tma) {
     tp = pl.tp;
-    tp.total_tiles = a.B * tp.ntiles;
-    tma_grid = std::min(tp.total_tiles, 3 * device_sm_count());
+    tp.total_tiles = a.B * tp.ntiles * (pl.large_array ? tp.nchunks : 1);  // z mode: every chunk in ONE launch
+    tma_grid = std::min(tp.total_tiles, device_sm_count());
     rc = make_x_map(x, a.B, a.ntx, a.T, tp.rows, pl.ntx_tpl, &xmap);
   }
-  for (int tx0 = 0; tx0 < p->num_tx && rc == HB_OK; tx0 += pl.ntx_tpl) {
+  for (int tx0 = 0; tx0 < (a.z_mode ? 1 : p->num_tx) && rc == HB_OK; tx0 += pl.ntx_tpl) {
     a.tx0 = tx0;
     a.ntx_chunk = std::min(pl.ntx_tpl, p->num_tx - tx0);
     a.accumulate = tx0 > 0 && !a.z_mode;

@@ -67,47 +67,71 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
       a.spatial32[((size_t)b * nch + c) * a.s32_stride + r] = v;
     }
   }
+  constexpr int NV = 2 * P <= 2 ? 2 : (2 * P <= 4 ? 4 : (2 * P <= 8 ? 8 : 16));  // values to reduce, padded to 2^k
   for (int g = warp; g < G; g += 4) {
     const int l0 = dt.group_start[g], l1 = dt.group_start[g + 1];
     const double shift = centre - (double)dt.group_delay[g];
-    float accr[P], acci[P];
+    float v[NV];  // v[2p] = Re, v[2p+1] = Im of moment p
 #pragma unroll
-    for (int p = 0; p < P; ++p) accr[p] = acci[p] = 0.f;
-    for (int idx = l0 * K + lane; idx < l1 * K; idx += 32) {
-      const int l = idx / K, k = idx - l * K;
-      const double om = om_b[idx];
-      const double th = fma(om, shift, ph_b[idx]);
-      double t = th * kInvTwoPi;
-      t -= rint(t);
-      float s, c;
-      sincosf((float)(t * kTwoPi), &s, &c);
-      const float am = (float)am_b[2 * l + (k != 0)];
-      float tr = am * c, ti = am * s;
-      const float u = (float)(om * (double)a.tile);
-      accr[0] += tr;
-      acci[0] += ti;
+    for (int i = 0; i < NV; ++i) v[i] = 0.f;
+    for (int l = l0; l < l1; ++l) {
+      const float a_los = (float)am_b[2 * l], a_nlos = (float)am_b[2 * l + 1];
+      for (int k = lane; k < K; k += 32) {  // fixed (tap, sinusoid) -> lane assignment: deterministic sums
+        const int idx = l * K + k;
+        const double om = om_b[idx];
+        const double th = fma(om, shift, ph_b[idx]);
+        double t = th * kInvTwoPi;
+        t -= rint(t);
+        float s, c;
+        sincosf((float)(t * kTwoPi), &s, &c);
+        const float am = k != 0 ? a_nlos : a_los;
+        float tr = am * c, ti = am * s;
+        const float u = (float)(om * (double)a.tile);
+        v[0] += tr;
+        v[1] += ti;
 #pragma unroll
-      for (int p = 1; p < P; ++p) {
-        const float f = u * (1.0f / (float)p);
-        const float nr = -ti * f, ni = tr * f;  // times (j u / p)
-        tr = nr;
-        ti = ni;
-        accr[p] += tr;
-        acci[p] += ti;
+        for (int p = 1; p < P; ++p) {
+          const float f = u * (1.0f / (float)p);
+          const float nr = -ti * f, ni = tr * f;  // times (j u / p)
+          tr = nr;
+          ti = ni;
+          v[2 * p] += tr;
+          v[2 * p + 1] += ti;
+        }
       }
     }
+    // Transposing butterfly: at every step a lane keeps one half of its values and sends the other half, so the NV
+    // sums cost NV - 1 + (5 - log2 NV) shuffles instead of 5 NV.  Value i ends up in the lanes whose top log2(NV)
+    // bits spell i (bit 4 = most significant).
+    int n = NV, off = 16;
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
+    for (int step = 0; step < 4; ++step) {
+      if (n > 1) {
+        const int half = n >> 1;
+        const bool upper = (lane & off) != 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        accr[p] += __shfl_xor_sync(0xffffffffu, accr[p], o);
-        acci[p] += __shfl_xor_sync(0xffffffffu, acci[p], o);
+        for (int i = 0; i < NV / 2; ++i) {
+          if (i < half) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        n = half;
+        off >>= 1;
       }
     }
-    if (lane == 0) {
-      float2* out = const_cast<float2*>(a.coef) + ((size_t)b * a.ntiles + q) * a.coef_stride + g * P;
+    for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    constexpr int LOG = NV == 2 ? 1 : (NV == 4 ? 2 : (NV == 8 ? 3 : 4));
+    if ((lane & ((32 >> LOG) - 1)) == 0) {
+      // index of the value this lane holds: lane bit 4 is the most significant index bit
+      int vi = 0;
 #pragma unroll
-      for (int p = 0; p < P; ++p) out[p] = make_float2(accr[p], acci[p]);
+      for (int sft = 0; sft < LOG; ++sft) vi |= ((lane >> (4 - sft)) & 1) << (LOG - 1 - sft);
+      if (vi < 2 * P) {
+        float* out = reinterpret_cast<float*>(const_cast<float2*>(a.coef) + ((size_t)b * a.ntiles + q) * a.coef_stride + g * P);
+        out[vi] = v[0];
+      }
     }
   }
 }

@@ -32,9 +32,11 @@
 
 namespace hb {
 
-constexpr int kTmaThreads = 128;
+constexpr int kTmaThreads = 384;   // ONE persistent CTA per SM: 12 independent warps
 constexpr int kTmaR = 8;
-constexpr int kTmaTile = kTmaThreads * kTmaR;  // 1024 outputs per tile
+constexpr int kTmaTile = 1024;     // outputs per tile = 4 warp parts of 32 rows x 8 outputs
+constexpr int kTmaParts = 4;
+constexpr int kTmaMaxSlots = 6;    // ring depth (tiles resident or in flight per SM)
 constexpr int kTmaMaxHaloRows = 8;             // 16-sample rows of delay halo: d <= 127
 constexpr int kTmaMaxBlocks = 2 * kTmaMaxHaloRows;
 
@@ -52,7 +54,9 @@ struct TmaPlan {
   int32_t nchunks;
   unsigned int* tile_counter;  // zeroed by K1; tiles past the first two of every CTA are claimed from it
   uint32_t stage_bytes;  // NTX * rows * 128 rounded up to 1024
-  uint32_t aux_bytes;    // one aux slot: coefficients (+ one group of padding) + spatial matrix, multiple of 16
+  uint32_t aux_bytes;    // coefficients (+ one group of padding) + spatial matrix (+ one row), multiple of 16
+  uint32_t slot_bytes;   // one ring slot: x stage + aux, multiple of 1024
+  int32_t num_slots;     // ring depth, <= kTmaMaxSlots
   uint32_t coef_bytes, s_bytes;  // bulk copy sizes (multiples of 16)
   uint32_t s_off;                // offset of the spatial matrix inside an aux slot
   // per block c: bits 0..7 "a tap has delay d = 8 c + s"; bits 8..15, odd s only: "the pair entering at d is
@@ -104,65 +108,86 @@ __device__ __forceinline__ void lds_pair_at(uint32_t addr, u64& lo, u64& hi) {
 }  // namespace tma
 
 template <int NTX, int P, bool LIN, bool ZMODE>
-__global__ void __launch_bounds__(kTmaThreads, 3)
+__global__ void __launch_bounds__(kTmaThreads, 1)
     tdl_tma_kernel(const FadingArgs a, const __grid_constant__ TmaPlan tp, const __grid_constant__ CUtensorMap xmap) {
   constexpr int R = kTmaR;
   constexpr int NH = LIN ? 2 : P;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  // Output row (unit of 8 samples) of this thread.  The lanes of a quarter warp take every other row of a 16-row
-  // span: their 64-byte half rows then share a parity for EVERY block shift of the walk, which is what makes the
-  // swizzled LDS.128 conflict-free (8 consecutive half rows starting at an odd one collide: first and last lane).
-  const int trow = (tid & ~31) + ((lane >> 4) << 4) + 2 * (lane & 7) + ((lane >> 3) & 1);
-  const uint32_t xs0 = smem_u32(smem_raw);                       // two x stages
-  const uint32_t aux0 = xs0 + 2u * tp.stage_bytes;               // three aux slots
-  const uint32_t bar0 = aux0 + 3u * tp.aux_bytes;                // two full barriers, then two release counters
-  const uint32_t cnt0 = bar0 + 16u;
-  const uint32_t tid0 = bar0 + 24u;                              // tile index held by each x slot (-1: no more work)
+  // Output row (unit of 8 samples) of a lane inside its 32-row part.  The lanes of a quarter warp take every other
+  // row of a 16-row span: their 64-byte half rows then share a parity for EVERY block shift of the walk, which is
+  // what makes the swizzled LDS.128 conflict-free (8 consecutive half rows starting at an odd one collide).
+  const int lrow = ((lane >> 4) << 4) + 2 * (lane & 7) + ((lane >> 3) & 1);
+  const int NS = tp.num_slots;
+  const uint32_t ring0 = smem_u32(smem_raw);                     // NS slots of (x stage | aux)
+  const uint32_t bar0 = ring0 + (uint32_t)NS * tp.slot_bytes;    // NS full barriers
+  const uint32_t cnt0 = bar0 + 8u * kTmaMaxSlots;                // NS release counters (parts finished)
+  const uint32_t tid0 = cnt0 + 4u * kTmaMaxSlots;                // tile index held by each slot (-1: no more work)
+  const uint32_t next0 = tid0 + 4u * kTmaMaxSlots;               // next (tile, part) ticket of this CTA
   const int Tout = a.T + a.D;
   const int step = (int)gridDim.x;
   const uint32_t plane = (uint32_t)tp.rows * 128u;
 
-  auto request = [&](int t, int i) {  // one thread: all copies of tile t (the CTA's i-th) on one barrier
-    const uint32_t bar = bar0 + 8u * (i & 1);
-    asm volatile("st.shared.s32 [%0], %1;" ::"r"(tid0 + 4u * (i & 1)), "r"(t < tp.total_tiles ? t : -1) : "memory");
+  auto request = [&](int t, int slot) {  // one thread: all copies of tile t into ring slot `slot`, one barrier
+    const uint32_t bar = bar0 + 8u * slot;
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(tid0 + 4u * slot), "r"(t < tp.total_tiles ? t : -1) : "memory");
     if (t >= tp.total_tiles) {  // no more work: complete the phase so that the waiting warps see the end marker
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
       return;
     }
-    const int b = t / tp.ntiles, q = t - b * tp.ntiles;
+    int b = t / tp.ntiles, chunk = tp.chunk;
+    const int q = t - b * tp.ntiles;
+    if constexpr (ZMODE) {  // one launch covers every antenna chunk: t = (link, chunk, tile)
+      chunk = b % tp.nchunks;
+      b /= tp.nchunks;
+    }
+    const uint32_t xs = ring0 + (uint32_t)slot * tp.slot_bytes;
     tma::mbar_expect_tx(bar, (uint32_t)NTX * plane + tp.coef_bytes + tp.s_bytes);
-    tma::load_4d(xs0 + (uint32_t)(i & 1) * tp.stage_bytes, &xmap, 0, q * (kTmaTile / 16) - tp.hrows, a.tx0, b, bar);
-    const uint32_t ax = aux0 + (uint32_t)(i % 3) * tp.aux_bytes;
+    tma::load_4d(xs, &xmap, 0, q * (kTmaTile / 16) - tp.hrows, chunk * NTX, b, bar);
+    const uint32_t ax = xs + tp.stage_bytes;
     const int qp = (q * kTmaTile) / tp.poly_tile;
     tma::load_1d(ax, a.coef + ((size_t)b * tp.npoly + qp) * tp.coef_stride, tp.coef_bytes, bar);
-    tma::load_1d(ax + tp.s_off, a.spatial32 + ((size_t)b * tp.nchunks + tp.chunk) * tp.s_stride, tp.s_bytes, bar);
+    tma::load_1d(ax + tp.s_off, a.spatial32 + ((size_t)b * tp.nchunks + chunk) * tp.s_stride, tp.s_bytes, bar);
   };
 
   if (tid == 0) {
-    if (xs0 & 1023u) __trap();  // the swizzle phase is derived from absolute shared addresses
+    if (ring0 & 1023u) __trap();  // the swizzle phase is derived from absolute shared addresses
     tma::prefetch_map(&xmap);
-    tma::mbar_init(bar0, 1);
-    tma::mbar_init(bar0 + 8, 1);
-    asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(cnt0), "r"(0u) : "memory");
+    for (int s = 0; s < NS; ++s) {
+      tma::mbar_init(bar0 + 8u * s, 1);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * s), "r"(0u) : "memory");
+    }
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(next0), "r"(0u) : "memory");
     tma::fence_barrier_init();
-    request((int)blockIdx.x, 0);  // the first two tiles of every CTA are static, the rest come from the counter
-    request((int)blockIdx.x + step, 1);
+    // the first NS tiles of every CTA are static, the rest are claimed from the global counter as slots free up
+    for (int s = 0; s < NS; ++s) request((int)blockIdx.x + s * step, s);
   }
   __syncthreads();
 
   const float inv = 1.0f / (float)tp.poly_tile;
-  for (int i = 0;; ++i) {
-    tma::mbar_wait(bar0 + 8u * (i & 1), (uint32_t)(i >> 1) & 1u);
+  for (;;) {
+    // ticket = (ring position k, part): every warp of the CTA pulls the next 256-output part on its own
+    uint32_t kw = 0;
+    if (lane == 0) asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(kw) : "r"(next0) : "memory");
+    kw = __shfl_sync(0xffffffffu, kw, 0);
+    const uint32_t k = kw / kTmaParts, part = kw % kTmaParts;
+    const uint32_t use = k / (uint32_t)NS, slot = k - use * (uint32_t)NS;
+    tma::mbar_wait(bar0 + 8u * slot, use & 1u);
     int t;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(tid0 + 4u * (i & 1)) : "memory");
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(tid0 + 4u * slot) : "memory");
     if (t < 0) break;
-    const int b = t / tp.ntiles, q = t - b * tp.ntiles;
+    int b = t / tp.ntiles, tx0 = a.tx0;
+    const int q = t - b * tp.ntiles;
+    if constexpr (ZMODE) {
+      tx0 = (b % tp.nchunks) * NTX;
+      b /= tp.nchunks;
+    }
+    const int trow = 32 * (int)part + lrow;
     const int m0 = q * kTmaTile + R * trow;
     const bool active = m0 < Tout;
-    const uint32_t xs = xs0 + (uint32_t)(i & 1) * tp.stage_bytes;
-    const uint32_t csa0 = aux0 + (uint32_t)(i % 3) * tp.aux_bytes;
+    const uint32_t xs = ring0 + slot * tp.slot_bytes;
+    const uint32_t csa0 = xs + tp.stage_bytes;
 
     u64 acc[R][NTX];
 #pragma unroll
@@ -273,20 +298,6 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
       }
     }
 
-    // Release: the LAST warp to finish the walk of this tile requests the tile after next into the slot just
-    // freed.  No CTA-wide barrier: warps drift apart by up to one tile, which overlaps one warp's epilogue
-    // (stores) with the others' walks.  Every warp that counted has finished the epilogue of the previous tile, so
-    // the aux slot (i + 2) % 3 == (i - 1) % 3 is free as well.
-    __syncwarp();
-    if (lane == 0) {
-      uint32_t old;
-      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt0 + 4u * (i & 1)) : "memory");
-      if (old == kTmaThreads / 32 - 1) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * (i & 1)), "r"(0u) : "memory");
-        request((int)atomicAdd(tp.tile_counter, 1u) + 2 * step, i + 2);  // dynamic schedule: no tail imbalance
-      }
-    }
-
     if (active) {
       const bool vec_ok = ((Tout & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && (m0 + R <= Tout) &&
                           !a.accumulate;
@@ -311,10 +322,10 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
       };
       if constexpr (ZMODE) {
         // ---- large arrays: the spatial product runs on the tensor cores (spatial_gemm.cuh); store z itself ----------
-        float2* zb = reinterpret_cast<float2*>(a.y) + ((size_t)b * a.ntx + a.tx0) * Tout + m0;
+        float2* zb = reinterpret_cast<float2*>(a.y) + ((size_t)b * a.ntx + tx0) * Tout + m0;
 #pragma unroll
         for (int j = 0; j < NTX; ++j) {
-          if (j < a.ntx_chunk) {
+          if (tx0 + j < a.ntx) {
             u64 yv[R];
 #pragma unroll
             for (int u = 0; u < R; ++u) yv[u] = acc[u][j];
@@ -346,6 +357,19 @@ __global__ void __launch_bounds__(kTmaThreads, 3)
           }
           store_row(yb + (size_t)irx * Tout, yv);
         }
+      }
+    }
+
+    // Release: the warp that finishes the LAST part of this tile claims the next unprocessed tile (global counter:
+    // SMs that run slower simply claim fewer) and requests it into the slot just freed.  No barrier anywhere in the
+    // loop: warps drift apart by up to NS - 1 tiles, so loads, walks and stores of different tiles overlap.
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt0 + 4u * slot) : "memory");
+      if (old == kTmaParts - 1) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * slot), "r"(0u) : "memory");
+        request((int)atomicAdd(tp.tile_counter, 1u) + NS * step, (int)slot);
       }
     }
   }
