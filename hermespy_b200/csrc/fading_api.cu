@@ -180,7 +180,7 @@ static void plan_tma(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
   const bool zmode = p->num_tx >= 16 && p->num_rx >= 16;  // large arrays: no spatial matrix in the kernel
   tp.s_stride = zmode ? 2 : (p->num_rx * pl->ntx_tpl + 1) & ~1;
   tp.nchunks = (p->num_tx + pl->ntx_tpl - 1) / pl->ntx_tpl;
-  tp.stage_bytes = (uint32_t)align_up((size_t)pl->ntx_tpl * tp.rows * 128, 1024);
+  tp.stage_bytes = (uint32_t)pl->ntx_tpl * kTmaPlaneBytes;  // one 1024-aligned plane of <= 72 rows per antenna
   tp.coef_bytes = (uint32_t)tp.coef_stride * 8u;
   tp.s_bytes = (uint32_t)tp.s_stride * 8u;
   tp.s_off = (uint32_t)align_up((size_t)(dt.num_groups + 1) * pl->P * 8, 16);
@@ -525,7 +525,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
     tp = pl.tp;
     tp.total_tiles = a.B * tp.ntiles * (pl.large_array ? tp.nchunks : 1);  // z mode: every chunk in ONE launch
     tma_grid = std::min(tp.total_tiles, device_sm_count());
-    rc = make_x_map(x, a.B, a.ntx, a.T, tp.rows, pl.ntx_tpl, &xmap);
+    rc = make_x_map(x, a.B, a.ntx, a.T, tp.rows, 1, &xmap);
   }
   for (int tx0 = 0; tx0 < (a.z_mode ? 1 : p->num_tx) && rc == HB_OK; tx0 += pl.ntx_tpl) {
     a.tx0 = tx0;

@@ -6,12 +6,12 @@
 // the delay axis once with the R inputs of every antenna in a register window.  What changes is how the signal
 // reaches shared memory and how the CTA is scheduled:
 //
-// * The x tile (+ delay halo) of ALL antennas of the chunk arrives by ONE `cp.async.bulk.tensor.4d` (TMA) per tile,
+// * The x tile (+ delay halo) of every antenna of the chunk arrives by `cp.async.bulk.tensor.4d` (TMA),
 //   in its natural time-major layout, written by the copy engine -- no LSU instructions, no shared-memory
 //   wavefronts spent on staging (the cp.async staging of the window kernel costs 2.1 of its 4.4 wavefronts per
 //   sample, profiles/r01_window_kernel.md).  The frame is described to the TMA unit as a 4-D tensor
-//   (32 floats = 16 samples, T / 16 rows, Ntx, B): a tile is the box {32, 64 + H, NTX, 1} at row 64 q - H, and the
-//   copy engine zero-fills rows before the frame start / past its end and antennas past the chunk.
+//   (32 floats = 16 samples, T / 16 rows, Ntx, B): a tile is one box {32, 64 + H, 1, 1} per antenna at row 64 q - H,
+//   and the copy engine zero-fills rows before the frame start / past its end and antennas past the chunk.
 // * SWIZZLE_128B: the 16-byte chunk index of every 128-byte row is XORed with (row & 7).  A thread reads TIME
 //   PAIRS (x[e], x[e+1]) of one antenna with LDS.128; the 8 lanes of a quarter warp are 64 bytes apart in the
 //   natural layout (4-way bank conflict) and land on 8 distinct chunk positions under the swizzle: conflict-free.
@@ -39,6 +39,7 @@ constexpr int kTmaParts = 4;
 constexpr int kTmaMaxSlots = 6;    // ring depth (tiles resident or in flight per SM)
 constexpr int kTmaMaxHaloRows = 8;             // 16-sample rows of delay halo: d <= 127
 constexpr int kTmaMaxBlocks = 2 * kTmaMaxHaloRows;
+constexpr uint32_t kTmaPlaneBytes = (kTmaTile / 16 + kTmaMaxHaloRows) * 128;  // 9216: antenna plane stride, a multiple of 1024
 
 struct TmaPlan {
   int32_t num_groups;
@@ -101,8 +102,9 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
 }
 // SWIZZLE_128B of an absolute shared address inside a 1024-byte aligned stage
 __device__ __forceinline__ uint32_t swz(uint32_t addr) { return addr ^ ((addr >> 3) & 0x70u); }
+template <int IMM>
 __device__ __forceinline__ void lds_pair_at(uint32_t addr, u64& lo, u64& hi) {
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2 + %3];" : "=l"(lo), "=l"(hi) : "r"(addr), "n"(IMM));
 }
 
 }  // namespace tma
@@ -144,7 +146,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     const uint32_t xs = ring0 + (uint32_t)slot * tp.slot_bytes;
     tma::mbar_expect_tx(bar, (uint32_t)NTX * plane + tp.coef_bytes + tp.s_bytes);
-    tma::load_4d(xs, &xmap, 0, q * (kTmaTile / 16) - tp.hrows, chunk * NTX, b, bar);
+    // one box per antenna, each plane on its own 1024-byte boundary: the swizzle phase of a (row, chunk) is then the
+    // same in every plane and the walk addresses all antennas from ONE swizzled pointer plus immediate offsets
+#pragma unroll
+    for (int j = 0; j < NTX; ++j)
+      tma::load_4d(xs + j * kTmaPlaneBytes, &xmap, 0, q * (kTmaTile / 16) - tp.hrows, chunk * NTX + j, b, bar);
     const uint32_t ax = xs + tp.stage_bytes;
     const int qp = (q * kTmaTile) / tp.poly_tile;
     tma::load_1d(ax, a.coef + ((size_t)b * tp.npoly + qp) * tp.coef_stride, tp.coef_bytes, bar);
@@ -207,11 +213,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       // window at d = 0: x[m0 .. m0+7] = pairs pe0 .. pe0+3, pe0 = 8 hrows + 4 trow (natural offset 16 pe0)
       u64 w[NTX][R];
       uint32_t nat = xs + (uint32_t)tp.hrows * 128u + 64u * (uint32_t)trow;  // antenna 0, first pair of the window
+      {
+        const uint32_t s0 = tma::swz(nat);
 #pragma unroll
-      for (int j = 0; j < NTX; ++j) {
-        const uint32_t sj = tma::swz(nat + (uint32_t)j * plane);
+        for (int k = 0; k < R / 2; ++k) {
+          const uint32_t ak = s0 ^ (16u * k);
 #pragma unroll
-        for (int k = 0; k < R / 2; ++k) tma::lds_pair_at(sj ^ (16u * k), w[j][2 * k], w[j][2 * k + 1]);
+          for (int j = 0; j < NTX; ++j) tma::lds_pair_at<0>(ak + j * kTmaPlaneBytes, w[j][2 * k], w[j][2 * k + 1]);
+        }
       }
 
       uint32_t csa = csa0;
@@ -247,16 +256,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         const uint32_t mk = tp.mask[c];
         if (mk == 0u) continue;
         const uint32_t pm = mk & 0xffu, lm = mk >> 8;
-        uint32_t sj[NTX];
-#pragma unroll
-        for (int j = 0; j < NTX; ++j) sj[j] = tma::swz(nat + (uint32_t)j * plane);
+        const uint32_t s0 = tma::swz(nat);
 #pragma unroll
         for (int s = 0; s < R; ++s) {
           auto load_pair = [&]() {  // odd s: (x[m0-d-1], x[m0-d]) -> slots 7 - s, 8 - s; chunk 3 - (s - 1) / 2 of the half row
             if ((lm >> s) & 1u) {
+              const uint32_t ak = s0 ^ (16u * (3 - (s >> 1)));
 #pragma unroll
-              for (int j = 0; j < NTX; ++j)
-                tma::lds_pair_at(sj[j] ^ (16u * (3 - (s >> 1))), w[j][7 - s], w[j][(8 - s) & 7]);
+              for (int j = 0; j < NTX; ++j) tma::lds_pair_at<0>(ak + j * kTmaPlaneBytes, w[j][7 - s], w[j][(8 - s) & 7]);
             }
           };
           if ((pm >> s) & 1u) {
