@@ -295,8 +295,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
               for (int u = 1; u < R - 1; ++u) mac_u(u);
               mac_u(0);
             } else {
+              // output 0 reads the element that entered with the pair loaded at the previous (odd) phase: last
 #pragma unroll
-              for (int u = 0; u < R; ++u) mac_u(u);
+              for (int u = 1; u < R; ++u) mac_u(u);
+              mac_u(0);
             }
           } else if (s & 1) {
             load_pair();
