@@ -5,7 +5,7 @@
     ... run any Simulation script ...
     dropin.disable()
 
-``enable()`` rebinds four methods of the reference -- nothing else is touched:
+``enable()`` rebinds three methods of the reference -- nothing else is touched:
 
 * ``hermespy.channel.fading.fading.MultipathFadingSample._propagate`` (fading.py:371-406) and ``.state`` (:345-369)
 * ``hermespy.channel.cdl.cluster_delay_lines.ClusterDelayLineSample._propagate`` (cluster_delay_lines.py:526-558)
@@ -126,6 +126,30 @@ def _fading_propagate(self, signal, interpolation):
     return SignalBlock(out.shape[0], out.shape[1], signal.offset, out.tobytes())
 
 
+def _fading_state(self, num_samples, max_num_taps, interpolation_mode=None):
+    """``MultipathFadingSample.state`` (fading.py:345-369): the SISO tap gains -- the sum-of-sinusoids cost of the call --
+    come from ``hb_fading_state``; the outer product with the spatial response and the sparse container stay the
+    reference's own expressions, so consumers (``OFDMIdealChannelEstimation`` ...) see the type they expect."""
+    from hermespy.core import ChannelStateFormat, ChannelStateInformation  # type: ignore
+    from sparse import GCXS  # type: ignore
+
+    from .kernels import FadingBatch, fading_state
+
+    b = fading_block_from_reference(self)
+    num_taps = min(1 + b["max_delay"], max_num_taps)
+    keep = b["tap_delay"] <= num_taps  # the reference skips taps with d_l > num_taps (fading.py:355) ...
+    if num_samples < 1 or num_taps < 1 or not np.any(keep) or np.any(b["tap_delay"][keep] >= num_taps):
+        return _ORIGINALS["fading_state"](self, num_samples, max_num_taps)  # ... and raises for d_l == num_taps
+    fb = FadingBatch.from_numpy(b["tap_delay"][keep], b["max_delay"], b["omega"][None][:, keep], b["phi"][None][:, keep],
+                                b["amp"][None][:, keep], b["spatial"][None], omega_max=b["omega_max"],
+                                device=f"cuda:{config.device}")
+    h, group_delay = fading_state(fb, int(num_samples), precision=config.precision, io128=True)
+    siso_csi = np.zeros((num_samples, num_taps), dtype=np.complex128)
+    siso_csi[:, group_delay] = h[0].cpu().numpy().T
+    mimo_csi = GCXS.from_numpy(np.einsum("ij,kl->ijkl", self.spatial_response, siso_csi), compressed_axes=(0, 1, 2))
+    return ChannelStateInformation(ChannelStateFormat.IMPULSE_RESPONSE, mimo_csi, num_delay_taps=num_taps)
+
+
 def _cdl_propagate(self, signal, interpolation):
     from hermespy.core import InterpolationMode  # type: ignore
     from hermespy.core.signal_model import SignalBlock  # type: ignore
@@ -163,8 +187,10 @@ def patch_reference() -> None:
 
     if not _ORIGINALS:
         _ORIGINALS["fading_propagate"] = MultipathFadingSample._propagate
+        _ORIGINALS["fading_state"] = MultipathFadingSample.state
         _ORIGINALS["cdl_propagate"] = ClusterDelayLineSample._propagate
     MultipathFadingSample._propagate = _fading_propagate
+    MultipathFadingSample.state = _fading_state
     ClusterDelayLineSample._propagate = _cdl_propagate
 
 
@@ -175,5 +201,6 @@ def disable() -> None:
     from hermespy.channel.fading.fading import MultipathFadingSample  # type: ignore
 
     MultipathFadingSample._propagate = _ORIGINALS["fading_propagate"]
+    MultipathFadingSample.state = _ORIGINALS["fading_state"]
     ClusterDelayLineSample._propagate = _ORIGINALS["cdl_propagate"]
     _ORIGINALS.clear()

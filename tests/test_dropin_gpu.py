@@ -189,6 +189,15 @@ def test_reference_fading_samples_propagate_through_dropin(ref, ci):
     assert y0.shape == y64.shape == y32.shape
     assert rel_l2(y64, y0) < (1e-10 if "extreme" in name else 1e-12)
     assert rel_l2(y32, y0) < 1e-5
+    # channel state (fading.py:345-369): the tap gains come from hb_fading_state, container and layout stay the reference's
+    taps = 1 + y0.shape[1] - sig.num_samples
+    c0 = np.asarray(s.state(150, taps).dense_state())
+    ref.enable(precision="f64")
+    st = s.state(150, taps)
+    ref.disable()
+    c64 = np.asarray(st.dense_state())
+    assert type(st).__name__ == "ChannelStateInformation" and c0.shape == c64.shape
+    assert rel_l2(c64, c0) < (1e-10 if "extreme" in name else 1e-12)
 
 
 @pytest.mark.parametrize("ci", range(len(CDL_CASES)), ids=[c[0] for c in CDL_CASES])

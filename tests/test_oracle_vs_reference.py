@@ -152,14 +152,16 @@ def test_dropin_patch_and_restore(ref):
     from hermespy.channel.fading.fading import MultipathFadingSample
     from hermespy_b200 import dropin
 
-    orig_f, orig_c = MultipathFadingSample._propagate, ClusterDelayLineSample._propagate
+    orig_f, orig_c, orig_s = MultipathFadingSample._propagate, ClusterDelayLineSample._propagate, MultipathFadingSample.state
     dropin.patch_reference()
     try:
         assert MultipathFadingSample._propagate is dropin._fading_propagate
+        assert MultipathFadingSample.state is dropin._fading_state
         assert ClusterDelayLineSample._propagate is dropin._cdl_propagate
     finally:
         dropin.disable()
     assert MultipathFadingSample._propagate is orig_f and ClusterDelayLineSample._propagate is orig_c
+    assert MultipathFadingSample.state is orig_s
 
 
 def test_stats_oracle_matches_reference_evaluator(ref):
