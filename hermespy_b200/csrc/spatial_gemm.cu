@@ -9,7 +9,9 @@ int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int
   if (B == 0 || T == 0 || nrx == 0) return HB_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    HB_CUDA(cudaFuncSetAttribute(spatial_gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HB_CUDA(cudaFuncSetAttribute(spatial_gemm_3xtf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kGemmSmemBytes));
+    HB_CUDA(cudaFuncSetAttribute(spatial_gemm_3xtf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kGemmSmemBytes));
     attr_set = true;
   }
@@ -39,7 +41,10 @@ int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int
       a.ntx = std::min(kGemmMaxAnt, ntx - tx0);
       a.accumulate = tx0 > 0;
       ProfileScope prof(KIND_SPATIAL_GEMM, st);
-      spatial_gemm_3xtf32_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(a);
+      if (a.nrx == kGemmMaxAnt && a.ntx == kGemmMaxAnt && !a.accumulate)
+        spatial_gemm_3xtf32_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(a);
+      else
+        spatial_gemm_3xtf32_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(a);
       HB_CUDA(cudaGetLastError());
     }
   }

@@ -118,6 +118,9 @@ __device__ __forceinline__ uint32_t gemm_operand_offset(int r, int k) {
   return (uint32_t)(r >> 3) * kGemmSbo + (uint32_t)(k >> 2) * kGemmLbo + (uint32_t)(r & 7) * 16 + (uint32_t)(k & 3) * 4;
 }
 
+// FULL: a full 64 x 64 antenna block without accumulation -- interior tiles (all 64 samples inside the frame) then run
+// without a single bounds predicate: plain loads, pair-shuffled 8-byte stores.
+template <bool FULL>
 __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(const GemmArgs a) {
   using namespace umma;
   extern __shared__ unsigned char gemm_smem_raw[];
@@ -195,6 +198,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
     float2 zr[kMaxPass][4];  // prefetched z elements of the next tile to stage
     auto load_tile = [&](int t) {
       const int n = t * kGemmTileSamples + ms;
+      if (FULL && (t + 1) * kGemmTileSamples <= a.T) {  // CTA-uniform
+        const float2* zp = zb + (size_t)(4 * kc0) * a.T + n;
+#pragma unroll
+        for (int p = 0; p < kMaxPass; ++p)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) zr[p][i] = ldg_stream(zp + (size_t)(16 * p + i) * a.T);
+        return;
+      }
 #pragma unroll
       for (int p = 0; p < kMaxPass; ++p) {
         const int kc = 4 * p + kc0;
@@ -248,6 +259,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
       fence_after_sync();
       const int n = t * kGemmTileSamples + em;
       const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 128 + (uint32_t)chalf * 64;
+      if (FULL && (t + 1) * kGemmTileSamples <= a.T) {  // CTA-uniform
+        // Pair shuffle: for receive streams (j0, j0 + 1) the even lane (Re z row: P, Q) finishes stream j0 and the odd
+        // lane (Im z row: U, V) finishes j0 + 1; each receives the partner's two coefficients of ITS stream, so every
+        // thread stores one complete complex sample (8 bytes); a warp writes two 128-byte row segments per instruction.
+        float2* yrow = reinterpret_cast<float2*>(yb) + (size_t)(chalf * 32 + comp) * a.T + n;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(taddr + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            // columns: (2 jj, 2 jj + 1) = stream j0, (2 jj + 2, 2 jj + 3) = stream j0 + 1
+            const float a0 = __uint_as_float(v[2 * jj]), b0 = __uint_as_float(v[2 * jj + 1]);
+            const float a1 = __uint_as_float(v[2 * jj + 2]), b1 = __uint_as_float(v[2 * jj + 3]);
+            // even lane keeps (P0, Q0) and sends (P1, Q1); odd lane keeps (U1, V1) and sends (U0, V0)
+            const float ra = __shfl_xor_sync(0xffffffffu, comp ? a0 : a1, 1);
+            const float rb = __shfl_xor_sync(0xffffffffu, comp ? b0 : b1, 1);
+            float2 out;
+            if (comp) {  // own (U1, V1), received (P1, Q1): y = (P - V, Q + U)
+              out.x = ra - b1;
+              out.y = rb + a1;
+            } else {     // own (P0, Q0), received (U0, V0)
+              out.x = a0 - rb;
+              out.y = b0 + ra;
+            }
+            stg_stream(yrow + (size_t)(h * 16 + jj) * a.T, out);
+          }
+        }
+        return;
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (chalf * 64 + h * 32 < Np) {  // warp-uniform

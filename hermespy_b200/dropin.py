@@ -5,10 +5,11 @@
     ... run any Simulation script ...
     dropin.disable()
 
-``enable()`` rebinds three methods of the reference -- nothing else is touched:
+``enable()`` rebinds four methods of the reference -- nothing else is touched:
 
 * ``hermespy.channel.fading.fading.MultipathFadingSample._propagate`` (fading.py:371-406) and ``.state`` (:345-369)
 * ``hermespy.channel.cdl.cluster_delay_lines.ClusterDelayLineSample._propagate`` (cluster_delay_lines.py:526-558)
+  and ``.state`` (:561-592)
 
 The replacements read the reference sample through its public properties (fading.py:217-287,
 cluster_delay_lines.py:321-403), lay out the same kernel parameter blocks the mirror classes of this package
@@ -168,6 +169,29 @@ def _cdl_propagate(self, signal, interpolation):
     return SignalBlock(out.shape[0], out.shape[1], signal._offset, out.tobytes())
 
 
+def _cdl_state(self, num_samples, max_num_taps, interpolation_mode=None):
+    """``ClusterDelayLineSample.state`` (cluster_delay_lines.py:561-592): per-delay MIMO impulse responses from
+    ``hb_cdl_state`` (FP64 ray synthesis), scattered into the reference's dense [Nrx, Ntx, T, 1 + D] container."""
+    from hermespy.core import ChannelStateFormat, ChannelStateInformation  # type: ignore
+
+    from .kernels import CdlDeviceBlock, cdl_state
+
+    try:
+        blk = cdl_block_from_reference(self)
+    except NotImplementedError:
+        return _ORIGINALS["cdl_state"](self, num_samples, max_num_taps)
+    if num_samples < 1:
+        return _ORIGINALS["cdl_state"](self, num_samples, max_num_taps)
+    D = min(max_num_taps, blk.max_delay)
+    h, gd = cdl_state(CdlDeviceBlock(blk, device=f"cuda:{config.device}"), int(num_samples))
+    h = h[0].cpu().numpy()  # [G, Nrx, Ntx, T]
+    raw_state = np.zeros((blk.num_rx, blk.num_tx, num_samples, 1 + D), dtype=np.complex128)
+    for g, d in enumerate(gd):
+        if d < max_num_taps:  # cluster_delay_lines.py:583-584
+            raw_state[:, :, :, d] = h[g]
+    return ChannelStateInformation(ChannelStateFormat.IMPULSE_RESPONSE, raw_state)
+
+
 def enable(precision: str = "f32") -> None:
     """Patch the reference classes.  Fails loudly when the library or a CUDA device is missing."""
     from . import _lib
@@ -189,6 +213,8 @@ def patch_reference() -> None:
         _ORIGINALS["fading_propagate"] = MultipathFadingSample._propagate
         _ORIGINALS["fading_state"] = MultipathFadingSample.state
         _ORIGINALS["cdl_propagate"] = ClusterDelayLineSample._propagate
+        _ORIGINALS["cdl_state"] = ClusterDelayLineSample.state
+    ClusterDelayLineSample.state = _cdl_state
     MultipathFadingSample._propagate = _fading_propagate
     MultipathFadingSample.state = _fading_state
     ClusterDelayLineSample._propagate = _cdl_propagate
@@ -202,5 +228,6 @@ def disable() -> None:
 
     MultipathFadingSample._propagate = _ORIGINALS["fading_propagate"]
     MultipathFadingSample.state = _ORIGINALS["fading_state"]
+    ClusterDelayLineSample.state = _ORIGINALS["cdl_state"]
     ClusterDelayLineSample._propagate = _ORIGINALS["cdl_propagate"]
     _ORIGINALS.clear()

@@ -226,3 +226,8 @@ def test_reference_cdl_samples_propagate_through_dropin(ref, ci):
     ref.disable()
     assert rel_l2(y64, y0) < 1e-10
     assert rel_l2(y32, y0) < 1e-5
+    c0 = np.asarray(s.state(40, 1000).dense_state())  # cluster_delay_lines.py:561-592
+    ref.enable(precision="f64")
+    c64 = np.asarray(s.state(40, 1000).dense_state())
+    ref.disable()
+    assert c0.shape == c64.shape and rel_l2(c64, c0) < 1e-10

@@ -153,15 +153,17 @@ def test_dropin_patch_and_restore(ref):
     from hermespy_b200 import dropin
 
     orig_f, orig_c, orig_s = MultipathFadingSample._propagate, ClusterDelayLineSample._propagate, MultipathFadingSample.state
+    orig_cs = ClusterDelayLineSample.state
     dropin.patch_reference()
     try:
         assert MultipathFadingSample._propagate is dropin._fading_propagate
         assert MultipathFadingSample.state is dropin._fading_state
         assert ClusterDelayLineSample._propagate is dropin._cdl_propagate
+        assert ClusterDelayLineSample.state is dropin._cdl_state
     finally:
         dropin.disable()
     assert MultipathFadingSample._propagate is orig_f and ClusterDelayLineSample._propagate is orig_c
-    assert MultipathFadingSample.state is orig_s
+    assert MultipathFadingSample.state is orig_s and ClusterDelayLineSample.state is orig_cs
 
 
 def test_stats_oracle_matches_reference_evaluator(ref):
