@@ -231,3 +231,47 @@ def test_reference_cdl_samples_propagate_through_dropin(ref, ci):
     c64 = np.asarray(s.state(40, 1000).dense_state())
     ref.disable()
     assert c0.shape == c64.shape and rel_l2(c64, c0) < 1e-10
+
+
+_STOCHASTIC = {
+    "uma_los": lambda C: C.UrbanMacrocells(expected_state=C.O2IState.LOS, seed=1),
+    "uma_nlos": lambda C: C.UrbanMacrocells(expected_state=C.O2IState.NLOS, seed=2),
+    "uma_o2i": lambda C: C.UrbanMacrocells(expected_state=C.O2IState.O2I, seed=3),
+    "umi_nlos": lambda C: C.UrbanMicrocells(expected_state=C.O2IState.NLOS, seed=4),
+    "rma_los": lambda C: C.RuralMacrocells(expected_state=C.O2IState.LOS, seed=5),
+    "inh_los": lambda C: C.IndoorOffice(expected_state=C.LOSState.LOS, seed=6),
+    "inf_nlos": lambda C: C.IndoorFactory(2000.0, 1500.0, C.FactoryType.DH, expected_state=C.LOSState.NLOS, seed=7),
+}
+
+
+@pytest.mark.parametrize("name", list(_STOCHASTIC))
+def test_stochastic_cdl_scenarios_through_dropin(ref, name):
+    """the 3GPP scenario models (UMa / UMi / RMa / InH / InF, cluster_delay_lines.py:1824-2013) only differ
+    from the static CDL tables in how a sample is DRAWN; the sample type -- and therefore the patched ``_propagate`` /
+    ``state`` -- is the same.  Cluster counts, delays and LOS state vary per realization (6..25 clusters here)."""
+    import hermespy.channel as RC
+    from hermespy.core import Signal, Transformation
+    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+
+    def dev(dims, pos, vel):
+        return SimulatedDevice(bandwidth=CDL_FS, oversampling_factor=1, carrier_frequency=CDL_FC,
+                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, CDL_SPACING, dims),
+                               pose=Transformation.From_Translation(np.array(pos, float)), velocity=np.array(vel, float))
+
+    ch = _STOCHASTIC[name](RC)
+    tx, rx = dev((2, 2, 1), (0.0, 0.0, 25.0), (0, 0, 0)), dev((2, 1, 1), (120.0, 40.0, 1.5), (3.0, -1.0, 0.0))
+    for rep in range(2):  # two realizations: different cluster sets / delay structures
+        s = ch.realize().sample(tx, rx)
+        sig = Signal.Create(golden_signal(400 + rep, 4, 2304), CDL_FS, CDL_FC)
+        ref.disable()
+        y0 = np.asarray(s.propagate(sig).view(np.ndarray))
+        c0 = np.asarray(s.state(32, 1000).dense_state())
+        ref.enable(precision="f64")
+        y64 = np.asarray(s.propagate(sig).view(np.ndarray))
+        c64 = np.asarray(s.state(32, 1000).dense_state())
+        ref.enable(precision="f32")
+        y32 = np.asarray(s.propagate(sig).view(np.ndarray))
+        ref.disable()
+        assert y0.shape == y64.shape == y32.shape and c0.shape == c64.shape
+        assert rel_l2(y64, y0) < 1e-10 and rel_l2(c64, c0) < 1e-10
+        assert rel_l2(y32, y0) < 1e-5
