@@ -200,7 +200,7 @@ static void plan_tma(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
   pl->Dpad = 16 * tp.hrows;
   tp.slot_bytes = (uint32_t)align_up((size_t)tp.stage_bytes + tp.aux_bytes, 1024);
   // ring depth: as many slots as fit the 227 KB of one SM (one CTA per SM), at most kTmaMaxSlots
-  const size_t ctl = 16 * kTmaMaxSlots + 16;  // barriers, release counters, tile indices, ticket counter
+  const size_t ctl = 20 * kTmaMaxSlots + 32;  // barriers, release counters, tile indices, ticket, done flags, retire ptr, lock
   tp.num_slots = (int)std::min<size_t>(kTmaMaxSlots, (kTmaSmemBudget - ctl) / tp.slot_bytes);
   pl->smem = (size_t)tp.num_slots * tp.slot_bytes + ctl;
   const double eps_w = 0.5 * (kTmaR - 1) * p->omega_max;

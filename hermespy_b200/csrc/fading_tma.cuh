@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   const uint32_t cnt0 = bar0 + 8u * kTmaMaxSlots;                // NS release counters (parts finished)
   const uint32_t tid0 = cnt0 + 4u * kTmaMaxSlots;                // tile index held by each slot (-1: no more work)
   const uint32_t next0 = tid0 + 4u * kTmaMaxSlots;               // next (tile, part) ticket of this CTA
+  const uint32_t done0 = next0 + 16u;                            // NS flags "all parts of the slot's tile are stored"
+  const uint32_t rptr0 = done0 + 4u * kTmaMaxSlots;              // ring position that retires next (in order)
+  const uint32_t lock0 = rptr0 + 4u;                             // spin lock of the retire loop
   const int Tout = a.T + a.D;
   const int step = (int)gridDim.x;
   const uint32_t plane = (uint32_t)tp.rows * 128u;
@@ -163,8 +166,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     for (int s = 0; s < NS; ++s) {
       tma::mbar_init(bar0 + 8u * s, 1);
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * s), "r"(0u) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 4u * s), "r"(0u) : "memory");
     }
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(next0), "r"(0u) : "memory");
+    asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(rptr0), "r"(0u) : "memory");
     tma::fence_barrier_init();
     // the first NS tiles of every CTA are static, the rest are claimed from the global counter as slots free up
     for (int s = 0; s < NS; ++s) request((int)blockIdx.x + s * step, s);
@@ -172,11 +177,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   __syncthreads();
 
   const float inv = 1.0f / (float)tp.poly_tile;
+  // ticket = (ring position k, part): every warp of the CTA pulls the next 256-output part on its own.  The ticket
+  // of the NEXT part is drawn right after the walk, so the shared-memory atomic completes under the epilogue.
+  uint32_t ticket = 0;
+  if (lane == 0) asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(ticket) : "r"(next0) : "memory");
   for (;;) {
-    // ticket = (ring position k, part): every warp of the CTA pulls the next 256-output part on its own
-    uint32_t kw = 0;
-    if (lane == 0) asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(kw) : "r"(next0) : "memory");
-    kw = __shfl_sync(0xffffffffu, kw, 0);
+    const uint32_t kw = __shfl_sync(0xffffffffu, ticket, 0);
     const uint32_t k = kw / kTmaParts, part = kw % kTmaParts;
     const uint32_t use = k / (uint32_t)NS, slot = k - use * (uint32_t)NS;
     tma::mbar_wait(bar0 + 8u * slot, use & 1u);
@@ -307,6 +313,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
 
+    if (lane == 0) asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(ticket) : "r"(next0) : "memory");
+
     if (active) {
       const bool vec_ok = ((Tout & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && (m0 + R <= Tout) &&
                           !a.accumulate;
@@ -369,16 +377,33 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
 
-    // Release: the warp that finishes the LAST part of this tile claims the next unprocessed tile (global counter:
-    // SMs that run slower simply claim fewer) and requests it into the slot just freed.  No barrier anywhere in the
-    // loop: warps drift apart by up to NS - 1 tiles, so loads, walks and stores of different tiles overlap.
+    // Release.  The warp that finishes the LAST part of a tile marks its slot done and runs the retire loop: ring
+    // positions retire IN ORDER, and each retirement claims the next unprocessed tile from the global counter (SMs that
+    // run slower simply claim fewer) and requests it into the freed slot.  In-order requests make the end markers a
+    // suffix of the ring sequence, so a warp may leave at the first marker it meets without stranding a later tile.
+    // No barrier anywhere in the loop: warps drift apart by up to NS - 1 tiles; loads, walks and stores overlap.
     __syncwarp();
     if (lane == 0) {
       uint32_t old;
       asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt0 + 4u * slot) : "memory");
       if (old == kTmaParts - 1) {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * slot), "r"(0u) : "memory");
-        request((int)atomicAdd(tp.tile_counter, 1u) + NS * step, (int)slot);
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(done0 + 4u * slot), "r"(1u) : "memory");
+        uint32_t busy;
+        do {
+          asm volatile("atom.acquire.cta.shared::cta.cas.b32 %0, [%1], 0, 1;" : "=r"(busy) : "r"(lock0) : "memory");
+        } while (busy != 0u);
+        for (;;) {
+          uint32_t pos, flag;
+          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(pos) : "r"(rptr0) : "memory");
+          const uint32_t rs = pos % (uint32_t)NS;
+          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(flag) : "r"(done0 + 4u * rs) : "memory");
+          if (flag == 0u) break;
+          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(done0 + 4u * rs), "r"(0u) : "memory");
+          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(rptr0), "r"(pos + 1u) : "memory");
+          request((int)atomicAdd(tp.tile_counter, 1u) + NS * step, (int)rs);
+        }
+        asm volatile("atom.release.cta.shared::cta.exch.b32 %0, [%1], 0;" : "=r"(busy) : "r"(lock0) : "memory");
       }
     }
   }

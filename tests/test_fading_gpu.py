@@ -144,6 +144,28 @@ def test_tma_matches_window_kernel_bitwise_model():
     assert torch.equal(y1, y2)
 
 
+@pytest.mark.parametrize("T", [2048, 4080])
+def test_tma_schedule_covers_every_tile(T):
+    """The persistent kernel's dynamic schedule (static first tiles, global counter, in-order slot retirement, end
+    markers) must process every tile exactly once for any tile count around multiples of the SM count and ring depth,
+    including frames whose last tile holds a handful of outputs (it retires almost immediately).  Bitwise against the
+    one-tile-per-CTA window kernel."""
+    import torch
+    from hermespy_b200.kernels import FadingBatch, fading_propagate
+
+    rng = np.random.default_rng(11)
+    p0 = random_fading_params(rng, 9, 8, 2, 2, 30.72e6, 100.0, 4e-7, None, None)
+    blk1 = stack_param_blocks([p0])
+    for B in (1, 2, 49, 50, 147, 148, 149, 295, 296, 297, 443, 445, 889, 1200):
+        blk = {k: (np.repeat(v, B, axis=0) if isinstance(v, np.ndarray) and v.ndim == 3 else v) for k, v in blk1.items()}
+        fb = FadingBatch.from_numpy(**blk)
+        x = torch.view_as_complex(torch.randn((B, 2, T, 2), device="cuda", dtype=torch.float32))
+        y1, i1 = fading_propagate(x, fb, sos_mode="poly_tma", return_info=True)
+        y2, i2 = fading_propagate(x, fb, sos_mode="poly_window", return_info=True)
+        assert i1["variant"] == "tma" and i2["variant"] == "window"
+        assert torch.equal(y1, y2), (B, T)
+
+
 def test_tma_falls_back_for_unaligned_frames():
     err, info = _run_case(B=2, L=14, N=12, ntx=4, nrx=4, T=4100, fs=30.72e6, doppler=100.0, max_delay_s=1.4e-6,
                           precision="f32", sos_mode="poly_tma", io=np.complex64)
