@@ -56,6 +56,39 @@ def test_planner_modes():
     assert st == 0 and info.launches == 3  # coefficient kernel + two antenna chunks (8 + 2)
 
 
+def test_planner_kernel_variants():
+    """Which POLY kernel the planner picks (host logic, no GPU): the persistent TMA kernel for complex64 frames of whole
+    16-sample rows and >= 2048 outputs with delays below 128 samples, the cp.async window kernel otherwise when its walk
+    pays, the gather kernel for the rest; large arrays add the tensor-core GEMM."""
+    V = {0: "gather", 1: "window", 2: "tma"}
+    st, info = _plan()  # C2 shape, three taps in 0..44
+    assert st == 0 and V[info.variant] == "tma" and info.tile == 1024 and info.poly_tile % 1024 == 0
+    st, info = _plan(sos_mode="poly_window")
+    assert st == 0 and V[info.variant] == "gather"  # 3 taps over 44 samples: a dense window walk would be wasted
+    dense = np.arange(0, 45, 3).astype(np.int32)
+    st, info = _plan(sos_mode="poly_window", num_taps=dense.size, tap_delay=dense)
+    assert st == 0 and V[info.variant] == "window"
+    st, info = _plan(sos_mode="poly_gather")
+    assert st == 0 and V[info.variant] == "gather"
+    st, info = _plan(num_samples=15346)  # not a whole number of 16-sample rows: no tensor map
+    assert st == 0 and V[info.variant] != "tma"
+    st, info = _plan(num_samples=1600)  # T + D < 2048: too short for the persistent kernel
+    assert st == 0 and V[info.variant] != "tma"
+    st, info = _plan(io128=True)  # complex128 frames are converted in the load of the window / gather kernels
+    assert st == 0 and V[info.variant] != "tma"
+    st, info = _plan(omega_max=3e4 / 30.72e6)  # fast fading: Taylor windows shorter than the 1024-output tile
+    assert st == 0 and info.poly_tile < 1024 and V[info.variant] != "tma"
+    far = np.array([0, 10, 200], np.int32)
+    st, info = _plan(max_delay=200, tap_delay=far)  # delays beyond the 8 halo rows
+    assert st == 0 and V[info.variant] != "tma"
+    st, info = _plan(num_tx=64, num_rx=64)  # C4: K1 + one z-mode launch over 16 antenna chunks + one 64 x 64 GEMM block
+    assert st == 0 and V[info.variant] == "tma" and info.launches == 3
+    st, info = _plan(num_tx=70, num_rx=66)
+    assert st == 0 and info.launches == 2 + 4
+    st, info = _plan(num_tx=64, num_rx=8)  # not a large array on both sides: chunked fused kernels (4 antennas each)
+    assert st == 0 and info.launches == 1 + 16 if V[info.variant] == "tma" else info.launches == 1 + 8
+
+
 def test_invalid_problems_are_rejected():
     st, _ = _plan(tap_delay=np.array([0, 50, 44], np.int32))
     assert st == _lib.HB_ERR_INVALID  # delay beyond max_delay / not ascending
