@@ -149,6 +149,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.hb_profile_begin.argtypes = []
     lib.hb_profile_end.restype = C.c_int
     lib.hb_profile_end.argtypes = [C.POINTER(ProfileReport)]
+    lib.hb_reserve_sms.restype = C.c_int
+    lib.hb_reserve_sms.argtypes = [C.c_int]
     lib.hb_release.restype = None
     lib.hb_release.argtypes = []
 
@@ -179,6 +181,11 @@ def check(status: int) -> None:
 
 def device_count() -> int:
     return int(load().hb_device_count())
+
+
+def reserve_sms(num_sms: int) -> int:
+    """Keep `num_sms` SMs out of the persistent kernels' grids (room for a concurrent NCCL collective)."""
+    return int(load().hb_reserve_sms(int(num_sms)))
 
 
 def launch_counts() -> dict:

@@ -524,7 +524,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   if (use_tma) {
     tp = pl.tp;
     tp.total_tiles = a.B * tp.ntiles * (pl.large_array ? tp.nchunks : 1);  // z mode: every chunk in ONE launch
-    tma_grid = std::min(tp.total_tiles, device_sm_count());
+    tma_grid = std::min(tp.total_tiles, persistent_sm_count());
     rc = make_x_map(x, a.B, a.ntx, a.T, tp.rows, 1, &xmap);
   }
   for (int tx0 = 0; tx0 < (a.z_mode ? 1 : p->num_tx) && rc == HB_OK; tx0 += pl.ntx_tpl) {

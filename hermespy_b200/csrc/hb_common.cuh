@@ -24,6 +24,7 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int require_device();
 int device_sm_count();
+int persistent_sm_count();  // device_sm_count() minus the SMs set aside by hb_reserve_sms()
 
 // ---- per-kernel accounting (hb_profile_begin/end, hb_launch_counts) -------------------------------
 enum KernelKind {

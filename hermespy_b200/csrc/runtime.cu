@@ -1,6 +1,7 @@
 // Library-wide runtime: error strings, device checks, per-kernel launch accounting.
 #include <stdarg.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -48,6 +49,10 @@ int require_device() {
   }
   return HB_OK;
 }
+
+static std::atomic<int> g_reserved_sms{0};
+
+int persistent_sm_count() { return std::max(1, device_sm_count() - g_reserved_sms.load(std::memory_order_relaxed)); }
 
 int device_sm_count() {
   static int cached[64] = {0};
@@ -147,6 +152,11 @@ int hb_device_count(void) {
     return 0;
   }
   return n;
+}
+
+int hb_reserve_sms(int num_sms) {
+  const int n = num_sms < 0 ? 0 : num_sms;
+  return g_reserved_sms.exchange(n);
 }
 
 void hb_release(void) {

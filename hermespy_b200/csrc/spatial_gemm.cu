@@ -15,7 +15,7 @@ int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int
                                  (int)kGemmSmemBytes));
     attr_set = true;
   }
-  const int sms = device_sm_count();
+  const int sms = persistent_sm_count();
   GemmArgs a;
   a.S = S;
   a.z = z;

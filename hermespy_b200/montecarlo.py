@@ -118,14 +118,31 @@ class GridStatistics:
         return errors, bits, art
 
     # ---- the collective ---------------------------------------------------------------------------------------
-    def all_reduce(self, group=None) -> None:
-        """Sum the statistics over all ranks (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    def all_reduce(self, group=None, async_op: bool = False):
+        """Sum the statistics over all ranks (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+        ONE collective: the integer counters ride along as float64 (exact below 2^53 bits) in a packed ``[cells, 5]``
+        buffer.  With ``async_op`` the collective is enqueued behind the work already on the current stream and runs on
+        the backend's own stream, so the next batch's kernels overlap it; call the returned function to finish
+        (waits and unpacks).  Without it the call is complete on return.
+        """
         import torch.distributed as dist
 
+        torch = _torch()
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return
-        dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(self.counts, op=dist.ReduceOp.SUM, group=group)
+            return (lambda: None) if async_op else None
+        packed = torch.cat((self.stats, self.counts.to(torch.float64)), dim=1)
+        work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+        def finish():
+            work.wait()
+            self.stats.copy_(packed[:, :3])
+            self.counts.copy_(packed[:, 3:].round().to(torch.int64))
+
+        if async_op:
+            return finish
+        finish()
+        return None
 
     # ---- read-out (what ScalarEvaluationResult reports) ---------------------------------------------------------
     def mean(self) -> np.ndarray:

@@ -238,6 +238,11 @@ HB_API int hb_profile_end(hb_profile_report* report);
 /* Release cached device workspaces / streams of the calling process. */
 HB_API void hb_release(void);
 
+/* Leave `num_sms` streaming multiprocessors out of the grids of the persistent kernels (tdl_tma, spatial GEMM) so that a
+ * concurrent collective (the NCCL all-reduce of the evaluator statistics, montecarlo.py) finds room to run instead of
+ * queueing behind a kernel that owns every SM.  0 (default) uses all SMs.  Returns the previous value. */
+HB_API int hb_reserve_sms(int num_sms);
+
 #ifdef __cplusplus
 }
 #endif
