@@ -125,7 +125,9 @@ def load_reference():
         if "sparse" not in sys.modules:
             sys.modules["sparse"] = _make_sparse_module()
         if REFERENCE_ROOT not in sys.path:
-            sys.path.insert(0, REFERENCE_ROOT)
+            # appended, not prepended: the reference tree has its own top-level `tests` package, which must not shadow
+            # this repo's (spawned test workers re-import `tests.*` from the inherited path)
+            sys.path.append(REFERENCE_ROOT)
         _loaded = True
     import hermespy.channel  # noqa: F401
     import hermespy.simulation  # noqa: F401
