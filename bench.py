@@ -13,7 +13,8 @@ re-realized) is 70000 / links steps of identical shape; K steps are 
 * ``e2e``    the same work through the host-buffer C-ABI (``hb_fading_propagate_host``): complex128 host
              buffers (the reference's SignalBlock dtype) in pinned memory, H2D + kernels + D2H inside the timed
              region.
-* ``roofline`` achieved algorithmic HBM bytes/s of the dominant kernel (tdl_poly) from per-launch CUDA events
+* ``roofline`` achieved algorithmic HBM bytes/s of the dominant kernel (the K3+K4 kernel the planner picked: tdl_tma for
+             this shape; accounting kind "tdl_poly") from per-launch CUDA events
              recorded by the library on the launch stream during the timed region, against MEASURED_PEAKS.json.
 * ``cpu_baseline`` the numpy oracle (a restatement of the reference's CPU path) on the host cores, bounded sample.
 
