@@ -9,7 +9,8 @@ path patched in -- and (d) by ``bench.py --impl reference``.  Everything that us
 to the numpy port when no reference is present.
 
 The reference imports ``matplotlib``, ``h5py``, ``ray`` and ``sparse`` at module import time
-and none of them is installed here.  They are replaced by inert stub modules; ``sparse`` gets
+and none of them is installed here.  ``matplotlib`` / ``h5py`` are replaced by inert stub modules, ``ray`` by the
+functional in-process stand-in ``hermespy_b200.shims.ray`` (so ``Simulation.run()`` works); ``sparse`` gets
 a small functional stand-in (dense-backed ``GCXS``/``COO``) because the fading ``state()``
 call-site (hermespy/channel/fading/fading.py:362) and ``ChannelStateInformation``
 (hermespy/core/channel.py:144) need real types.
@@ -115,13 +116,16 @@ def load_reference():
             "mpl_toolkits.mplot3d.art3d",
             "mpl_toolkits.mplot3d.axes3d",
             "h5py",
-            "ray",
         ]
         for n in names:
             if n not in sys.modules:
                 m = _Stub(n)
                 m.__path__ = []  # type: ignore[attr-defined]
                 sys.modules[n] = m
+        # `ray`: a FUNCTIONAL in-process stand-in (hermespy_b200/shims/ray.py) so that Simulation.run() itself works
+        from hermespy_b200.shims import ray as _ray_shim
+
+        _ray_shim.install()
         if "sparse" not in sys.modules:
             sys.modules["sparse"] = _make_sparse_module()
         if REFERENCE_ROOT not in sys.path:

@@ -275,3 +275,44 @@ def test_stochastic_cdl_scenarios_through_dropin(ref, name):
         assert y0.shape == y64.shape == y32.shape and c0.shape == c64.shape
         assert rel_l2(y64, y0) < 1e-10 and rel_l2(c64, c0) < 1e-10
         assert rel_l2(y32, y0) < 1e-5
+
+
+def test_unmodified_simulation_run_with_gpu_channel(ref):
+    """``Simulation.run()`` itself (the reference's Monte-Carlo engine with its queue manager / actor / collector, driven
+    through the in-process ``ray`` stand-in) with the channel on the GPU: every drop launches CUDA kernels."""
+    import ray
+
+    from hermespy_b200 import _lib
+    from hermespy_b200.shims import ray as shim
+
+    if getattr(ray, "__version__", "") != shim.__version__:
+        pytest.skip("a real ray is installed")
+    from hermespy.channel import TDL
+    from hermespy.core import ConsoleMode, dB
+    from hermespy.modem import (BitErrorEvaluator, RootRaisedCosineWaveform, SimplexLink,
+                                SingleCarrierLeastSquaresChannelEstimation, SingleCarrierZeroForcingChannelEqualization)
+    from hermespy.simulation import SNR, Simulation
+
+    simulation = Simulation(console_mode=ConsoleMode.SILENT, num_samples=5, seed=42)
+    tx_device = simulation.new_device(oversampling_factor=4)
+    rx_device = simulation.new_device(oversampling_factor=4)
+    tx_device.noise_level = SNR(dB(20), tx_device)
+    rx_device.noise_level = SNR(dB(20), tx_device)
+    simulation.set_channel(tx_device, rx_device, TDL())
+    link = SimplexLink()
+    tx_device.transmitters.add(link)
+    rx_device.receivers.add(link)
+    link.waveform = RootRaisedCosineWaveform(num_preamble_symbols=10, num_data_symbols=100, roll_off=0.9)
+    link.waveform.channel_estimation = SingleCarrierLeastSquaresChannelEstimation()
+    link.waveform.channel_equalization = SingleCarrierZeroForcingChannelEqualization()
+    simulation.new_dimension("noise_level", dB(20, 10, 0), rx_device)
+    simulation.add_evaluator(BitErrorEvaluator(link, link))
+    before = sum(_lib.launch_counts().values())
+    ref.enable(precision="f64")
+    try:
+        result = simulation.run()
+    finally:
+        ref.disable()
+    ber = np.asarray(result.evaluation_results[0].to_array(), dtype=float).ravel()
+    assert ber.shape == (3,) and np.all((ber >= 0) & (ber <= 0.5 + 1e-9))
+    assert sum(_lib.launch_counts().values()) - before >= 15  # 3 SNR points x 5 drops, at least one kernel each
