@@ -1,1 +1,6 @@
-"""Import shims that let an unmodified HermesPy run where its cluster / plotting dependencies are absent."""
+"""Import shims that let an unmodified HermesPy run where its cluster / plotting / storage dependencies are absent.
+
+    import hermespy_b200.shims as shims
+    shims.install()      # before `import hermespy`; touches only packages that are really missing
+"""
+from .stubs import install  # noqa: F401
