@@ -102,6 +102,49 @@ def test_cdl_oracle_matches_live_reference(ref):
         assert np.linalg.norm(yo - y) <= 5e-12 * np.linalg.norm(y)
 
 
+def test_cdl_oracle_matches_live_reference_stochastic_scenarios(ref):
+    """The 3GPP scenario models (UMa / UMi / RMa / InH / InF) draw their samples differently but hand out the same
+    ``ClusterDelayLineSample``: the oracle (and the kernels behind the drop-in) must follow any cluster count, LOS state
+    and delay structure they produce."""
+    from hermespy.core import Transformation
+    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+
+    from hermespy_b200 import dropin
+    from oracle import cdl_oracle as co
+    from oracle.golden_cases import CDL_FC, CDL_FS, CDL_SPACING
+    from oracle.ref_extract import cdl_params_from_reference_sample
+
+    RC = ref["RC"]
+    rng = np.random.default_rng(9)
+
+    def dev(dims, pos, vel):
+        return SimulatedDevice(bandwidth=CDL_FS, oversampling_factor=1, carrier_frequency=CDL_FC,
+                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, CDL_SPACING, dims),
+                               pose=Transformation.From_Translation(np.array(pos, float)), velocity=np.array(vel, float))
+
+    builders = [
+        lambda: RC.UrbanMacrocells(expected_state=RC.O2IState.LOS, seed=1),
+        lambda: RC.UrbanMacrocells(expected_state=RC.O2IState.O2I, seed=3),
+        lambda: RC.UrbanMicrocells(expected_state=RC.O2IState.NLOS, seed=4),
+        lambda: RC.RuralMacrocells(expected_state=RC.O2IState.LOS, seed=5),
+        lambda: RC.IndoorOffice(expected_state=RC.LOSState.LOS, seed=6),
+        lambda: RC.IndoorFactory(2000.0, 1500.0, RC.FactoryType.DH, expected_state=RC.LOSState.NLOS, seed=7),
+    ]
+    counts = set()
+    for build in builders:
+        tx, rx = dev((2, 2, 1), (0.0, 0.0, 25.0), (0, 0, 0)), dev((2, 1, 1), (120.0, 40.0, 1.5), (3.0, -1.0, 0.0))
+        s = build().realize().sample(tx, rx)
+        x = (rng.standard_normal((4, 120)) + 1j * rng.standard_normal((4, 120))) / np.sqrt(2)
+        y = s.propagate(ref["Signal"].Create(x, CDL_FS, CDL_FC)).view(np.ndarray)
+        yo = co.propagate(cdl_params_from_reference_sample(s), x)
+        assert yo.shape == y.shape and np.linalg.norm(yo - y) <= 5e-12 * np.linalg.norm(y)
+        blk = dropin.cdl_block_from_reference(s)  # what the patched _propagate hands to hb_cdl_propagate_host
+        assert blk.batch == 1 and blk.num_tx == 4 and blk.num_rx == 2 and blk.max_delay == y.shape[1] - 120
+        assert blk.term_delay.size == blk.amplitude.shape[1] == blk.angles.shape[1] and blk.term_delay.max() <= blk.max_delay
+        counts.add(int(s.num_clusters))
+    assert len(counts) >= 4  # the scenarios really produce different cluster counts
+
+
 def test_dropin_extraction_equals_mirror_blocks(ref):
     """The drop-in adapter reads reference samples into the same kernel blocks the mirror classes build."""
     import hermespy_b200.channel as MC
