@@ -111,3 +111,41 @@ def test_no_cpu_fallback():
         fading_propagate_host(x, np.array([0], np.int32), 0, np.zeros((1, 1, 21)), np.zeros((1, 1, 21)),
                               np.ones((1, 1, 2)), np.ones((1, 1, 1), complex))
     assert e.value.status == _lib.HB_ERR_NO_DEVICE
+
+
+def test_planner_fuzz_never_crashes_and_respects_its_own_limits():
+    """Host logic: random shapes / delay tables / Doppler through hb_fading_plan -- every answer is a status code, and an
+    accepted plan is self-consistent (tile sizes, Taylor window multiples, launch counts, error bound)."""
+    rng = np.random.default_rng(2026)
+    V = {0: "gather", 1: "window", 2: "tma"}
+    accepted = {"gather": 0, "window": 0, "tma": 0, "direct": 0}
+    for _ in range(400):
+        ntx, nrx = int(rng.choice([1, 2, 3, 4, 5, 8, 10, 16, 33, 64, 70])), int(rng.choice([1, 2, 4, 7, 8, 16, 40, 64, 66]))
+        T = int(rng.choice([0, 1, 37, 500, 1024, 2048, 4100, 15344, 16384, 1 << 20]))
+        L = int(rng.integers(1, 40))
+        dmax = int(rng.choice([0, 1, 7, 44, 66, 115, 127, 128, 300, 1023, 1500]))
+        delays = np.sort(rng.integers(0, dmax + 1, L)).astype(np.int32)
+        delays[0] = 0 if rng.random() < 0.7 else delays[0]
+        delays[-1] = dmax
+        delays = np.sort(delays).astype(np.int32)
+        omega = float(rng.choice([0.0, 1e-7, 3.3e-6, 1e-4, 1e-2, 0.5]))
+        st, info = _plan(batch=int(rng.integers(0, 5000)), num_tx=ntx, num_rx=nrx, num_samples=T, max_delay=dmax,
+                         num_taps=L, num_sinusoids=int(rng.choice([0, 1, 8, 20])), omega_max=omega, tap_delay=delays,
+                         io128=bool(rng.random() < 0.3), precision=str(rng.choice(["f32", "f32", "f64"])),
+                         sos_mode=str(rng.choice(["auto", "auto", "poly", "direct", "poly_window", "poly_gather", "poly_tma"])))
+        assert st in (0, _lib.HB_ERR_INVALID, _lib.HB_ERR_UNSUPPORTED), st
+        if st != 0:
+            assert _lib.load().hb_last_error()  # a refused problem always says why
+            continue
+        assert info.num_groups == np.unique(delays).size and info.launches >= 1 and info.num_tiles >= 1
+        if info.mode == _lib.HB_SOS_POLY:
+            v = V[info.variant]
+            accepted[v] += 1
+            assert info.error_bound <= 2e-7 and info.poly_order in (1, 2, 3, 4, 6, 8)
+            assert info.poly_tile % info.tile == 0 or v == "gather"
+            if v == "tma":
+                assert info.tile == 1024 and T % 16 == 0 and T + dmax >= 2048 and dmax <= 127
+        else:
+            accepted["direct"] += 1
+            assert info.tile == 256
+    assert all(n > 0 for n in accepted.values()), accepted  # the fuzz reaches every kernel family
