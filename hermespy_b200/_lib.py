@@ -31,6 +31,11 @@ HB_VARIANT_WINDOW = 1
 HB_VARIANT_TMA = 2
 
 HB_MAX_TAPS = 256
+HB_CDL_MAX_TERMS = 1024
+HB_CDL_MAX_GROUPS = 64
+HB_ELEMENT_STRIDE = 12
+HB_ELEMENTS_IDEAL, HB_ELEMENTS_UNIFORM, HB_ELEMENTS_PER_ELEMENT = 0, 1, 2
+HB_ELEMENT_IDEAL, HB_ELEMENT_LINEAR, HB_ELEMENT_PATCH, HB_ELEMENT_DIPOLE = 0, 1, 2, 3
 
 
 class HermesB200Error(RuntimeError):
@@ -111,6 +116,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.hb_last_error.argtypes = []
     lib.hb_device_count.restype = C.c_int
     lib.hb_device_count.argtypes = []
+    lib.hb_set_device.restype = C.c_int
+    lib.hb_set_device.argtypes = [C.c_int]
     lib.hb_fading_plan.restype = C.c_int
     lib.hb_fading_plan.argtypes = [C.POINTER(FadingProblem), C.POINTER(FadingPlanInfo)]
     lib.hb_fading_propagate.restype = C.c_int
@@ -183,6 +190,12 @@ def device_count() -> int:
     return int(load().hb_device_count())
 
 
+def set_device(device) -> None:
+    """Make ``device`` (index, or None = leave as is) the CUDA device of the calling thread (``hb_set_device``)."""
+    if device is not None:
+        check(load().hb_set_device(int(device)))
+
+
 def reserve_sms(num_sms: int) -> int:
     """Keep `num_sms` SMs out of the persistent kernels' grids (room for a concurrent NCCL collective)."""
     return int(load().hb_reserve_sms(int(num_sms)))
@@ -233,6 +246,10 @@ class CdlProblem(C.Structure):
         ("rel_velocity", C.c_void_p),
         ("tx_topology", C.c_void_p),
         ("rx_topology", C.c_void_p),
+        ("element_mode", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("tx_elements", C.c_void_p),
+        ("rx_elements", C.c_void_p),
     ]
 
 

@@ -43,6 +43,10 @@ static int build_cdl_table(const hb_cdl_problem* p, CdlTable* tb) {
     set_error("sampling rate must be positive and carrier frequency non-negative");
     return HB_ERR_INVALID;
   }
+  if (p->element_mode < HB_ELEMENTS_IDEAL || p->element_mode > HB_ELEMENTS_PER_ELEMENT) {
+    set_error("unknown element_mode %d", p->element_mode);
+    return HB_ERR_INVALID;
+  }
   memset(tb, 0, sizeof(*tb));
   tb->num_terms = Rt;
   tb->has_los = p->line_of_sight ? 1 : 0;
@@ -205,6 +209,10 @@ static void fill_args(const hb_cdl_problem* p, const CdlTable& tb, const CdlPlan
   a->rel_velocity = p->rel_velocity;
   a->tx_topology = p->tx_topology;
   a->rx_topology = p->rx_topology;
+  a->tx_elements = p->tx_elements;
+  a->rx_elements = p->rx_elements;
+  a->element_mode = p->element_mode;
+  a->rank = p->element_mode == HB_ELEMENTS_PER_ELEMENT ? 2 : 1;
   a->wavelength_factor = p->carrier_frequency / kSpeedOfLight;
   a->fs = p->sampling_rate;
   a->los_amp = p->los_amplitude;
@@ -225,8 +233,8 @@ static int alloc_rays(CdlArgs* a, CdlWorkspace* ws, cudaStream_t st) {
   const size_t bt = (size_t)a->B * a->Rt;
   HB_CUDA(cudaMallocAsync((void**)&ws->alpha, sizeof(double2) * bt, st));
   HB_CUDA(cudaMallocAsync((void**)&ws->w, sizeof(double) * bt, st));
-  HB_CUDA(cudaMallocAsync((void**)&ws->u, sizeof(double2) * bt * a->nrx, st));
-  HB_CUDA(cudaMallocAsync((void**)&ws->v, sizeof(double2) * bt * a->ntx, st));
+  HB_CUDA(cudaMallocAsync((void**)&ws->u, sizeof(double2) * bt * a->nrx * a->rank, st));
+  HB_CUDA(cudaMallocAsync((void**)&ws->v, sizeof(double2) * bt * a->ntx * a->rank, st));
   a->alpha = ws->alpha;
   a->w = ws->w;
   a->u = ws->u;
@@ -312,7 +320,8 @@ int hb_cdl_propagate(const hb_cdl_problem* p, const void* x, void* y, void* stre
   fill_cdl_info(pl, tb, p, info);
   if (int e = require_device()) return e;
   if (p->batch > 0 && (!x || !y || !p->tx_pose || !p->rx_pose || !p->rel_velocity || !p->tx_topology ||
-                       !p->rx_topology || (p->num_terms > 0 && (!p->angles || !p->jones || !p->amplitude)))) {
+                       !p->rx_topology || (p->num_terms > 0 && (!p->angles || !p->jones || !p->amplitude)) ||
+                       (p->element_mode != HB_ELEMENTS_IDEAL && (!p->tx_elements || !p->rx_elements)))) {
     set_error("NULL device pointer in CDL problem");
     return HB_ERR_INVALID;
   }
@@ -330,7 +339,8 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
   const int Tout = p->num_samples + p->max_delay;
   if (p->batch == 0 || Tout == 0) return HB_OK;
   if (!x || !y || !p->tx_pose || !p->rx_pose || !p->rel_velocity || !p->tx_topology || !p->rx_topology ||
-      (p->num_terms > 0 && (!p->angles || !p->jones || !p->amplitude))) {
+      (p->num_terms > 0 && (!p->angles || !p->jones || !p->amplitude)) ||
+      (p->element_mode != HB_ELEMENTS_IDEAL && (!p->tx_elements || !p->rx_elements))) {
     set_error("NULL host pointer in CDL problem");
     return HB_ERR_INVALID;
   }
@@ -341,6 +351,9 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
   const size_t jon_link = 16 * 4 * (size_t)p->num_terms;
   const size_t amp_link = sizeof(double) * (size_t)p->num_terms;
   const size_t topo_tx = sizeof(double) * 3 * (size_t)p->num_tx, topo_rx = sizeof(double) * 3 * (size_t)p->num_rx;
+  const size_t el_row = sizeof(double) * HB_ELEMENT_STRIDE;
+  const size_t el_tx = p->element_mode == HB_ELEMENTS_IDEAL ? 0 : el_row * (p->element_mode == HB_ELEMENTS_UNIFORM ? 1 : (size_t)p->num_tx);
+  const size_t el_rx = p->element_mode == HB_ELEMENTS_IDEAL ? 0 : el_row * (p->element_mode == HB_ELEMENTS_UNIFORM ? 1 : (size_t)p->num_rx);
   int chunk = chunk_links;
   if (chunk <= 0) {
     chunk = (int)std::max<size_t>(1, (48u << 20) / std::max<size_t>(1, x_link + y_link));
@@ -356,7 +369,7 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
   const size_t off_x = take(x_link * chunk), off_y = take(y_link * chunk), off_ang = take(ang_link * chunk),
                off_jon = take(jon_link * chunk), off_amp = take(amp_link * chunk), off_tp = take(96 * (size_t)chunk),
                off_rp = take(96 * (size_t)chunk), off_rv = take(24 * (size_t)chunk), off_tt = take(topo_tx),
-               off_rt = take(topo_rx);
+               off_rt = take(topo_rx), off_et = take(el_tx), off_er = take(el_rx);
   const size_t total = off;
 
   std::lock_guard<std::mutex> lock(g_pipe.mu);
@@ -378,6 +391,8 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
     q.rel_velocity = (const double*)(base + off_rv);
     q.tx_topology = (const double*)(base + off_tt);
     q.rx_topology = (const double*)(base + off_rt);
+    q.tx_elements = (const double*)(base + off_et);
+    q.rx_elements = (const double*)(base + off_er);
     struct Cp {
       size_t dst;
       const void* src;
@@ -391,6 +406,8 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
         {off_rv, (const char*)p->rel_velocity + 24 * (size_t)b0, 24 * (size_t)nb},
         {off_tt, p->tx_topology, topo_tx},
         {off_rt, p->rx_topology, topo_rx},
+        {off_et, p->tx_elements, el_tx},
+        {off_er, p->rx_elements, el_rx},
         {off_x, (const char*)x + x_link * b0, x_link * nb},
     };
     for (const Cp& c : cps) {

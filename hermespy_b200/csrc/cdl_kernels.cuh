@@ -47,11 +47,15 @@ struct CdlArgs {
   const double* rel_velocity; // [B, 3]
   const double* tx_topology;  // [Ntx, 3]
   const double* rx_topology;  // [Nrx, 3]
+  const double* tx_elements;  // [Ntx or 1, HB_ELEMENT_STRIDE] element models (element_mode != IDEAL)
+  const double* rx_elements;  // [Nrx or 1, HB_ELEMENT_STRIDE]
+  int element_mode;           // hb_element_mode
+  int rank;                   // 1: H_t = alpha u v^T;  2: H_t = sum_c u[:, c] v[:, c]^T (per-element patterns, alpha = 1)
   // ray coefficients (K5 out)
   double2* alpha;  // [B, Rt]
   double* w;       // [B, Rt] rad / sample
-  double2* u;      // [B, Rt, Nrx]
-  double2* v;      // [B, Rt, Ntx]
+  double2* u;      // [B, Rt, Nrx, rank]   receive steering phases (x element polarization when rank == 2)
+  double2* v;      // [B, Rt, Ntx, rank]   transmit steering phases (x amp J F_tx when rank == 2)
   float2* moments; // [B, ntiles, G, P, Nrx, Ntx]
   double wavelength_factor;  // fc / c0
   double fs;
@@ -84,16 +88,61 @@ __device__ __forceinline__ void sph_basis(Vec3 d, Vec3* th, Vec3* ph) {
   *ph = {-sa, ca, 0.0};
 }
 
-// Polarization of an ideal isotropic element ([2^-1/2, 2^-1/2] locally) towards global unit direction g
-// for an element whose orientation is R (core/antennas.py:138-210).
-__device__ __forceinline__ void ideal_polarization(const double* R, Vec3 g, double* f_theta, double* f_phi) {
+// Local field pattern (F_theta, F_phi) of the reference's element models towards the LOCAL unit direction l
+// (core/antennas.py:435-436 ideal, :509-510 linear, :556-560 patch, :610-614 dipole; the reference hands the zenith angle
+// to the parameter it calls "elevation").
+__device__ __forceinline__ void local_pattern(int kind, double param, Vec3 l, double* f0, double* f1) {
+  switch (kind) {
+    case HB_ELEMENT_LINEAR: {
+      double s, c;
+      sincos(param, &s, &c);
+      *f0 = c;
+      *f1 = s;
+      return;
+    }
+    case HB_ELEMENT_PATCH: {
+      const double az = atan2(l.y, l.x);
+      const double cz = fmin(1.0, fmax(-1.0, l.z));
+      const double va = 0.1 + 0.9 * exp(-1.315 * az * az);
+      *f0 = fmax(0.1, va * cz * cz);
+      *f1 = 0.0;
+      return;
+    }
+    case HB_ELEMENT_DIPOLE: {
+      const double cz = fmin(1.0, fmax(-1.0, l.z));
+      const double ze = acos(cz);  // as the reference: the pattern is evaluated on arccos(z)
+      *f0 = ze == 0.0 ? 0.0 : cos(1.5707963267948966 * cos(ze)) / sin(ze);
+      *f1 = 0.0;
+      return;
+    }
+    default:
+      *f0 = 0.70710678118654752440;
+      *f1 = 0.70710678118654752440;
+  }
+}
+
+// Polarization of an element whose orientation is R (element frame -> global) towards global unit direction g:
+// the local pattern rotated into the global theta / phi basis by the 2x2 matrix of TR 38.901 eq. 7.1-12
+// (core/antennas.py:138-210).
+__device__ __forceinline__ void element_polarization(const double* R, Vec3 g, int kind, double param, double* f_theta,
+                                                     double* f_phi) {
   Vec3 thg, phg, thl, phl;
   sph_basis(g, &thg, &phg);
-  sph_basis(mat_t_vec(R, g), &thl, &phl);
+  const Vec3 l = mat_t_vec(R, g);
+  sph_basis(l, &thl, &phl);
   const Vec3 thlt = mat_vec(R, thl), phlt = mat_vec(R, phl);
-  const double s = 0.70710678118654752440;
-  *f_theta = (dot3(thg, thlt) + dot3(thg, phlt)) * s;
-  *f_phi = (dot3(phg, thlt) + dot3(phg, phlt)) * s;
+  double f0, f1;
+  local_pattern(kind, param, l, &f0, &f1);
+  *f_theta = dot3(thg, thlt) * f0 + dot3(thg, phlt) * f1;
+  *f_phi = dot3(phg, thlt) * f0 + dot3(phg, phlt) * f1;
+}
+
+// C = A B for row-major 3x3 matrices
+__device__ __forceinline__ void mat_mul3(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -161,28 +210,80 @@ __global__ void __launch_bounds__(128) cdl_ray_kernel(const CdlArgs a, const __g
   grx = {grx.x / n, grx.y / n, grx.z / n};
   n = sqrt(dot3(gtx, gtx));
   gtx = {gtx.x / n, gtx.y / n, gtx.z / n};
-  double frt, frp, ftt, ftp;
-  ideal_polarization(rp, grx, &frt, &frp);
-  ideal_polarization(tp, gtx, &ftt, &ftp);
-  // F_rx^T J F_tx
-  double2 jt0 = make_double2(j00.x * ftt + j01.x * ftp, j00.y * ftt + j01.y * ftp);
-  double2 jt1 = make_double2(j10.x * ftt + j11.x * ftp, j10.y * ftt + j11.y * ftp);
-  double2 pol = make_double2(frt * jt0.x + frp * jt1.x, frt * jt0.y + frp * jt1.y);
-  a.alpha[(size_t)b * a.Rt + t] = cmul(pol, scale);
   a.w[(size_t)b * a.Rt + t] = kTwoPi * dot3(wave, rv) * a.wavelength_factor / a.fs;
+  double2* u = a.u + ((size_t)b * a.Rt + t) * a.nrx * a.rank;
+  double2* v = a.v + ((size_t)b * a.Rt + t) * a.ntx * a.rank;
 
-  double2* u = a.u + ((size_t)b * a.Rt + t) * a.nrx;
+  if (a.rank == 1) {
+    // identical, identically oriented elements: one polarization pair per array, H_t = alpha u v^T
+    double frt, frp, ftt, ftp;
+    if (a.element_mode == HB_ELEMENTS_IDEAL) {
+      element_polarization(rp, grx, HB_ELEMENT_IDEAL, 0.0, &frt, &frp);
+      element_polarization(tp, gtx, HB_ELEMENT_IDEAL, 0.0, &ftt, &ftp);
+    } else {
+      double Rr[9], Rt_[9];
+      mat_mul3(rp, a.rx_elements, Rr);
+      mat_mul3(tp, a.tx_elements, Rt_);
+      element_polarization(Rr, grx, (int)a.rx_elements[9], a.rx_elements[10], &frt, &frp);
+      element_polarization(Rt_, gtx, (int)a.tx_elements[9], a.tx_elements[10], &ftt, &ftp);
+    }
+    // F_rx^T J F_tx
+    double2 jt0 = make_double2(j00.x * ftt + j01.x * ftp, j00.y * ftt + j01.y * ftp);
+    double2 jt1 = make_double2(j10.x * ftt + j11.x * ftp, j10.y * ftt + j11.y * ftp);
+    double2 pol = make_double2(frt * jt0.x + frp * jt1.x, frt * jt0.y + frp * jt1.y);
+    a.alpha[(size_t)b * a.Rt + t] = cmul(pol, scale);
+    for (int i = 0; i < a.nrx; ++i) {
+      const double dx = a.rx_topology[i * 3] - lrx.x, dy = a.rx_topology[i * 3 + 1] - lrx.y,
+                   dz = a.rx_topology[i * 3 + 2] - lrx.z;
+      u[i] = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+    }
+    for (int j = 0; j < a.ntx; ++j) {
+      const double dx = a.tx_topology[j * 3] - ltx.x, dy = a.tx_topology[j * 3 + 1] - ltx.y,
+                   dz = a.tx_topology[j * 3 + 2] - ltx.z;
+      v[j] = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+    }
+    return;
+  }
+  // per-element patterns / orientations: a_rx[i, :] = u_i F_rx,i and (scale J F_tx,j) v_j are stored per polarization
+  // component; H_t[i, j] = sum_c u[i, c] v[j, c]  (a_rx J a_tx^T, cluster_delay_lines.py:481-486)
+  a.alpha[(size_t)b * a.Rt + t] = make_double2(1.0, 0.0);
   for (int i = 0; i < a.nrx; ++i) {
+    const double* el = a.rx_elements + (size_t)i * HB_ELEMENT_STRIDE;
+    double Rm[9], ft, fp;
+    mat_mul3(rp, el, Rm);
+    element_polarization(Rm, grx, (int)el[9], el[10], &ft, &fp);
     const double dx = a.rx_topology[i * 3] - lrx.x, dy = a.rx_topology[i * 3 + 1] - lrx.y,
                  dz = a.rx_topology[i * 3 + 2] - lrx.z;
-    u[i] = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+    const double2 ph = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+    u[2 * i] = make_double2(ph.x * ft, ph.y * ft);
+    u[2 * i + 1] = make_double2(ph.x * fp, ph.y * fp);
   }
-  double2* v = a.v + ((size_t)b * a.Rt + t) * a.ntx;
   for (int j = 0; j < a.ntx; ++j) {
+    const double* el = a.tx_elements + (size_t)j * HB_ELEMENT_STRIDE;
+    double Rm[9], ft, fp;
+    mat_mul3(tp, el, Rm);
+    element_polarization(Rm, gtx, (int)el[9], el[10], &ft, &fp);
     const double dx = a.tx_topology[j * 3] - ltx.x, dy = a.tx_topology[j * 3 + 1] - ltx.y,
                  dz = a.tx_topology[j * 3 + 2] - ltx.z;
-    v[j] = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+    const double2 ph = phasor_neg_turns(sqrt(dx * dx + dy * dy + dz * dz) * a.wavelength_factor);
+    const double2 jf0 = cmul(make_double2(j00.x * ft + j01.x * fp, j00.y * ft + j01.y * fp), scale);
+    const double2 jf1 = cmul(make_double2(j10.x * ft + j11.x * fp, j10.y * ft + j11.y * fp), scale);
+    v[2 * j] = cmul(jf0, ph);
+    v[2 * j + 1] = cmul(jf1, ph);
   }
+}
+
+// Entry (i, j) of the unit-amplitude ray matrix of term t: u_i v_j (rank one) or sum_c u[i, c] v[j, c] (rank two).
+__device__ __forceinline__ double2 ray_entry(const CdlArgs& a, int b, int t, int i, int j) {
+  const double2* u = a.u + (((size_t)b * a.Rt + t) * a.nrx + i) * a.rank;
+  const double2* v = a.v + (((size_t)b * a.Rt + t) * a.ntx + j) * a.rank;
+  double2 r = cmul(u[0], v[0]);
+  if (a.rank == 2) {
+    const double2 r1 = cmul(u[1], v[1]);
+    r.x += r1.x;
+    r.y += r1.y;
+  }
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -223,9 +324,8 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
         const int nc = min(64, t1 - c0);
         for (int k = 0; k < nc; ++k) {
           const int t = tb.term_order[c0 + k];
-          const double2 uu = a.u[((size_t)b * a.Rt + t) * a.nrx + i];
-          const double2 vv = a.v[((size_t)b * a.Rt + t) * a.ntx + j];
-          const float uvr = (float)(uu.x * vv.x - uu.y * vv.y), uvi = (float)(uu.x * vv.y + uu.y * vv.x);
+          const double2 uv = ray_entry(a, b, t, i, j);
+          const float uvr = (float)uv.x, uvi = (float)uv.y;
           float tr = beta[k].x * uvr - beta[k].y * uvi, ti = beta[k].x * uvi + beta[k].y * uvr;
           accr[0] += tr;
           acci[0] += ti;
@@ -361,19 +461,34 @@ __global__ void __launch_bounds__(128) cdl_direct_f64_kernel(const CdlArgs a, co
     for (int t = 0; t < a.Rt; ++t) {
       const int n = m - (int)tb.term_delay[t];
       if (n < 0 || n >= a.T) continue;
-      const double2* v = a.v + ((size_t)b * a.Rt + t) * a.ntx;
-      double2 s = make_double2(0.0, 0.0);
-      for (int j = 0; j < a.ntx; ++j) {
-        const double2 xv = to_c64(xb[(size_t)j * a.T + n]);
-        cmac<double>(s, v[j], xv);
+      const double2* v = a.v + ((size_t)b * a.Rt + t) * a.ntx * a.rank;
+      double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
+      if (a.rank == 1) {
+        for (int j = 0; j < a.ntx; ++j) cmac<double>(s0, v[j], to_c64(xb[(size_t)j * a.T + n]));
+      } else {
+        for (int j = 0; j < a.ntx; ++j) {
+          const double2 xv = to_c64(xb[(size_t)j * a.T + n]);
+          cmac<double>(s0, v[2 * j], xv);
+          cmac<double>(s1, v[2 * j + 1], xv);
+        }
       }
       double sn, cs;
       sincos(a.w[(size_t)b * a.Rt + t] * (double)n, &sn, &cs);
-      const double2 g = cmul(cmul(a.alpha[(size_t)b * a.Rt + t], make_double2(cs, sn)), s);
-      const double2* u = a.u + ((size_t)b * a.Rt + t) * a.nrx;
+      const double2 e = cmul(a.alpha[(size_t)b * a.Rt + t], make_double2(cs, sn));
+      const double2 g0 = cmul(e, s0), g1 = cmul(e, s1);
+      const double2* u = a.u + ((size_t)b * a.Rt + t) * a.nrx * a.rank;
+      if (a.rank == 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i0 + i < a.nrx) cmac<double>(acc[i], u[i0 + i], g);
+        for (int i = 0; i < 8; ++i)
+          if (i0 + i < a.nrx) cmac<double>(acc[i], u[i0 + i], g0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i0 + i < a.nrx) {
+            cmac<double>(acc[i], u[2 * (i0 + i)], g0);
+            cmac<double>(acc[i], u[2 * (i0 + i) + 1], g1);
+          }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -402,7 +517,7 @@ __global__ void __launch_bounds__(128) cdl_state_kernel(const CdlArgs a, const _
     const int t = tb.term_order[c];
     double sn, cs;
     sincos(a.w[(size_t)b * a.Rt + t] * (double)n, &sn, &cs);
-    const double2 uv = cmul(a.u[((size_t)b * a.Rt + t) * a.nrx + i], a.v[((size_t)b * a.Rt + t) * a.ntx + j]);
+    const double2 uv = ray_entry(a, b, t, i, j);
     cmac<double>(h, cmul(a.alpha[(size_t)b * a.Rt + t], make_double2(cs, sn)), uv);
   }
   IO* out = reinterpret_cast<IO*>(a.y) + ((((size_t)b * tb.num_groups + g) * nij + ij) * a.T) + n;

@@ -154,6 +154,21 @@ int hb_device_count(void) {
   return n;
 }
 
+int hb_set_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible; libhermes_b200 has no CPU fallback");
+    return HB_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d outside [0, %d)", device, n);
+    return HB_ERR_INVALID;
+  }
+  HB_CUDA(cudaSetDevice(device));
+  return HB_OK;
+}
+
 int hb_reserve_sms(int num_sms) {
   const int n = num_sms < 0 ? 0 : num_sms;
   return g_reserved_sms.exchange(n);

@@ -16,6 +16,11 @@ cluster_delay_lines.py:321-403), lay out the same kernel parameter blocks the mi
 use, and call the host-buffer C-ABI (``hb_fading_propagate_host`` / ``hb_cdl_propagate_host``).  Realization,
 sampling, hooks, Signal bookkeeping, serialization and the whole drop loop remain the reference's own code.
 The functions are module-level (picklable), so Ray actors that import this module inherit the patch.
+
+There is NO fallback into the reference's numpy code: a sample the kernels cannot serve (a user-defined antenna
+element class without a device pattern, a delay spread beyond the planner's limits) raises ``HermesB200Error``.
+``enable(allow_reference_fallback=True)`` is the only way to let such samples run the saved reference methods; every use
+is counted in ``fallbacks`` and warned about once.
 """
 from __future__ import annotations
 
@@ -26,6 +31,30 @@ import numpy as np
 from . import config
 
 _ORIGINALS = {}
+#: opt-in only (``enable(allow_reference_fallback=True)``): samples served by the saved reference methods, per kind
+fallbacks = {"fading_propagate": 0, "fading_state": 0, "cdl_propagate": 0, "cdl_state": 0}
+_allow_fallback = False
+_warned = set()
+
+
+class UnsupportedByKernels(Exception):
+    """A reference sample the CUDA kernels have no model for (carries the reason)."""
+
+
+def _unsupported(kind: str, why: str, self, *args):
+    """No silent CPU path: raise, unless the user opted into the reference fallback (counted + warned once)."""
+    from . import _lib
+
+    if not _allow_fallback:
+        raise _lib.HermesB200Error(_lib.HB_ERR_UNSUPPORTED, f"{kind}: {why} (hermespy_b200 has no CPU fallback; "
+                                   "dropin.enable(allow_reference_fallback=True) opts into the reference code)")
+    fallbacks[kind] += 1
+    if kind not in _warned:
+        import warnings
+
+        _warned.add(kind)
+        warnings.warn(f"hermespy_b200.dropin: {kind} served by the reference's CPU code ({why})", RuntimeWarning)
+    return _ORIGINALS[kind](self, *args)
 
 
 # ---- parameter extraction from reference objects (pure host code, testable without a GPU) --------------------
@@ -46,20 +75,34 @@ def fading_block_from_reference(sample) -> dict:
                 spatial=spatial, omega_max=float(max(abs(sample.los_doppler), abs(sample.nlos_doppler)) / fs))
 
 
-def _ideal_uniform(antennas_state) -> bool:
-    try:
-        from hermespy.core.antennas import IdealAntenna  # type: ignore
+def element_table(antennas) -> np.ndarray:
+    """Rows ``[rotation element -> array frame (9), hb_element_kind, parameter, 0]`` of reference ``Antenna`` objects
+    (core/antennas.py:392-622).  Subclasses of the four models that override ``local_characteristics`` -- and any other
+    user-defined element -- have no device pattern."""
+    from hermespy.core.antennas import Dipole, IdealAntenna, LinearAntenna, PatchAntenna  # type: ignore
 
-        return all(isinstance(a, IdealAntenna) for a in antennas_state.antennas)
-    except Exception:
-        return False
+    from . import _lib
+
+    kinds = ((LinearAntenna, _lib.HB_ELEMENT_LINEAR), (PatchAntenna, _lib.HB_ELEMENT_PATCH),
+             (Dipole, _lib.HB_ELEMENT_DIPOLE), (IdealAntenna, _lib.HB_ELEMENT_IDEAL))
+    rows = np.zeros((len(antennas), _lib.HB_ELEMENT_STRIDE))
+    for m, a in enumerate(antennas):
+        for base, kind in kinds:
+            if isinstance(a, base) and type(a).local_characteristics is base.local_characteristics:
+                rows[m, 9] = kind
+                rows[m, 10] = a.slant if kind == _lib.HB_ELEMENT_LINEAR else 0.0
+                break
+        else:
+            raise UnsupportedByKernels(f"antenna element {type(a).__name__} has no CUDA pattern model "
+                                       "(supported: IdealAntenna, LinearAntenna, PatchAntenna, Dipole)")
+        rows[m, :9] = np.asarray(a.pose, dtype=np.float64)[:3, :3].ravel()
+    return rows
 
 
 def cdl_block_from_reference(sample):
     """``kernels.CdlBlock`` (B = 1) of a reference ``ClusterDelayLineSample``.
 
-    Raises ``NotImplementedError`` for antenna elements other than ideal isotropic ones (the CUDA ray kernel
-    implements the ideal element's polarization model, core/antennas.py:138-210 with a constant local pattern).
+    Raises ``UnsupportedByKernels`` for antenna element classes without a device pattern (``element_table``).
     """
     from hermespy.core import AntennaMode  # type: ignore
 
@@ -67,8 +110,7 @@ def cdl_block_from_reference(sample):
     from .kernels import CdlBlock
 
     tx_a, rx_a = sample.transmitter_antennas, sample.receiver_antennas
-    if not (_ideal_uniform(tx_a) and _ideal_uniform(rx_a)):
-        raise NotImplementedError("hermespy_b200 CDL kernels support ideal isotropic antenna elements only")
+    tx_el, rx_el = element_table(list(tx_a.transmit_antennas)), element_table(list(rx_a.receive_antennas))
     fs = sample.bandwidth
     C_, R_ = sample.num_clusters, sample.num_rays
     nsplit = min(2, C_)
@@ -104,7 +146,7 @@ def cdl_block_from_reference(sample):
         rx_topology=np.asarray(rx_a._topology(AntennaMode.RX), dtype=np.float64),
         carrier_frequency=sample.carrier_frequency, sampling_rate=fs, line_of_sight=bool(sample.line_of_sight),
         los_delay=int((sample.cluster_delays[0] + sample.delay_offset) * fs),
-        los_amplitude=float((rice_lin / (1 + rice_lin)) ** 0.5))
+        los_amplitude=float((rice_lin / (1 + rice_lin)) ** 0.5), tx_elements=tx_el, rx_elements=rx_el)
 
 
 # ---- replacement methods (module level => picklable) ------------------------------------------------------------
@@ -123,7 +165,7 @@ def _fading_propagate(self, signal, interpolation):
         x = np.ascontiguousarray(np.asarray(signal, dtype=np.complex128))[None]
         out = fading_propagate_host(x, b["tap_delay"], b["max_delay"], b["omega"][None], b["phi"][None], b["amp"][None],
                                     b["spatial"][None], omega_max=b["omega_max"], precision=config.precision,
-                                    sos_mode=config.sos_mode)[0]
+                                    sos_mode=config.sos_mode, device=config.device)[0]
     return SignalBlock(out.shape[0], out.shape[1], signal.offset, out.tobytes())
 
 
@@ -134,19 +176,22 @@ def _fading_state(self, num_samples, max_num_taps, interpolation_mode=None):
     from hermespy.core import ChannelStateFormat, ChannelStateInformation  # type: ignore
     from sparse import GCXS  # type: ignore
 
+    from . import _lib
     from .kernels import FadingBatch, fading_state
 
     b = fading_block_from_reference(self)
     num_taps = min(1 + b["max_delay"], max_num_taps)
-    keep = b["tap_delay"] <= num_taps  # the reference skips taps with d_l > num_taps (fading.py:355) ...
-    if num_samples < 1 or num_taps < 1 or not np.any(keep) or np.any(b["tap_delay"][keep] >= num_taps):
-        return _ORIGINALS["fading_state"](self, num_samples, max_num_taps)  # ... and raises for d_l == num_taps
-    fb = FadingBatch.from_numpy(b["tap_delay"][keep], b["max_delay"], b["omega"][None][:, keep], b["phi"][None][:, keep],
-                                b["amp"][None][:, keep], b["spatial"][None], omega_max=b["omega_max"],
-                                device=f"cuda:{config.device}")
-    h, group_delay = fading_state(fb, int(num_samples), precision=config.precision, io128=True)
     siso_csi = np.zeros((num_samples, num_taps), dtype=np.complex128)
-    siso_csi[:, group_delay] = h[0].cpu().numpy().T
+    keep = b["tap_delay"] <= num_taps  # the reference skips taps with d_l > num_taps (fading.py:355) ...
+    if np.any(b["tap_delay"][keep] >= num_taps):  # ... and indexes out of bounds for d_l == num_taps (:358)
+        raise IndexError(f"index {num_taps} is out of bounds for axis 1 with size {num_taps}")
+    if num_samples >= 1 and num_taps >= 1 and np.any(keep):
+        _lib.set_device(config.device)
+        fb = FadingBatch.from_numpy(b["tap_delay"][keep], b["max_delay"], b["omega"][None][:, keep],
+                                    b["phi"][None][:, keep], b["amp"][None][:, keep], b["spatial"][None],
+                                    omega_max=b["omega_max"], device=f"cuda:{config.device}")
+        h, group_delay = fading_state(fb, int(num_samples), precision=config.precision, io128=True)
+        siso_csi[:, group_delay] = h[0].cpu().numpy().T
     mimo_csi = GCXS.from_numpy(np.einsum("ij,kl->ijkl", self.spatial_response, siso_csi), compressed_axes=(0, 1, 2))
     return ChannelStateInformation(ChannelStateFormat.IMPULSE_RESPONSE, mimo_csi, num_delay_taps=num_taps)
 
@@ -159,13 +204,13 @@ def _cdl_propagate(self, signal, interpolation):
 
     try:
         blk = cdl_block_from_reference(self)
-    except NotImplementedError:
-        return _ORIGINALS["cdl_propagate"](self, signal, interpolation)  # non-ideal elements: reference code
+    except UnsupportedByKernels as e:
+        return _unsupported("cdl_propagate", str(e), self, signal, interpolation)
     if interpolation != InterpolationMode.NEAREST:
         out = np.zeros((self.num_receive_antennas, signal.num_samples + blk.max_delay), dtype=np.complex128)
     else:
         x = np.ascontiguousarray(np.asarray(signal, dtype=np.complex128))[None]
-        out = cdl_propagate_host(x, blk, precision=config.precision)[0]
+        out = cdl_propagate_host(x, blk, precision=config.precision, device=config.device)[0]
     return SignalBlock(out.shape[0], out.shape[1], signal._offset, out.tobytes())
 
 
@@ -174,33 +219,44 @@ def _cdl_state(self, num_samples, max_num_taps, interpolation_mode=None):
     ``hb_cdl_state`` (FP64 ray synthesis), scattered into the reference's dense [Nrx, Ntx, T, 1 + D] container."""
     from hermespy.core import ChannelStateFormat, ChannelStateInformation  # type: ignore
 
+    from . import _lib
     from .kernels import CdlDeviceBlock, cdl_state
 
     try:
         blk = cdl_block_from_reference(self)
-    except NotImplementedError:
-        return _ORIGINALS["cdl_state"](self, num_samples, max_num_taps)
-    if num_samples < 1:
-        return _ORIGINALS["cdl_state"](self, num_samples, max_num_taps)
+    except UnsupportedByKernels as e:
+        return _unsupported("cdl_state", str(e), self, num_samples, max_num_taps)
     D = min(max_num_taps, blk.max_delay)
-    h, gd = cdl_state(CdlDeviceBlock(blk, device=f"cuda:{config.device}"), int(num_samples))
-    h = h[0].cpu().numpy()  # [G, Nrx, Ntx, T]
     raw_state = np.zeros((blk.num_rx, blk.num_tx, num_samples, 1 + D), dtype=np.complex128)
-    for g, d in enumerate(gd):
-        if d < max_num_taps:  # cluster_delay_lines.py:583-584
-            raw_state[:, :, :, d] = h[g]
+    if num_samples >= 1:
+        _lib.set_device(config.device)
+        h, gd = cdl_state(CdlDeviceBlock(blk, device=f"cuda:{config.device}"), int(num_samples))
+        h = h[0].cpu().numpy()  # [G, Nrx, Ntx, T]
+        for g, d in enumerate(gd):
+            if d < max_num_taps:  # cluster_delay_lines.py:583-584
+                raw_state[:, :, :, d] = h[g]
     return ChannelStateInformation(ChannelStateFormat.IMPULSE_RESPONSE, raw_state)
 
 
-def enable(precision: str = "f32") -> None:
-    """Patch the reference classes.  Fails loudly when the library or a CUDA device is missing."""
+def enable(precision: str = "f32", device: int | None = None, allow_reference_fallback: bool = False) -> None:
+    """Patch the reference classes.  Fails loudly when the library or a CUDA device is missing.
+
+    ``device``: CUDA device index every patched call runs on, from whatever thread it is made (None keeps
+    ``config.device``; one process per GPU passes its local rank).  ``allow_reference_fallback``: see module docstring.
+    """
+    global _allow_fallback
     from . import _lib
 
     if _lib.device_count() < 1:
         raise _lib.HermesB200Error(_lib.HB_ERR_NO_DEVICE, "no CUDA device visible; hermespy_b200 has no CPU fallback")
     if precision not in ("f32", "f64"):
         raise ValueError("precision must be 'f32' or 'f64'")
+    if device is not None:
+        if not 0 <= int(device) < _lib.device_count():
+            raise ValueError(f"device {device} outside the {_lib.device_count()} visible CUDA devices")
+        config.device = int(device)
     config.precision = precision
+    _allow_fallback = bool(allow_reference_fallback)
     patch_reference()
 
 

@@ -278,12 +278,15 @@ def fading_propagate_host(
     out: Optional[np.ndarray] = None,
     chunk_links: int = 0,
     return_info=False,
+    device: Optional[int] = None,
 ):
     """Host-buffer entry (what a drop-in plugin calls): numpy in, numpy out, copies inside the call.
 
-    ``x`` is ``[B, Ntx, T]`` complex64 or complex128 (the reference's ``SignalBlock`` dtype).
+    ``x`` is ``[B, Ntx, T]`` complex64 or complex128 (the reference's ``SignalBlock`` dtype).  ``device``: CUDA device
+    index the call runs on (``hb_set_device`` on the calling thread; None = the thread's current device).
     """
     lib = _lib.load()
+    _lib.set_device(device)
     x = np.ascontiguousarray(x)
     if x.dtype not in (np.complex64, np.complex128):
         raise ValueError("x must be complex64 or complex128")
@@ -385,7 +388,7 @@ def spatial_gemm(spatial, z, out=None):
     ``[B, Nrx, Ntx]``, ``z``: device complex64 ``[B, Ntx, T]``; returns device complex64 ``[B, Nrx, T]``."""
     torch = _torch()
     if not (spatial.is_cuda and z.is_cuda):
-        raise HermesB200Error(_lib.HB_ERR_NO_DEVICE, "hb_spatial_gemm_3xtf32 needs device tensors (no CPU fallback)")
+        raise _lib.HermesB200Error(_lib.HB_ERR_NO_DEVICE, "hb_spatial_gemm_3xtf32 needs device tensors (no CPU fallback)")
     s = spatial.to(torch.complex128).contiguous()
     zz = z.to(torch.complex64).contiguous()
     B, nrx, ntx = (int(v) for v in s.shape)
@@ -400,6 +403,17 @@ def spatial_gemm(spatial, z, out=None):
                                                       C.c_void_p(st)))
     return out
 
+
+
+def ideal_elements(n: int) -> np.ndarray:
+    """Element table of ``n`` unrotated ideal isotropic elements."""
+    t = np.zeros((int(n), _lib.HB_ELEMENT_STRIDE))
+    t[:, [0, 4, 8]] = 1.0
+    return t
+
+
+def _all_plain_ideal(table: np.ndarray) -> bool:
+    return bool(np.all(table == ideal_elements(table.shape[0])))
 
 
 @dataclass
@@ -422,6 +436,10 @@ class CdlBlock:
     los_delay: int = 0
     los_amplitude: float = 0.0
     max_speed: Optional[float] = None
+    #: antenna element models, rows of ``HB_ELEMENT_STRIDE`` doubles (rotation element -> array frame, kind, parameter);
+    #: None = unrotated ideal isotropic elements (include/hermes_b200.h, hb_element_mode)
+    tx_elements: Optional[np.ndarray] = None
+    rx_elements: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.term_delay = np.ascontiguousarray(self.term_delay, dtype=np.int32)
@@ -435,6 +453,25 @@ class CdlBlock:
         self.rx_topology = np.ascontiguousarray(self.rx_topology, dtype=np.float64)
         if self.max_speed is None:
             self.max_speed = float(np.linalg.norm(self.rel_velocity, axis=-1).max()) if self.rel_velocity.size else 0.0
+        if (self.tx_elements is None) != (self.rx_elements is None):
+            ideal = ideal_elements  # one side given: the other is an array of unrotated ideal elements
+            self.tx_elements = ideal(self.tx_topology.shape[0]) if self.tx_elements is None else self.tx_elements
+            self.rx_elements = ideal(self.rx_topology.shape[0]) if self.rx_elements is None else self.rx_elements
+        if self.tx_elements is not None:
+            self.tx_elements = np.ascontiguousarray(self.tx_elements, dtype=np.float64).reshape(-1, _lib.HB_ELEMENT_STRIDE)
+            self.rx_elements = np.ascontiguousarray(self.rx_elements, dtype=np.float64).reshape(-1, _lib.HB_ELEMENT_STRIDE)
+            if self.tx_elements.shape[0] != self.num_tx or self.rx_elements.shape[0] != self.num_rx:
+                raise ValueError("element tables need one row per antenna")
+            if _all_plain_ideal(self.tx_elements) and _all_plain_ideal(self.rx_elements):
+                self.tx_elements = self.rx_elements = None
+
+    @property
+    def element_mode(self) -> int:
+        """``hb_element_mode``: ideal / uniform (all rows of each table equal: rank-one ray matrices) / per element."""
+        if self.tx_elements is None:
+            return _lib.HB_ELEMENTS_IDEAL
+        uniform = all(np.all(t == t[:1]) for t in (self.tx_elements, self.rx_elements))
+        return _lib.HB_ELEMENTS_UNIFORM if uniform else _lib.HB_ELEMENTS_PER_ELEMENT
 
     @property
     def batch(self) -> int:
@@ -449,6 +486,14 @@ class CdlBlock:
         return int(self.rx_topology.shape[0])
 
     ARRAYS = ("angles", "jones", "amplitude", "tx_pose", "rx_pose", "rel_velocity", "tx_topology", "rx_topology")
+    ELEMENT_ARRAYS = ("tx_elements", "rx_elements")
+
+    def pointers(self, getter) -> dict:
+        """Field -> address through ``getter(array)`` (host: ``a.ctypes.data``, device: tensor ``data_ptr``)."""
+        d = {k: getter(getattr(self, k)) for k in self.ARRAYS}
+        for k in self.ELEMENT_ARRAYS:
+            d[k] = getter(getattr(self, k)) if self.tx_elements is not None else None
+        return d
 
     @classmethod
     def stack(cls, blocks) -> "CdlBlock":
@@ -461,11 +506,12 @@ class CdlBlock:
             rel_velocity=np.concatenate([b.rel_velocity for b in blocks]), tx_topology=b0.tx_topology,
             rx_topology=b0.rx_topology, carrier_frequency=b0.carrier_frequency, sampling_rate=b0.sampling_rate,
             line_of_sight=b0.line_of_sight, los_delay=b0.los_delay, los_amplitude=b0.los_amplitude,
-            max_speed=max(b.max_speed for b in blocks))
+            max_speed=max(b.max_speed for b in blocks), tx_elements=b0.tx_elements, rx_elements=b0.rx_elements)
 
     def group_key(self):
+        el = b"" if self.tx_elements is None else self.tx_elements.tobytes() + self.rx_elements.tobytes()
         return (self.term_delay.tobytes(), self.max_delay, self.tx_topology.tobytes(), self.rx_topology.tobytes(),
-                self.carrier_frequency, self.sampling_rate, self.line_of_sight, self.los_delay, self.los_amplitude)
+                self.carrier_frequency, self.sampling_rate, self.line_of_sight, self.los_delay, self.los_amplitude, el)
 
 
 def _cdl_problem(blk: CdlBlock, num_samples: int, precision, io128: bool, ptrs: dict):
@@ -495,24 +541,28 @@ def _cdl_problem(blk: CdlBlock, num_samples: int, precision, io128: bool, ptrs: 
     p.rel_velocity = ptrs["rel_velocity"]
     p.tx_topology = ptrs["tx_topology"]
     p.rx_topology = ptrs["rx_topology"]
+    p.element_mode = blk.element_mode
+    p.tx_elements = ptrs.get("tx_elements")
+    p.rx_elements = ptrs.get("rx_elements")
     return p
 
 
 def cdl_plan(blk: CdlBlock, num_samples: int, precision="f32") -> dict:
     lib = _lib.load()
-    p = _cdl_problem(blk, num_samples, precision, False, {k: None for k in CdlBlock.ARRAYS})
+    p = _cdl_problem(blk, num_samples, precision, False, {k: None for k in CdlBlock.ARRAYS})  # planning reads no arrays
     info = FadingPlanInfo()
     _lib.check(lib.hb_cdl_plan(C.byref(p), C.byref(info)))
     return _info_dict(info)
 
 
 def cdl_propagate_host(x: np.ndarray, blk: CdlBlock, precision="f32", out: Optional[np.ndarray] = None,
-                       chunk_links: int = 0, return_info=False):
+                       chunk_links: int = 0, return_info=False, device: Optional[int] = None):
     """Host-buffer CDL propagation: ``x[B, Ntx, T]`` numpy complex64/128 -> ``y[B, Nrx, T + D]``.
 
     GPU counterpart of ``ClusterDelayLineSample._propagate`` (cluster_delay_lines.py:526-558) for a batch.
     """
     lib = _lib.load()
+    _lib.set_device(device)
     x = np.ascontiguousarray(x)
     if x.dtype not in (np.complex64, np.complex128):
         raise ValueError("x must be complex64 or complex128")
@@ -527,7 +577,7 @@ def cdl_propagate_host(x: np.ndarray, blk: CdlBlock, precision="f32", out: Optio
         out = np.empty((blk.batch, blk.num_rx, Tout), dtype=x.dtype)
     elif out.shape != (blk.batch, blk.num_rx, Tout) or out.dtype != x.dtype or not out.flags.c_contiguous:
         raise ValueError("out has the wrong shape / dtype / layout")
-    p = _cdl_problem(blk, T, precision, x.dtype == np.complex128, {k: getattr(blk, k).ctypes.data for k in CdlBlock.ARRAYS})
+    p = _cdl_problem(blk, T, precision, x.dtype == np.complex128, blk.pointers(lambda a: a.ctypes.data))
     info = FadingPlanInfo()
     _lib.check(lib.hb_cdl_propagate_host(C.byref(p), x.ctypes.data, out.ctypes.data, int(chunk_links), C.byref(info)))
     if return_info:
@@ -541,7 +591,8 @@ class CdlDeviceBlock(object):
     def __init__(self, blk: CdlBlock, device="cuda") -> None:
         torch = _torch()
         self.host = blk
-        self.tensors = {k: torch.from_numpy(getattr(blk, k)).to(device) for k in CdlBlock.ARRAYS}
+        names = CdlBlock.ARRAYS + (CdlBlock.ELEMENT_ARRAYS if blk.tx_elements is not None else ())
+        self.tensors = {k: torch.from_numpy(getattr(blk, k)).to(device) for k in names}
         self.device = self.tensors["angles"].device
 
 
@@ -549,9 +600,11 @@ def cdl_propagate(x, dblk: CdlDeviceBlock, precision="f32", out=None, return_inf
     """Device-resident CDL propagation on torch's current stream (no synchronization)."""
     torch = _torch()
     lib = _lib.load()
-    blk = dblk.host
     if not x.is_cuda:
         raise _lib.HermesB200Error(_lib.HB_ERR_NO_DEVICE, "x must be a CUDA tensor (no CPU fallback)")
+    blk = dblk.host
+    if x.dtype not in (torch.complex64, torch.complex128):
+        raise ValueError("x must be complex64 or complex128")
     if x.dim() != 3 or x.shape[0] != blk.batch or x.shape[1] != blk.num_tx:
         raise ValueError("x must have shape [B, Ntx, T] matching the parameter block")
     x = x.contiguous()
@@ -559,6 +612,9 @@ def cdl_propagate(x, dblk: CdlDeviceBlock, precision="f32", out=None, return_inf
     Tout = T + blk.max_delay
     if out is None:
         out = torch.empty((blk.batch, blk.num_rx, Tout), dtype=x.dtype, device=x.device)
+    elif tuple(out.shape) != (blk.batch, blk.num_rx, Tout) or out.dtype != x.dtype or not out.is_contiguous() \
+            or out.device != x.device:
+        raise ValueError("out has the wrong shape / dtype / layout / device")
     p = _cdl_problem(blk, T, precision, x.dtype == torch.complex128, {k: v.data_ptr() for k, v in dblk.tensors.items()})
     info = FadingPlanInfo()
     with torch.cuda.device(x.device):
@@ -576,7 +632,7 @@ def cdl_state(dblk: CdlDeviceBlock, num_samples: int, io128=True):
     blk = dblk.host
     p = _cdl_problem(blk, num_samples, "f64", io128, {k: v.data_ptr() for k, v in dblk.tensors.items()})
     G = C.c_int32(0)
-    gd = np.zeros(64, dtype=np.int32)
+    gd = np.zeros(_lib.HB_CDL_MAX_GROUPS, dtype=np.int32)
     _lib.check(lib.hb_cdl_state(C.byref(p), None, gd.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(G), None))
     G = int(G.value)
     h = torch.empty((blk.batch, G, blk.num_rx, blk.num_tx, int(num_samples)),

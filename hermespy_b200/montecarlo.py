@@ -156,10 +156,13 @@ class GridStatistics:
         with np.errstate(invalid="ignore", divide="ignore"):
             return (c[:, 0] / c[:, 1]).reshape(self.grid_shape or (1,))
 
-    def confident(self, cell: int, accuracy: float, confidence: float) -> bool:
-        """Stopping rule of ScalarEvaluationResult.add_artifact (scalar.py:117-123) on the reduced statistics."""
+    def confident(self, cell: int, accuracy: float, confidence: float, min_num_samples: int = 1) -> bool:
+        """Stopping rule of ScalarEvaluationResult.add_artifact (scalar.py:117-123) on the reduced statistics.
+
+        As in the reference the rule is only evaluated when the cell's sample count is a multiple of
+        ``min_num_samples`` (scalar.py:117); between those counts the cell is never declared confident."""
         s, s2, n = (float(v) for v in self.stats[cell].detach().cpu())
-        if n < 2:
+        if n < 2 or min_num_samples < 1 or int(round(n)) % int(min_num_samples) != 0:
             return False
         var = (s2 - s * s / n) / (n - 1)
         std = math.sqrt(var) if var > 0 else 0.0

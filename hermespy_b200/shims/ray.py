@@ -18,6 +18,7 @@ import copy
 import sys
 import threading
 import time
+import weakref
 from concurrent.futures import FIRST_COMPLETED, Future, ThreadPoolExecutor
 from concurrent.futures import wait as _futures_wait
 from typing import Any, Sequence
@@ -53,6 +54,17 @@ class _RemoteMethod(object):
         return ObjectRef(self._handle._pool.submit(bound, *args, **kwargs))
 
 
+def _retire_pool(pool) -> None:
+    pool.shutdown(wait=False)
+    try:
+        _live_pools.remove(pool)
+    except ValueError:
+        pass
+
+
+_live_pools: list = []  # thread pools of the actors created since the last shutdown()
+
+
 class ActorHandle(object):
     """Reference to an in-process actor; attribute access yields ``.remote``-callable methods."""
 
@@ -60,6 +72,10 @@ class ActorHandle(object):
         self._instance = instance
         self._pool = ThreadPoolExecutor(max_workers=max(1, int(max_concurrency)),
                                         thread_name_prefix=type(instance).__name__)
+        _live_pools.append(self._pool)
+        # the reference never calls ray.shutdown() (monte_carlo.py:252-262): release the actor's threads when the last
+        # handle goes away, so repeated Simulation.run() calls do not accumulate idle threads
+        weakref.finalize(self, _retire_pool, self._pool)
 
     def __getattr__(self, name: str) -> _RemoteMethod:
         if name.startswith("_"):
@@ -113,6 +129,9 @@ def put(value: Any) -> ObjectRef:
 def wait(refs: Sequence[ObjectRef], num_returns: int = 1, timeout: float | None = None):
     """Block until ``num_returns`` of ``refs`` are done; returns (ready, pending) in the order of ``refs``."""
     refs = list(refs)
+    if not refs:
+        return [], []
+    num_returns = min(int(num_returns), len(refs))  # Ray raises for num_returns > len(refs); never spin on it
     deadline = None if timeout is None else time.monotonic() + timeout
     while True:
         ready = [r for r in refs if r._future.done()]
@@ -141,8 +160,11 @@ def is_initialized() -> bool:
 
 
 def shutdown(*args, **kwargs) -> None:
+    """End the 'cluster': actor threads are released (pending calls are dropped, running ones finish)."""
     global _initialized
     _initialized = False
+    while _live_pools:
+        _live_pools.pop().shutdown(wait=False, cancel_futures=True)
 
 
 def available_resources() -> dict:

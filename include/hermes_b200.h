@@ -42,7 +42,7 @@ extern "C" {
 #define HB_API
 #endif
 
-#define HB_VERSION 100 /* 0.1.0 */
+#define HB_VERSION 110 /* 0.1.1: antenna element models, per-link delay tables, fused receive, SINC mode */
 #define HB_MAX_TAPS 256
 #define HB_MAX_POLY_ORDER 8
 #define HB_NUM_KERNEL_KINDS 9
@@ -115,6 +115,10 @@ HB_API int hb_version(void);
 HB_API const char* hb_last_error(void);
 /* Number of CUDA devices visible (0 when none / driver missing). */
 HB_API int hb_device_count(void);
+/* Make `device` the CUDA device of the calling thread (cudaSetDevice).  The host-buffer entries and every
+ * device-pointer entry run on the calling thread's current device; a plugin that serves one GPU per process calls
+ * this once per thread (hermespy_b200.dropin does it on every call: worker threads default to device 0). */
+HB_API int hb_set_device(int device);
 
 HB_API int hb_fading_plan(const hb_fading_problem* p, hb_fading_plan_info* info);
 
@@ -138,14 +142,24 @@ HB_API int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_d
 
 /* ---- 3GPP cluster delay line ------------------------------------------------------------------------------
  * Batched replacement of ClusterDelayLineSample._propagate / .state and the per-ray array responses
- * (hermespy/channel/cdl/cluster_delay_lines.py:409-592, hermespy/core/antennas.py:138-210, 883-1000) for arrays of
- * identical ideal elements (SimulatedIdealAntenna on a uniform array, any device orientation).
+ * (hermespy/channel/cdl/cluster_delay_lines.py:409-592, hermespy/core/antennas.py:138-210, 883-1000).
+ * Antenna elements: the reference's four element models -- IdealAntenna, LinearAntenna(slant), PatchAntenna, Dipole
+ * (core/antennas.py:392-622) -- each with its own orientation inside the array (element_mode below).
  *
  * A "ray term" is one iteration of the reference's ray generator: (cluster sub-partition, ray) in generator order.
  * Per term the host supplies the four ray angles, the 2x2 Jones matrix and the real amplitude
  * sqrt(P_c / num_rays) * nlos_scale; the delay index int((tau + offset) * fs) is launch-uniform.  The optional
  * line-of-sight term (cluster_delay_lines.py:498-523) is synthesized by the library from the device poses.
  */
+#define HB_ELEMENT_STRIDE 12
+typedef enum hb_element_mode { HB_ELEMENTS_IDEAL = 0, HB_ELEMENTS_UNIFORM = 1, HB_ELEMENTS_PER_ELEMENT = 2 } hb_element_mode;
+typedef enum hb_element_kind {
+  HB_ELEMENT_IDEAL = 0,  /* F = [2^-1/2, 2^-1/2]                                    core/antennas.py:435-436 */
+  HB_ELEMENT_LINEAR = 1, /* F = [cos(slant), sin(slant)]                            core/antennas.py:509-510 */
+  HB_ELEMENT_PATCH = 2,  /* F = [max(0.1, (0.1 + 0.9 e^{-1.315 az^2}) cos^2 ze), 0] core/antennas.py:556-560 */
+  HB_ELEMENT_DIPOLE = 3  /* F = [cos(pi/2 cos ze) / sin ze, 0] (0 at ze = 0)        core/antennas.py:610-614 */
+} hb_element_kind;
+
 typedef struct hb_cdl_problem {
   int32_t batch;            /* B links                                                              */
   int32_t num_tx, num_rx;   /* antenna counts                                                       */
@@ -169,6 +183,16 @@ typedef struct hb_cdl_problem {
   const double* rel_velocity;  /* DEVICE f64 [B, 3]: v_rx - v_tx (global frame)                     */
   const double* tx_topology;   /* DEVICE f64 [Ntx, 3] element positions in the array frame          */
   const double* rx_topology;   /* DEVICE f64 [Nrx, 3]                                               */
+  /* Antenna element models (core/antennas.py:138-210 global_characteristics, :392-622 local patterns).
+   * element_mode HB_ELEMENTS_IDEAL: unrotated IdealAntenna elements, the two tables are ignored (may be NULL);
+   * HB_ELEMENTS_UNIFORM: every element of an array equals row 0 of its table (rank-one ray matrices);
+   * HB_ELEMENTS_PER_ELEMENT: one row per element (rank-two ray matrices a_rx J a_tx^T).
+   * Row layout (HB_ELEMENT_STRIDE doubles): [0..8] rotation element frame -> array frame (row-major 3x3),
+   * [9] hb_element_kind, [10] kind parameter (LinearAntenna: slant in radians), [11] reserved. */
+  int32_t element_mode;        /* hb_element_mode                                                   */
+  int32_t reserved0;
+  const double* tx_elements;   /* DEVICE f64 [Ntx or 1, HB_ELEMENT_STRIDE]                          */
+  const double* rx_elements;   /* DEVICE f64 [Nrx or 1, HB_ELEMENT_STRIDE]                          */
 } hb_cdl_problem;
 
 typedef struct hb_cdl_plan_info {

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass, replace
 from math import ceil
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 
@@ -38,6 +38,9 @@ class ArrayGeometry:
     translation: np.ndarray  # [3]
     topology: np.ndarray  # [M, 3] element positions in the array frame
     velocity: np.ndarray  # [3] global
+    #: per-element models [M, 12]: rotation element frame -> array frame (9, row-major), kind (0 ideal, 1 linear,
+    #: 2 patch, 3 dipole), kind parameter (linear: slant), reserved; None = unrotated ideal elements
+    elements: Optional[np.ndarray] = None
 
 
 @dataclass
@@ -78,14 +81,24 @@ def to_spherical(v: np.ndarray) -> Tuple[float, float]:
     return float(np.arctan2(v[1], v[0])), float(np.arccos(v[2]))
 
 
-def ideal_polarization(geom: ArrayGeometry, global_direction: np.ndarray) -> np.ndarray:
-    """Polarization 2-vector of an ideal isotropic element seen from ``global_direction`` (antennas.py:138-210).
+def local_pattern(kind: int, param: float, azimuth: float, zenith: float) -> np.ndarray:
+    """``Antenna.local_characteristics`` of the reference's four element models (antennas.py:435-436 ideal,
+    :509-510 linear, :556-560 patch, :610-614 dipole).  The reference passes the ZENITH angle to the parameter it
+    names "elevation" (antennas.py:157)."""
+    if kind == 1:
+        return np.array([np.cos(param), np.sin(param)])
+    if kind == 2:
+        vertical_azimuth = 0.1 + 0.9 * np.exp(-1.315 * azimuth**2)
+        return np.array([max(0.1, vertical_azimuth * np.cos(zenith) ** 2), 0.0])
+    if kind == 3:
+        return np.array([0.0 if zenith == 0.0 else np.cos(0.5 * np.pi * np.cos(zenith)) / np.sin(zenith), 0.0])
+    return np.array([2**-0.5, 2**-0.5])
 
-    The element's local pattern is the constant [2^-1/2, 2^-1/2]; it is rotated into the global theta/phi basis
-    by the 2x2 matrix of TR 38.901 eq. 7.1-12 built from the element's orientation (= the array's, for uniform
-    arrays of unrotated elements).
-    """
-    R = geom.rotation
+
+def element_polarization(R: np.ndarray, global_direction: np.ndarray, kind: int = 0, param: float = 0.0) -> np.ndarray:
+    """Polarization 2-vector of an element with orientation ``R`` (element frame -> global) seen from
+    ``global_direction`` (antennas.py:138-210): the local pattern rotated into the global theta/phi basis by the
+    2x2 matrix of TR 38.901 eq. 7.1-12."""
     local_direction = R.T @ global_direction
     az_g, ze_g = to_spherical(global_direction)
     az_l, ze_l = to_spherical(local_direction)
@@ -95,20 +108,31 @@ def ideal_polarization(geom: ArrayGeometry, global_direction: np.ndarray) -> np.
     th_l = np.array([np.cos(ze_l) * np.cos(az_l), np.cos(ze_l) * np.sin(az_l), -np.sin(ze_l)])
     th_lt, phi_lt = R @ th_l, R @ phi_l
     pt = np.array([[th_g @ th_lt, th_g @ phi_lt], [phi_g @ th_lt, phi_g @ phi_lt]])
-    return pt @ np.array([2**-0.5, 2**-0.5])
+    return pt @ local_pattern(kind, param, az_l, ze_l)
+
+
+def ideal_polarization(geom: ArrayGeometry, global_direction: np.ndarray) -> np.ndarray:
+    """Unrotated ideal isotropic element: constant local pattern [2^-1/2, 2^-1/2], orientation = the array's."""
+    return element_polarization(geom.rotation, global_direction)
 
 
 def array_response(geom: ArrayGeometry, fc: float, target_position: np.ndarray) -> np.ndarray:
     """``cartesian_array_response(fc, position, 'global', mode)`` -> [M, 2] (antennas.py:954-1000).
 
-    phase_m = exp(-2j pi fc / c * || q_m - T^-1(position) ||), polarization towards normalize(position - t).
+    phase_m = exp(-2j pi fc / c * || q_m - T^-1(position) ||), polarization of element m towards
+    normalize(position - t) (antennas.py:797-836: one ``global_characteristics`` call per element).
     """
     local_position = geom.rotation.T @ (np.asarray(target_position, dtype=np.float64) - geom.translation)
     distances = np.linalg.norm(geom.topology.T - local_position[:, None], axis=0)
     phase = np.exp(-2j * np.pi * fc * distances / SPEED_OF_LIGHT)
     d = np.asarray(target_position, dtype=np.float64) - geom.translation
-    pol = ideal_polarization(geom, d / np.linalg.norm(d))
-    return phase[:, None] * pol[None, :]
+    d = d / np.linalg.norm(d)
+    if geom.elements is None:
+        pol = ideal_polarization(geom, d)
+        return phase[:, None] * pol[None, :]
+    pol = np.stack([element_polarization(geom.rotation @ e[:9].reshape(3, 3), d, int(e[9]), float(e[10]))
+                    for e in np.asarray(geom.elements, dtype=np.float64)])
+    return phase[:, None] * pol
 
 
 def ray_terms(p: CdlParams) -> List[Tuple[np.ndarray, float, float]]:

@@ -33,14 +33,36 @@ def static_normals_of(realization) -> np.ndarray:
     return np.array(rr._StaticConsistentRealization__scalar_samples, dtype=np.float64)
 
 
+def element_table_from_reference(antennas) -> np.ndarray:
+    """[M, 12] element rows (rotation element -> array frame, kind, parameter) of reference ``Antenna`` objects."""
+    from hermespy.core.antennas import Dipole, IdealAntenna, LinearAntenna, PatchAntenna
+
+    rows = np.zeros((len(antennas), 12))
+    for m, a in enumerate(antennas):
+        rows[m, :9] = np.asarray(a.pose, dtype=np.float64)[:3, :3].ravel()
+        if isinstance(a, LinearAntenna):
+            rows[m, 9:11] = 1, a.slant
+        elif isinstance(a, PatchAntenna):
+            rows[m, 9] = 2
+        elif isinstance(a, Dipole):
+            rows[m, 9] = 3
+        elif not isinstance(a, IdealAntenna):
+            raise TypeError(f"no oracle pattern for antenna type {type(a).__name__}")
+    return rows
+
+
 def array_geometry_from_reference(antennas_state, velocity, mode):
     """``ArrayGeometry`` of a reference ``AntennaArrayState`` (pose = local -> global homogeneous matrix)."""
+    from hermespy.core import AntennaMode
+
     from .cdl_oracle import ArrayGeometry
 
     fwd = np.asarray(antennas_state.forwards_transformation, dtype=np.float64)
+    ants = antennas_state.transmit_antennas if mode == AntennaMode.TX else antennas_state.receive_antennas
     return ArrayGeometry(rotation=fwd[:3, :3].copy(), translation=fwd[:3, 3].copy(),
                          topology=np.asarray(antennas_state._topology(mode), dtype=np.float64).copy(),
-                         velocity=np.asarray(velocity, dtype=np.float64).copy())
+                         velocity=np.asarray(velocity, dtype=np.float64).copy(),
+                         elements=element_table_from_reference(list(ants)))
 
 
 def cdl_params_from_reference_sample(sample):

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert "hb_fading_propagate" in names and "hb_fading_propagate_host" in names and len(names) >= 8
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ but not exported"
-    assert lib.hb_version() == 100
+    assert lib.hb_version() == 110
 
 
 def _plan(**kw):

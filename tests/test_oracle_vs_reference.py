@@ -230,3 +230,50 @@ def test_stats_oracle_matches_reference_evaluator(ref):
         errors, bits, artifact = so.bit_errors(tx, rx)
         assert errors == int(np.sum(evaluation.evaluation)) and bits == len(evaluation.evaluation)
         assert artifact == evaluation.artifact().to_scalar()
+
+
+def test_dropin_extracts_element_tables_of_non_ideal_arrays(ref):
+    """dropin.cdl_block_from_reference on dipole / patch / cross-polarized arrays: element tables, element mode and the
+    whole parameter block equal the test-side layout from the oracle parameters; unknown element classes are refused."""
+    import hermespy_b200.dropin as dropin
+    from hermespy.core import Transformation
+    from hermespy.simulation import (SimulatedCustomArray, SimulatedDevice, SimulatedDipole, SimulatedIdealAntenna,
+                                     SimulatedLinearAntenna, SimulatedPatchAntenna, SimulatedUniformArray)
+    from oracle.ref_extract import cdl_params_from_reference_sample
+    from tests.helpers import cdl_block_from_oracle_params
+
+    RC = ref["RC"]
+    fs, fc = 30.72e6, 3.5e9
+
+    def dev(arr, pos, rpy=(0, 0, 0)):
+        return SimulatedDevice(bandwidth=fs, oversampling_factor=1, carrier_frequency=fc, antennas=arr,
+                               pose=Transformation.From_RPY(np.array(rpy, float), np.array(pos, float)))
+
+    xpol = SimulatedCustomArray([SimulatedLinearAntenna(slant=s_, pose=Transformation.From_RPY(
+        np.array([0.0, 0.1 * i, 0.0]), np.array([0.0, 0.04 * i, 0.0]))) for i in range(2) for s_ in (0.7, -0.7)])
+    cases = [(SimulatedUniformArray(SimulatedDipole, 0.04, (2, 2, 1)), SimulatedUniformArray(SimulatedPatchAntenna, 0.04, (2, 1, 1)), 1),
+             (xpol, SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (2, 1, 1)), 2),
+             (SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (2, 1, 1)), SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (1, 1, 1)), 0)]
+    for txa, rxa, mode in cases:
+        s = RC.CDL(RC.CDLType.E, 1e-7, seed=3).realize().sample(dev(txa, (0, 0, 10.0), (0.1, 0.2, 0.3)), dev(rxa, (40.0, 5.0, 1.5)))
+        got = dropin.cdl_block_from_reference(s)
+        want = cdl_block_from_oracle_params(cdl_params_from_reference_sample(s))
+        assert got.element_mode == want.element_mode == mode
+        for f in ("term_delay", "angles", "jones", "amplitude", "tx_pose", "rx_pose", "rel_velocity", "tx_topology",
+                  "rx_topology", "tx_elements", "rx_elements"):
+            a, b = getattr(got, f), getattr(want, f)
+            assert (a is None and b is None) or np.array_equal(a, b), f
+        assert (got.max_delay, got.line_of_sight, got.los_delay, got.los_amplitude) == \
+               (want.max_delay, want.line_of_sight, want.los_delay, want.los_amplitude)
+
+    class Cardioid(SimulatedIdealAntenna):
+        def local_characteristics(self, azimuth, elevation):
+            return np.array([0.5 * (1 + np.cos(azimuth)), 0.0])
+
+        def copy(self):
+            return Cardioid(self.mode, self.pose.copy())
+
+    s = RC.CDL(RC.CDLType.A, 1e-7, seed=3).realize().sample(
+        dev(SimulatedUniformArray(Cardioid, 0.04, (2, 1, 1)), (0, 0, 10.0)), dev(SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (1, 1, 1)), (40.0, 5.0, 1.5)))
+    with pytest.raises(dropin.UnsupportedByKernels):
+        dropin.cdl_block_from_reference(s)
