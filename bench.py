@@ -1,33 +1,40 @@
 #!/usr/bin/env python
-"""Benchmark of the channel hot path: propagated complex samples/s per link (BASELINE.json metric).
+"""Benchmark of the channel hot path: propagated complex samples/s per link (BASELINE.json metric), every BASELINE config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--links B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config C1|C2|C3|C4|C5] [--precision f32|f64] [--only]
 
-A *step* is one pass of the hot path over one batch of ``--links`` synthetic links of config C2
-(BASELINE.json configs[1]: 4x4 MIMO, 5G TDL-B, rms delay 300 ns, Doppler 100, medium antenna correlation,
-T = 15 344 samples at 30.72 MHz).  The whole job (10 000 drops x 7 SNR points = 70 000 links, every one
-re-realized) is 70000 / links steps of identical shape; K steps are timed.
+A *step* is one pass of the hot path over one batch of synthetic links of a BASELINE.json config:
 
-* ``value``  device-resident throughput: inputs and parameters already in HBM, CUDA events around K steps,
-             max over ranks, aggregate over all ranks (weak scaling: same links per GPU).
-* ``e2e``    the same work through the host-buffer C-ABI (``hb_fading_propagate_host``): complex128 host
-             buffers (the reference's SignalBlock dtype) in pinned memory, H2D + kernels + D2H inside the timed
-             region.
-* ``roofline`` achieved algorithmic HBM bytes/s of the dominant kernel (the K3+K4 kernel the planner picked: tdl_tma for
-             this shape; accounting kind "tdl_poly") from per-launch CUDA events
-             recorded by the library on the launch stream during the timed region, against MEASURED_PEAKS.json.
-* ``cpu_baseline`` the numpy oracle (a restatement of the reference's CPU path) on the host cores, bounded sample.
+    C1  SISO RRC frame (500 samples @ 400 MHz) over 5G TDL-A, 11 SNR points x 1000 drops        (configs[0])
+    C2  4x4 MIMO OFDM frame (15 344 samples @ 30.72 MHz) over 5G TDL-B, 10k drops x 7 SNR points  (configs[1], headline)
+    C3  3GPP CDL-C, 32x4 UPA link, moving receiver, 2048-sample frames                            (configs[2])
+    C4  64x64 Rician (TDL-D profile) with Kronecker correlation, tensor-core spatial GEMM        (configs[3])
+    C5  COST259 typical urban, SISO, 2^20-sample frames                                          (configs[4])
 
-``--impl reference`` times that CPU path alone (rank 0 only): the UNMODIFIED reference classes when the pip install
-``baseline/_ref`` (tools/install_reference.py, git-ignored, travels with the snapshot) is present (kind
-"reference"), else the numpy port under ``oracle/`` (kind "port").
+The printed JSON line is the headline config (default C2, complex64 arithmetic).  Unless ``--only`` is given it also
+carries ``"configs"``: one sub-record per other config plus the float64 parity mode of the headline config, each with
+its own ``value`` / ``roofline`` / ``e2e`` / ``cpu_baseline`` / ``parity`` (north_star: "throughput on synthetic signals of
+each named shape").  Per record:
+
+* ``value``    device-resident throughput: inputs and parameters already in HBM, CUDA events around K steps, max over
+               ranks, aggregate over all ranks (weak scaling: same links per GPU).
+* ``e2e``      the same work through the host-buffer C-ABI (``hb_fading_propagate_host`` / ``hb_cdl_propagate_host``):
+               complex128 pinned host buffers (the reference's SignalBlock dtype), H2D + kernels + D2H inside the timed region.
+* ``roofline`` the dominant kernel from per-launch CUDA events recorded by the library on the launch stream during the
+               timed region: algorithmic HBM bytes/s against MEASURED_PEAKS.json (HBM-bound kernels), or flop/s against the
+               FP32 / tensor pipe peak for the CDL contraction.
+* ``parity``   the gate beside the timing: relative L2 of the first links of the SAME batch against the numpy oracle.
+* ``cpu_baseline`` the reference's CPU path on the host cores, bounded sample: the UNMODIFIED reference classes from
+               ``baseline/_ref`` (kind "reference"), or the oracle port where the reference cannot run the shape (C4).
+
+``--impl reference`` times that CPU path alone (rank 0 only) for ``--config``.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -37,21 +44,76 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# ---- workload: BASELINE.json configs[1] (C2) -------------------------------------------------------------
-C2 = dict(
-    name="C2: 4x4 MIMO OFDM frame (14 x (1024+72) = 15344 samples @30.72 MHz) over 5G TDL-B, rms_delay 300 ns, "
-         "doppler 100, 3GPP medium antenna correlation; 10k drops x 7 SNR points = 70000 links",
-    ntx=4, nrx=4, T=15344, fs=30.72e6, rms_delay=300e-9, doppler=100.0, total_links=70000,
-)
 UNIT = "complex samples/s per link direction"
 METRIC = "propagated complex samples/s per link"
 
+# ---- workloads: BASELINE.json configs -----------------------------------------------------------------
+CONFIGS = {
+    "C1": dict(id="C1", kind="fading", ntx=1, nrx=1, T=500, fs=4e8, links=11000, e2e_links=11000, total_links=11000,
+               oracle_links=2, cpu_links_per_core=64,
+               name="C1: SISO RRC frame (500 samples @ 400 MHz) over 5G TDL-A, doppler 100; 11 SNR points x 1000 drops "
+                    "= 11000 links"),
+    "C2": dict(id="C2", kind="fading", ntx=4, nrx=4, T=15344, fs=30.72e6, links=2048, e2e_links=512, total_links=70000,
+               oracle_links=1, cpu_links_per_core=16,
+               name="C2: 4x4 MIMO OFDM frame (14 x (1024+72) = 15344 samples @30.72 MHz) over 5G TDL-B, rms_delay 300 ns, "
+                    "doppler 100, 3GPP medium antenna correlation; 10k drops x 7 SNR points = 70000 links"),
+    "C3": dict(id="C3", kind="cdl", ntx=32, nrx=4, T=2048, fs=30.72e6, fc=3.5e9, links=4096, e2e_links=512,
+               total_links=100000, distinct=128, oracle_links=1, cpu_links_per_core=1,
+               name="C3: 3GPP CDL-C (rms delay 300 ns), 32 tx (8x4 UPA) x 4 rx (2x2) ideal elements, fc 3.5 GHz, receiver "
+                    "moving at (10, -3, 0) m/s, 2048-sample frames @30.72 MHz; 100k drops"),
+    "C4": dict(id="C4", kind="fading", ntx=64, nrx=64, T=16384, fs=30.72e6, links=256, e2e_links=16, total_links=256,
+               oracle_links=1, cpu_links_per_core=1,
+               name="C4: 64x64 Rician sum-of-sinusoids (TDL-D profile, rms_delay 300 ns, doppler 100) with exponential "
+                    "Kronecker correlation rho = 0.7, 16384-sample frames; 256 links"),
+    "C5": dict(id="C5", kind="fading", ntx=1, nrx=1, T=1 << 20, fs=30.72e6, links=64, e2e_links=16, total_links=64,
+               oracle_links=1, oracle_samples=1 << 16, cpu_links_per_core=1,
+               name="C5: COST259 typical urban, doppler 50, SISO, 2^20-sample frames @30.72 MHz (NEAREST delays); 64 links"),
+}
 
-def make_channel(seed):
-    import hermespy_b200.channel as MC
 
-    return MC.TDL(MC.TDLType.B, rms_delay=C2["rms_delay"], doppler_frequency=C2["doppler"], seed=seed,
-                  antenna_correlation=MC.StandardAntennaCorrelation(MC.CorrelationType.MEDIUM))
+def make_channel(cfg, M, seed):
+    """The config's channel from a module exposing the reference's public names (``hermespy.channel`` for the CPU
+    arm, ``hermespy_b200.channel`` for the GPU arm): one source text drives both implementations."""
+    cid = cfg["id"]
+    if cid == "C1":
+        return M.TDL(M.TDLType.A, doppler_frequency=100.0, seed=seed)
+    if cid == "C2":
+        return M.TDL(M.TDLType.B, rms_delay=300e-9, doppler_frequency=100, seed=seed,
+                     antenna_correlation=M.StandardAntennaCorrelation(M.CorrelationType.MEDIUM))
+    if cid == "C3":
+        return M.CDL(M.CDLType.C, 300e-9, seed=seed)
+    if cid == "C4":
+        n = cfg["ntx"]
+        R = 0.7 ** np.abs(np.subtract.outer(np.arange(n), np.arange(n))).astype(complex)
+        return M.TDL(M.TDLType.D, rms_delay=300e-9, doppler_frequency=100, seed=seed, max_antennas=n,
+                     antenna_correlation=M.CustomAntennaCorrelation(R))
+    if cid == "C5":
+        return M.Cost259(M.Cost259Type.URBAN, doppler_frequency=50, seed=seed)
+    raise KeyError(cid)
+
+
+def make_devices(cfg, S, T):
+    """(tx, rx) devices of the config from a module exposing SimulatedDevice & co; ``T`` = Transformation class."""
+    fs = cfg["fs"]
+    if cfg["kind"] == "cdl":
+        fc = cfg["fc"]
+        lam = 299792458.0 / fc
+        tx = S.SimulatedDevice(bandwidth=fs, oversampling_factor=1, carrier_frequency=fc,
+                               antennas=S.SimulatedUniformArray(S.SimulatedIdealAntenna, lam / 2, (8, 4, 1)),
+                               pose=T.From_Translation(np.array([0.0, 0.0, 25.0])))
+        rx = S.SimulatedDevice(bandwidth=fs, oversampling_factor=1, carrier_frequency=fc,
+                               antennas=S.SimulatedUniformArray(S.SimulatedIdealAntenna, lam / 2, (2, 2, 1)),
+                               pose=T.From_Translation(np.array([100.0, 20.0, 1.5])), velocity=np.array([10.0, -3.0, 0.0]))
+        return tx, rx
+    dev = lambda n: S.SimulatedDevice(bandwidth=fs, oversampling_factor=1, carrier_frequency=3.5e9,
+                                      antennas=S.SimulatedUniformArray(S.SimulatedIdealAntenna, 0.04, (n, 1, 1)))
+    return dev(cfg["ntx"]), dev(cfg["nrx"])
+
+
+def public_config(cfg, precision):
+    """The ``config`` object of the JSON line: identical for both arms (the driver compares them)."""
+    return {"workload": cfg["name"], "id": cfg["id"], "num_tx": cfg["ntx"], "num_rx": cfg["nrx"],
+            "samples_per_frame": cfg["T"], "sampling_rate_hz": cfg["fs"], "gpu_arithmetic": precision}
 
 
 def measured_peaks():
@@ -59,10 +121,10 @@ def measured_peaks():
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
 # ---- clocks ------------------------------------------------------------------------------------------------
@@ -121,83 +183,90 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(seen), "samples": len(self.rows), "power_w_max": max(r[2] for r in self.rows)}
 
 
-# ---- CPU baseline: the reference's own code when its install travelled (baseline/_ref), else the oracle port ----
-def cpu_kind():
+# ---- CPU arm: the reference's own code when its install travelled (baseline/_ref), else the oracle port ----------
+def cpu_kind(cfg):
     from oracle.refload import REFERENCE_ROOT, reference_available
 
+    if cfg["id"] == "C4":
+        return "port"  # the reference caps fading at 10x10 antennas: float64 restatement, labelled
     # /root/reference is never read at run time on the GPU box; only the pip install under baseline/_ref counts
     if reference_available() and os.path.realpath(REFERENCE_ROOT).startswith(os.path.realpath(os.path.join(ROOT, "baseline"))):
         return "reference"
     return "port"
 
 
-def _cpu_worker_reference(args):
-    """realize + sample + propagate of ONE C2 link per iteration through the unmodified reference classes
-    (hermespy/channel/fading/fading.py:371-406 and its generator :293-343), complex128."""
-    seed, n = args
-    from oracle.refload import load_reference
-
-    load_reference()
-    from hermespy.channel import TDL, CorrelationType, StandardAntennaCorrelation, TDLType
-    from hermespy.core import Signal
-    from hermespy.simulation import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
-
-    ch = TDL(TDLType.B, rms_delay=C2["rms_delay"], doppler_frequency=C2["doppler"], seed=seed,
-             antenna_correlation=StandardAntennaCorrelation(CorrelationType.MEDIUM))
-    dev = lambda n_: SimulatedDevice(bandwidth=C2["fs"], oversampling_factor=1, carrier_frequency=3.5e9,
-                                     antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (n_, 1, 1)))
-    tx, rx = dev(C2["ntx"]), dev(C2["nrx"])
-    rng = np.random.default_rng(seed)
-    done = 0
-    for _ in range(n):
-        s = ch.realize().sample(tx, rx)
-        x = (rng.standard_normal((C2["ntx"], C2["T"])) + 1j * rng.standard_normal((C2["ntx"], C2["T"]))) / np.sqrt(2)
-        y = s.propagate(Signal.Create(x, C2["fs"], 3.5e9))
-        done += y.num_samples > 0
-    return done
+def _signal(rng, ntx, T):
+    return (rng.standard_normal((ntx, T)) + 1j * rng.standard_normal((ntx, T))) / np.sqrt(2)
 
 
 def _cpu_worker(args):
-    if cpu_kind() == "reference":
-        return _cpu_worker_reference(args)
-    seed, n = args
-    from oracle import fading_oracle as fo
-
-    ch = make_channel(seed)
+    """realize + sample + propagate of ``n`` links of a config, complex128, one host process."""
+    cid, seed, n = args
+    cfg = CONFIGS[cid]
     rng = np.random.default_rng(seed)
     done = 0
-    # same per-link work as the reference: realize + sample + propagate, complex128
-    from hermespy_b200.core import SimulatedDevice, SimulatedIdealAntenna, SimulatedUniformArray
+    if cpu_kind(cfg) == "reference":
+        # the unmodified reference classes (fading.py:371-406 + generator :293-343; cluster_delay_lines.py:409-558)
+        from oracle.refload import load_reference
 
-    dev = lambda n_: SimulatedDevice(bandwidth=C2["fs"], antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (n_, 1, 1)))
-    tx, rx = dev(C2["ntx"]), dev(C2["nrx"])
+        load_reference()
+        import hermespy.channel as RC
+        import hermespy.simulation as RS
+        from hermespy.core import Signal, Transformation
+
+        ch = make_channel(cfg, RC, seed)
+        tx, rx = make_devices(cfg, RS, Transformation)
+        fc = cfg.get("fc", 3.5e9)
+        for _ in range(n):
+            s = ch.realize().sample(tx, rx)
+            y = s.propagate(Signal.Create(_signal(rng, cfg["ntx"], cfg["T"]), cfg["fs"], fc))
+            done += y.num_samples > 0
+        return done
+    # oracle port (float64 numpy restatement) through the host mirror classes
+    import hermespy_b200.channel as MC
+    import hermespy_b200.core as MS
+    from oracle import cdl_oracle as co
+    from oracle import fading_oracle as fo
+
+    ch = make_channel(cfg, MC, seed)
+    tx, rx = make_devices(cfg, MS, MS.Transformation)
     for _ in range(n):
         s = ch.realize().sample(tx, rx)
-        p = fo.FadingParams(power=s.power_profile, delay=s.delay_profile, los_gain=s.los_gains, nlos_gain=s.nlos_gains,
-                            los_angle=s.los_angles, nlos_angle=s.nlos_angles, los_phase=s.los_phases,
-                            nlos_phase=s.nlos_phases, los_doppler=s.los_doppler, nlos_doppler=s.nlos_doppler,
-                            spatial=s.spatial_response, gain=s.gain, fs=C2["fs"], num_rx=C2["nrx"], num_tx=C2["ntx"])
-        x = (rng.standard_normal((C2["ntx"], C2["T"])) + 1j * rng.standard_normal((C2["ntx"], C2["T"]))) / np.sqrt(2)
-        y = fo.propagate(p, x)
+        x = _signal(rng, cfg["ntx"], cfg["T"])
+        if cfg["kind"] == "cdl":
+            from tests.test_cdl_golden import oracle_params
+
+            y = co.propagate(oracle_params(s), x)
+        else:
+            y = fo.propagate(_fading_oracle_params(s, cfg), x)
         done += y.shape[1] > 0
     return done
+
+
+def _fading_oracle_params(s, cfg):
+    from oracle import fading_oracle as fo
+
+    return fo.FadingParams(power=s.power_profile, delay=s.delay_profile, los_gain=s.los_gains, nlos_gain=s.nlos_gains,
+                           los_angle=s.los_angles, nlos_angle=s.nlos_angles, los_phase=s.los_phases,
+                           nlos_phase=s.nlos_phases, los_doppler=s.los_doppler, nlos_doppler=s.nlos_doppler,
+                           spatial=s.spatial_response, gain=s.gain, fs=cfg["fs"], num_rx=cfg["nrx"], num_tx=cfg["ntx"])
 
 
 class CpuPool:
     """`cores` worker processes (one per host core, as Ray's one actor per core, monte_carlo.py:176,621), warmed up
     once (imports, page-in); every pass maps a bounded number of links onto them."""
 
-    def __init__(self, cores):
+    def __init__(self, cid, cores):
         import multiprocessing as mp
 
-        self.cores = cores
+        self.cid, self.cores = cid, cores
         self.pool = mp.get_context("fork").Pool(cores)
-        self.pool.map(_cpu_worker, [(1000 + i, 1) for i in range(cores)])
+        self.pool.map(_cpu_worker, [(cid, 1000 + i, 1 if CONFIGS[cid]["T"] <= 20000 else 0) for i in range(cores)])
         self.seed = 0
 
     def run(self, links_per_core):
         t0 = time.perf_counter()
-        done = self.pool.map(_cpu_worker, [(self.seed + i, links_per_core) for i in range(self.cores)])
+        done = self.pool.map(_cpu_worker, [(self.cid, self.seed + i, links_per_core) for i in range(self.cores)])
         dt = time.perf_counter() - t0
         self.seed += self.cores
         return int(sum(done)), dt
@@ -207,46 +276,55 @@ class CpuPool:
         self.pool.join()
 
 
-def cpu_reference_pass(links_per_core, cores):
-    """One bounded pass of the CPU path on `cores` processes; returns (links, seconds)."""
-    pool = CpuPool(cores)
+def cpu_sample_text(cfg, links, per_core, cores, dt=None):
+    kind = cpu_kind(cfg)
+    what = ("the unmodified reference classes from baseline/_ref" if kind == "reference" else
+            "float64 numpy port under oracle/ (the reference cannot run this shape)" if cfg["id"] == "C4" else "oracle port")
+    return (f"{links} links of {cfg['id']} ({per_core} per core process, {cores} processes), realize+sample+propagate in "
+            f"complex128 numpy ({what})" + (f"; {dt:.1f} s" if dt is not None else ""))
+
+
+def cpu_baseline(cfg):
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    per_core = cfg["cpu_links_per_core"]
+    pool = CpuPool(cfg["id"], cores)
     try:
-        return pool.run(links_per_core)
+        links, dt = pool.run(per_core)
     finally:
         pool.close()
+    return {"value": links * cfg["T"] / dt, "unit": UNIT, "cores": cores, "kind": cpu_kind(cfg),
+            "sample": cpu_sample_text(cfg, links, per_core, cores, dt)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    # a step = a bounded sample of the C2 workload: per_core links on every host core, sized so that K steps end
-    # within a few minutes (one reference link costs ~0.7 s of one core)
-    per_core = max(1, min(8, 240 // max(1, args.steps + args.warmup)))
-    pool = CpuPool(cores)
+    # a step = a bounded sample of the workload: per_core links on every host core, sized so that K steps end within
+    # a few minutes (one C2 reference link costs ~0.7 s of one core, a C3 link 4.5 s, a C5 link ~8 s)
+    budget = {"C1": 2048, "C2": 240, "C3": 40, "C4": 16, "C5": 20}[cfg["id"]]
+    per_core = max(1, min(cfg["cpu_links_per_core"], budget // max(1, args.steps + args.warmup)))
+    pool = CpuPool(cfg["id"], cores)
     for _ in range(args.warmup):
         pool.run(per_core)
-    t_total = 0.0
-    links_total = 0
+    t_total, links_total = 0.0, 0
     for _ in range(args.steps):
         links, dt = pool.run(per_core)
         t_total += dt
         links_total += links
     pool.close()
-    value = links_total * C2["T"] / t_total
-    kind = cpu_kind()
+    value = links_total * cfg["T"] / t_total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": C2["name"], "links_per_step": per_core * cores},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{per_core * cores} links of C2 per step ({per_core} per core process), "
-                                   "realize+sample+propagate in complex128 numpy (" + (
-                                       "the unmodified reference classes from baseline/_ref" if kind == "reference"
-                                       else "oracle port of fading.py:293-406") + ")"},
+        "config": public_config(cfg, args.precision), "run": {"links_per_step": per_core * cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(cfg),
+                         "sample": cpu_sample_text(cfg, per_core * cores, per_core, cores) + " per step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -255,13 +333,293 @@ def run_reference(args):
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------
+class Workload:
+    """One config on one rank: device-resident step, end-to-end step, algorithmic work, parity gate."""
+
+    def __init__(self, cfg, precision, rank, dev, links, e2e_links, sos_mode="auto"):
+        import torch
+
+        self.cfg, self.precision, self.dev, self.rank = cfg, precision, dev, rank
+        self.B, self.T, self.ntx, self.nrx = links, cfg["T"], cfg["ntx"], cfg["nrx"]
+        self.sos_mode = sos_mode
+        self.cdtype = torch.complex128 if precision == "f64" else torch.complex64
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(rank)
+        rdtype = torch.float64 if precision == "f64" else torch.float32
+        self.x = torch.view_as_complex(torch.randn((self.B, self.ntx, self.T, 2), device=dev, generator=gen, dtype=rdtype)
+                                       * (0.5 ** 0.5))
+        t0 = time.perf_counter()
+        self._sample_links(42 + rank * 12345678)  # rank-dependent seed as simulation.py:220-223
+        self.host_sampling_s = time.perf_counter() - t0
+        self.y = torch.empty((self.B, self.nrx, self.T + self.D), dtype=self.cdtype, device=dev)
+        self.Be = max(1, min(self.B, e2e_links))
+
+    # -- realize + sample the step's links on the host (numpy RNG, reference draw order) ---------------------------
+    def _sample_links(self, seed):
+        import hermespy_b200.channel as MC
+        import hermespy_b200.core as MS
+
+        cfg = self.cfg
+        ch = make_channel(cfg, MC, seed)
+        if cfg["kind"] == "fading":
+            from hermespy_b200.batch import sample_fading_links
+            from hermespy_b200.kernels import FadingBatch
+
+            self.blk = sample_fading_links(ch, self.B, self.ntx, self.nrx, cfg["fs"])
+            self.fb = FadingBatch.from_numpy(device=self.dev, **self.blk)
+            self.D = self.blk["max_delay"]
+            self.channel = ch
+        else:
+            from hermespy_b200.kernels import CdlBlock, CdlDeviceBlock
+
+            tx, rx = make_devices(cfg, MS, MS.Transformation)
+            distinct = min(self.B, cfg["distinct"])  # host sampling of CDL links costs 10 ms each: tile a distinct set
+            self.samples = [ch.realize().sample(tx, rx) for _ in range(distinct)]
+            blocks = [s.kernel_block() for s in self.samples]
+            self.blk = CdlBlock.stack([blocks[i % distinct] for i in range(self.B)])
+            self.dblk = CdlDeviceBlock(self.blk, device=self.dev)
+            self.D = self.blk.max_delay
+
+    def step(self, return_info=False):
+        if self.cfg["kind"] == "fading":
+            from hermespy_b200.kernels import fading_propagate
+
+            return fading_propagate(self.x, self.fb, precision=self.precision, sos_mode=self.sos_mode, out=self.y,
+                                    return_info=return_info)
+        from hermespy_b200.kernels import cdl_propagate
+
+        return cdl_propagate(self.x, self.dblk, precision=self.precision, out=self.y, return_info=return_info)
+
+    # -- algorithmic work (SURVEY 8(d)) ------------------------------------------------------------------------------
+    def algorithmic_bytes(self):
+        esz = 16.0 if self.precision == "f64" else 8.0
+        return esz * self.B * (self.ntx * self.T + self.nrx * (self.T + self.D))
+
+    def dominant(self, prof, info):
+        """(accounting kind, kernel name, bound) of the step's dominant kernel."""
+        if self.cfg["kind"] == "cdl":
+            return "cdl_propagate", ("cdl_poly_kernel" if info.get("mode") == "poly" else "cdl_direct_f64_kernel"), "fp32"
+        if prof["tdl_poly"]["launches"]:
+            if prof["spatial_gemm"]["launches"] and prof["spatial_gemm"]["ms"] > prof["tdl_poly"]["ms"]:
+                return "spatial_gemm", "spatial_gemm_3xtf32_kernel", "hbm"
+            name = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel", "tma": "tdl_tma_kernel"}.get(
+                info.get("variant"), "tdl_poly_kernel")
+            return "tdl_poly", name, "hbm"
+        return "tdl_direct", "tdl_direct_kernel", "hbm"
+
+    # -- end to end through the host-buffer C-ABI (complex128 host buffers, as the reference's SignalBlock) -----------
+    def e2e_prepare(self):
+        import torch
+
+        Be = self.Be
+        self.xh = torch.empty((Be, self.ntx, self.T), dtype=torch.complex128).pin_memory()
+        self.xh.copy_(self.x[:Be].to(torch.complex128).cpu())
+        self.yh = torch.empty((Be, self.nrx, self.T + self.D), dtype=torch.complex128).pin_memory()
+        if self.cfg["kind"] == "fading":
+            self.sub = {k: (v[:Be] if isinstance(v, np.ndarray) and v.ndim == 3 else v) for k, v in self.blk.items()}
+            self.h2d = int(self.xh.numel() * 16 + sum(self.sub[k].nbytes for k in ("omega", "phi", "amp", "spatial")))
+        else:
+            from hermespy_b200.kernels import CdlBlock
+
+            blocks = [s.kernel_block() for s in self.samples]
+            self.sub = CdlBlock.stack([blocks[i % len(blocks)] for i in range(Be)])
+            self.h2d = int(self.xh.numel() * 16 + sum(getattr(self.sub, k).nbytes for k in CdlBlock.ARRAYS))
+        self.d2h = int(self.yh.numel() * 16)
+
+    def e2e_step(self):
+        if self.cfg["kind"] == "fading":
+            from hermespy_b200.kernels import fading_propagate_host
+
+            fading_propagate_host(self.xh.numpy(), out=self.yh.numpy(), precision=self.precision, device=self.dev.index,
+                                  **self.sub)
+        else:
+            from hermespy_b200.kernels import cdl_propagate_host
+
+            cdl_propagate_host(self.xh.numpy(), self.sub, out=self.yh.numpy(), precision=self.precision,
+                               device=self.dev.index)
+
+    # -- parity gate: the first links of THIS batch against the numpy oracle ------------------------------------------
+    def parity(self):
+        cfg = self.cfg
+        n = cfg["oracle_links"]
+        Tn = min(self.T, cfg.get("oracle_samples", self.T))  # causal channel: a prefix of x determines the same prefix of y
+        y = self.y[:n, :, :Tn].cpu().numpy().astype(np.complex128)
+        x = self.x[:n, :, :Tn].cpu().numpy().astype(np.complex128)
+        worst = 0.0
+        for b in range(n):
+            if cfg["kind"] == "fading":
+                blk = self.blk
+                nn = np.arange(Tn)
+                K = blk["omega"].shape[2]
+                ampk = blk["amp"][b][:, [0] + [1] * (K - 1), None]
+                h = (ampk * np.exp(1j * (blk["omega"][b][:, :, None] * nn + blk["phi"][b][:, :, None]))).sum(1)  # fading.py:326-342
+                z = np.zeros((self.ntx, Tn + self.D), complex)
+                for l, d in enumerate(blk["tap_delay"]):
+                    z[:, d: d + Tn] += x[b] * h[l]  # fading.py:385-390
+                S = blk["spatial"][b]
+                if "r_rx" in blk:  # large arrays: the Kronecker mix runs on the device (K2), fading.py:480-489
+                    S = blk["r_rx"] @ S @ blk["r_tx"]
+                ref = (S @ z)[:, :Tn]  # fading.py:393
+            else:
+                from oracle import cdl_oracle as co
+                from tests.test_cdl_golden import oracle_params
+
+                ref = co.propagate(oracle_params(self.samples[b % len(self.samples)]), x[b])[:, :Tn]
+            worst = max(worst, float(np.linalg.norm(y[b] - ref) / np.linalg.norm(ref)))
+        tol = 1e-5 if self.precision == "f32" else (1e-10 if cfg["kind"] == "cdl" else 1e-12)
+        return {"rel_l2_vs_oracle": worst, "tolerance": tol, "links_checked": n, "samples_checked": Tn,
+                "ok": bool(worst <= tol), "oracle": "numpy float64 restatement (oracle/), same links and signal as the timed batch"}
+
+
+def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allreduce):
+    """One config on this rank (all ranks call it together): returns the record (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+
+    from hermespy_b200 import _lib
+    from hermespy_b200.montecarlo import GridStatistics
+
+    links = args.links if (args.links and cfg["id"] == args.config) else cfg["links"]
+    if precision == "f64":
+        links = max(1, links // 8)  # the FP64 direct kernels are ~10x slower per link: keep the step a fraction of a second
+    wl = Workload(cfg, precision, rank, dev, links, min(args.e2e_links or cfg["e2e_links"], cfg["e2e_links"]), args.sos_mode)
+    B, T = wl.B, wl.T
+    grid_stats = GridStatistics((7,), device=dev)  # evaluator statistics: the only data that crosses GPUs (SURVEY 8(e))
+    pending, counter = [], [0]
+
+    def step():
+        wl.step()
+        counter[0] += 1
+        if stats_allreduce and counter[0] % args.stats_every == 0:
+            # the only collective of the path: (sum, sum^2, count) + (bit errors, bits) of the grid cells, ONE packed
+            # all-reduce every `stats_every` batches, enqueued behind this step's kernels, overlapped with the next step's
+            if pending:
+                pending.pop()()
+            pending.append(grid_stats.all_reduce(async_op=True))
+
+    _, info = wl.step(return_info=True)
+    for _ in range(max(3, args.warmup)):
+        step()
+    if stats_allreduce:
+        grid_stats.all_reduce()
+        counter[0] = 0
+    # everything with a variable host cost happens BEFORE the barrier (start skew is paid at the first collective)
+    sampler = ClockSampler(dev.index)
+    _lib.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    if stats_allreduce:
+        if pending:
+            pending.pop()()
+        grid_stats.all_reduce()  # the final reduction of the campaign statistics, inside the timed region
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    prof = _lib.profile_end()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * T * steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    kind, kname, bound = wl.dominant(prof, info)
+    k = prof[kind]
+    k_ms = k["ms"] / max(1, k["launches"]) * (k["launches"] / max(1, steps))  # per step (a step may launch it per chunk)
+    alg_bytes = wl.algorithmic_bytes()
+    others = {n: v["ms"] / steps for n, v in prof.items() if v["launches"] and n != kind}
+    if bound == "hbm":
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": _traffic(cfg, kname, B), "peak_source": peak_src}
+    else:
+        # CDL contraction: 8 P G Nrx Ntx real flop per output sample (DESIGN.md section 4, K6), on the FP32 pipe
+        flops = 8.0 * info["poly_order"] * info["num_groups"] * wl.nrx * wl.ntx * B * (T + wl.D) if info.get("mode") == "poly" else 0.0
+        peak_tf = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+        achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        roofline = {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None,
+                    "peak_source": f"148 SMs x 128 FMA lanes x 2 x {sm_max_mhz:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json)",
+                    "hbm_frac_of_step": alg_bytes / (ms_total / steps * 1e-3) / 1e9 / hbm_peak}
+    roofline.update({"kernel_ms_per_step": k_ms, "algorithmic_bytes_per_step": alg_bytes,
+                     "kernel_share_of_step": k["ms"] / ms_total if ms_total > 0 else None,
+                     "step_frac_of_hbm_peak": alg_bytes / (ms_total / steps * 1e-3) / 1e9 / hbm_peak,
+                     "other_kernels_ms_per_step": others})
+    launches = sum(v["launches"] for v in prof.values())
+
+    # ---- parity gate beside the timing ---------------------------------------------------------------------------
+    parity = wl.parity() if rank == 0 else None
+
+    # ---- end to end -------------------------------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        wl.e2e_prepare()
+        wl.e2e_step()
+        wl.e2e_step()
+        if world > 1:
+            dist.barrier()
+        n_e2e = max(1, min(steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            wl.e2e_step()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * wl.Be * T * n_e2e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": wl.h2d,
+               "d2h_bytes_per_step": wl.d2h, "links_per_step": wl.Be, "host_dtype": "complex128",
+               "timing": "host wall clock around the blocking C-ABI call, max over ranks"}
+
+    cpu = cpu_baseline(cfg) if (with_cpu and rank == 0 and world == 1) else None
+    host_sampling_s = wl.host_sampling_s
+    del wl
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": precision, "data": "synthetic", "config": public_config(cfg, precision),
+        "run": {"links_per_step_per_gpu": B, "steps_for_whole_job": int(np.ceil(cfg["total_links"] / (B * world))),
+                "l2_policy": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB in + out per step)" if alg_bytes > 2 * 126e6
+                else f"in + out {alg_bytes / 1e6:.0f} MB per step: L2-resident between steps (the whole job of this config is one step)",
+                "plan": info, "host_sampling_s": round(host_sampling_s, 3),
+                "stats_allreduce": (f"NCCL, packed [7, 5] float64, every {args.stats_every} steps + once at the end, inside "
+                                    "the timed region") if stats_allreduce else "none"},
+        "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+
+
+def _traffic(cfg, kname, B):
+    """dram bytes of one launch from the committed ncu --set full captures (same kernel, same launch shape), or None."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                tr = json.load(fh)
+            rows = tr if isinstance(tr, list) else [tr]
+            for r in rows:
+                if r.get("config", "C2") == cfg["id"] and r["kernel"].startswith(kname) and r.get("links", 2048) == B:
+                    return r["dram_bytes_read"] + r["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from hermespy_b200 import _lib
-    from hermespy_b200.batch import sample_fading_links
-    from hermespy_b200.kernels import FadingBatch, fading_propagate, fading_propagate_host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -273,150 +631,28 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         _lib.reserve_sms(args.reserve_sms)  # room for the statistics all-reduce next to the persistent kernels
-    B, T, ntx, nrx = args.links, C2["T"], C2["ntx"], C2["nrx"]
-
-    # ---- realize + sample the step's links on the host (numpy RNG, rank-dependent seed as simulation.py:220-223)
-    ch = make_channel(42 + rank * 12345678)
-    blk = sample_fading_links(ch, B, ntx, nrx, C2["fs"])
-    fb = FadingBatch.from_numpy(device=dev, **blk)
-    D = blk["max_delay"]
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(rank)
-    x = torch.view_as_complex(torch.randn((B, ntx, T, 2), device=dev, generator=gen, dtype=torch.float32) * (0.5 ** 0.5))
-    y = torch.empty((B, nrx, T + D), dtype=torch.complex64, device=dev)
-    from hermespy_b200.montecarlo import GridStatistics
-
-    # evaluator statistics of the 7 SNR points of C2: the only data that crosses GPUs
-    grid_stats = GridStatistics((7,), device=dev)
-
-    pending = []
-    counter = [0]
-
-    def step():
-        fading_propagate(x, fb, precision="f32", sos_mode=args.sos_mode, out=y)
-        counter[0] += 1
-        if world > 1 and counter[0] % args.stats_every == 0 and not os.environ.get("HB_BENCH_SKIP_COLLECTIVE"):
-            # the only collective of the path: (sum, sum^2, count) + (bit errors, bits) of the grid cells, ONE packed
-            # all-reduce every `stats_every` batches (the reference's collector polls its actors between batches, never
-            # per drop: actors.py:219-225), enqueued behind this step's kernels and overlapped with the next step's.
-            # Measured at 8 GPUs: a collective per step costs 0.078 ms of rank-synchronization jitter per 0.69 ms step.
-            if pending:
-                pending.pop()()
-            pending.append(grid_stats.all_reduce(async_op=True))
-
-    _, info = fading_propagate(x, fb, out=y, sos_mode=args.sos_mode, return_info=True)
-    for _ in range(max(3, args.warmup)):
-        step()
-    if world > 1:
-        grid_stats.all_reduce()  # warm-up of the collective too (communicator set-up happens on first use)
-        counter[0] = 0
-    # Everything with a variable host cost (NVML set-up takes milliseconds) happens BEFORE the barrier: ranks that leave
-    # it must start their timed region together, or the rank that started first pays the others' start skew at the
-    # first collective (measured at 8 GPUs: ~8 ms per run, 11 % of 100 steps).
-    sampler = ClockSampler(local_rank)
-    _lib.profile_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    if world > 1 and not os.environ.get("HB_BENCH_SKIP_COLLECTIVE"):
-        if pending:
-            pending.pop()()
-        grid_stats.all_reduce()  # the final reduction of the campaign statistics, inside the timed region
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    prof = _lib.profile_end()
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * B * T * args.steps / (ms_total * 1e-3)
-
-    # ---- roofline of the dominant kernel --------------------------------------------------------------------
-    peak, peak_src = measured_peaks()
-    alg_bytes = 8.0 * B * (ntx * T + nrx * (T + D))  # complex64 in + out, SURVEY 8(d): 8 (Ntx + Nrx) B / sample
-    k = prof["tdl_poly"] if prof["tdl_poly"]["launches"] else prof["tdl_direct"]
-    kname = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel", "tma": "tdl_tma_kernel"}.get(info.get("variant"), "tdl_poly_kernel") \
-        if prof["tdl_poly"]["launches"] else "tdl_direct_kernel"
-    traffic = None  # dram bytes of one launch from the committed ncu --set full capture (same kernel, same launch shape)
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")) as fh:
-            tr = json.load(fh)
-        if tr["kernel"].startswith(kname) and B == 2048:
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-    except (OSError, KeyError, ValueError):
-        traffic = None
-    k_ms = k["ms"] / max(1, k["launches"])
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_share_of_step": k["ms"] / ms_total if ms_total > 0 else None,
-                "other_kernels_ms": {n: v["ms"] / max(1, v["launches"]) for n, v in prof.items()
-                                     if v["launches"] and n not in ("tdl_poly", "tdl_direct")}}
-    launches = sum(v["launches"] for v in prof.values())
-
-    # ---- end to end through the host-buffer C-ABI (complex128 host buffers, as the reference's SignalBlock) ----
-    Be = min(B, args.e2e_links)
-    if args.no_e2e:  # profiling runs only (tools/ncu_one.sh); such a line is not a bench result
-        Be = 1
-    xh = torch.empty((Be, ntx, T), dtype=torch.complex128).pin_memory()
-    xh.copy_(x[:Be].to(torch.complex128).cpu())
-    yh = torch.empty((Be, nrx, T + D), dtype=torch.complex128).pin_memory()
-    sub = {k_: (v[:Be] if isinstance(v, np.ndarray) and v.ndim == 3 else v) for k_, v in blk.items()}
-
-    def e2e_step():
-        fading_propagate_host(xh.numpy(), out=yh.numpy(), precision="f32", **sub)
-
-    e2e_step()
-    e2e_step()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 5))
-    for _ in range(n_e2e):
-        e2e_step()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * Be * T * n_e2e / float(t.item())
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 16 + sum(
-        sub[k_].nbytes for k_ in ("omega", "phi", "amp", "spatial"))), "d2h_bytes_per_step": int(yh.numel() * 16),
-           "links_per_step": Be, "host_dtype": "complex128", "timing": "host wall clock around the blocking C-ABI call"}
-
-    # ---- CPU baseline: rank 0, N = 1 only ---------------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        per_core = 16 if cpu_kind() == "reference" else 4  # 10-30 s of host work
-        links, dtc = cpu_reference_pass(per_core, cores)
-        cpu = {"value": links * T / dtc, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
-               "sample": f"{links} links of C2 ({per_core} per core process, {cores} processes), realize+sample+propagate "
-                         f"in complex128 numpy ({'unmodified reference from baseline/_ref' if cpu_kind() == 'reference' else 'oracle port'}); {dtc:.1f} s"}
-
+    allreduce = world > 1 and not os.environ.get("HB_BENCH_SKIP_COLLECTIVE")
+    head = measure(CONFIGS[args.config], args.precision, args, world, rank, dev, args.steps, not args.no_cpu_baseline, allreduce)
+    subs = {}
+    if not args.only:
+        sub_steps = max(1, min(args.steps, 20))
+        todo = [(c, "f32") for c in CONFIGS if c != args.config] + [(args.config, "f64" if args.precision == "f32" else "f32")]
+        for cid, prec in todo:
+            try:
+                rec = measure(CONFIGS[cid], prec, args, world, rank, dev, sub_steps, not args.no_cpu_baseline and prec == "f32",
+                              allreduce)
+            except Exception as e:  # one config must not hide the others; the failure is part of the record
+                rec = {"error": repr(e), "config": public_config(CONFIGS[cid], prec)}
+                if world > 1:
+                    raise
+            if rank == 0:
+                subs[cid if prec == "f32" or cid != args.config else f"{cid}_{prec}"] = rec
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": C2["name"], "links_per_step_per_gpu": B, "steps_for_whole_job": int(np.ceil(
-                C2["total_links"] / (B * world))), "l2_policy": f"inputs larger than L2 ({x.numel() * 8 / 1e6:.0f} MB in, "
-                f"{y.numel() * 8 / 1e6:.0f} MB out per step)", "plan": info,
-                "stats_allreduce": (f"NCCL, packed [7, 5] float64, every {args.stats_every} steps + once at the end, inside "
-                                    "the timed region") if world > 1 else "none (one rank)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        }
-        print(json.dumps(line))
+        if subs:
+            head["configs"] = subs
+            head["gpu_launches_all_configs"] = head["gpu_launches"] + sum(r.get("gpu_launches", 0) for r in subs.values())
+            head["parity_all_ok"] = bool(head["parity"]["ok"] and all(r.get("parity", {}).get("ok", False) for r in subs.values()))
+        print(json.dumps(head))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -428,12 +664,16 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--links", type=int, default=2048, help="links per step per GPU")
-    ap.add_argument("--e2e-links", type=int, default=512, help="links per end-to-end step per GPU")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="headline config of the printed line")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"],
+                    help="f32: complex64 arithmetic (rel-L2 <= 1e-5); f64: float64 parity mode (bit-exact BER counts)")
+    ap.add_argument("--only", action="store_true", help="measure the headline config only (no per-config sub-records)")
+    ap.add_argument("--links", type=int, default=0, help="links per step per GPU of the headline config (0 = config default)")
+    ap.add_argument("--e2e-links", type=int, default=0, help="links per end-to-end step per GPU (0 = config default)")
     ap.add_argument("--stats-every", type=int, default=10, help="N > 1: batches between statistics all-reduces")
     ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs left to the NCCL all-reduce of the statistics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: shrink the end-to-end leg to one link")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "poly_tma", "direct"],
                     help="kernel selection (profiling / A-B runs); the default lets the planner choose")
     args = ap.parse_args()

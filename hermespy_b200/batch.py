@@ -37,10 +37,16 @@ def sample_fading_links(channel: MultipathFadingChannel, num_links: int, num_tx:
     o = dim * dim
     spatial = np.exp(2j * np.pi * u[:, :o].reshape(num_links, dim, dim))[:, :num_rx, :num_tx]
     corr = channel.antenna_correlation
+    mix = {}
     if corr is not None:
         r_rx = corr.sample_covariance(num_rx, AntennaMode.RX)
         r_tx = corr.sample_covariance(num_tx, AntennaMode.TX)
-        spatial = r_rx[None] @ spatial @ r_tx[None]
+        if dim > 10 and not reciprocal:
+            # large-array extension: the Kronecker mix R_rx S R_tx (fading.py:480-489) runs on the device (K2,
+            # hb_kron_mix) when the block is uploaded -- FadingBatch.from_numpy / fading_propagate_host take the factors
+            mix = dict(r_rx=np.ascontiguousarray(r_rx, dtype=np.complex128), r_tx=np.ascontiguousarray(r_tx, dtype=np.complex128))
+        else:
+            spatial = r_rx[None] @ spatial @ r_tx[None]
     los_angle = 2 * np.pi * u[:, o : o + L]
     o += L
     nlos_angle = -np.pi + 2 * np.pi * u[:, o : o + L * N].reshape(num_links, L, N)
@@ -61,4 +67,5 @@ def sample_fading_links(channel: MultipathFadingChannel, num_links: int, num_tx:
         max_delay=int(round(channel.max_delay * bandwidth)),
         omega=omega, phi=phi, amp=amp, spatial=np.ascontiguousarray(spatial),
         omega_max=float(max(abs(channel.los_doppler_frequency), abs(channel.doppler_frequency)) / bandwidth),
+        **mix,
     )

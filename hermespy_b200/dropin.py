@@ -70,9 +70,14 @@ def fading_block_from_reference(sample) -> dict:
     spatial = np.ascontiguousarray(
         np.asarray(sample.spatial_response)[: sample.num_receive_antennas, : sample.num_transmit_antennas],
         dtype=np.complex128)
-    return dict(tap_delay=np.rint(np.asarray(sample.delay_profile) * fs).astype(np.int32),
-                max_delay=int(round(float(np.max(sample.delay_profile)) * fs)), omega=omega, phi=phi, amp=amp,
-                spatial=spatial, omega_max=float(max(abs(sample.los_doppler), abs(sample.nlos_doppler)) / fs))
+    tap_delay = np.rint(np.asarray(sample.delay_profile) * fs).astype(np.int32)
+    if np.any(np.diff(tap_delay) < 0):
+        # a sample built by hand (the reference's own unit tests do) may list its taps in any order; the channel classes
+        # sort theirs (fading.py:707-711).  The kernels want ascending delays: a tap sum does not care about the order.
+        order = np.argsort(tap_delay, kind="stable")
+        tap_delay, omega, phi, amp = tap_delay[order], omega[order], phi[order], amp[order]
+    return dict(tap_delay=tap_delay, max_delay=int(round(float(np.max(sample.delay_profile)) * fs)), omega=omega, phi=phi,
+                amp=amp, spatial=spatial, omega_max=float(max(abs(sample.los_doppler), abs(sample.nlos_doppler)) / fs))
 
 
 def element_table(antennas) -> np.ndarray:

@@ -109,7 +109,10 @@ class FadingBatch:
         return int(self.spatial.shape[2])
 
     @classmethod
-    def from_numpy(cls, tap_delay, max_delay, omega, phi, amp, spatial, omega_max=None, device="cuda"):
+    def from_numpy(cls, tap_delay, max_delay, omega, phi, amp, spatial, omega_max=None, device="cuda", r_rx=None,
+                   r_tx=None):
+        """Upload a host parameter block.  ``r_rx`` / ``r_tx``: antenna-correlation factors still to be applied,
+        ``spatial <- r_rx @ spatial @ r_tx`` on the device (K2 ``hb_kron_mix``, fading.py:480-489)."""
         torch = _torch()
         omega = np.ascontiguousarray(omega, dtype=np.float64)
         if omega_max is None:
@@ -119,13 +122,19 @@ class FadingBatch:
         def up(a, dt):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev, non_blocking=False)
 
+        s_dev = up(spatial, np.complex128)
+        if r_rx is not None or r_tx is not None:
+            from .montecarlo import kron_mix
+
+            s_dev = kron_mix(s_dev, None if r_rx is None else up(r_rx, np.complex128),
+                             None if r_tx is None else up(r_tx, np.complex128), out=s_dev)
         return cls(
             tap_delay=np.ascontiguousarray(tap_delay, dtype=np.int32),
             max_delay=int(max_delay),
             omega=up(omega, np.float64),
             phi=up(phi, np.float64),
             amp=up(amp, np.float64),
-            spatial=up(spatial, np.complex128),
+            spatial=s_dev,
             omega_max=float(omega_max),
         )
 
@@ -279,8 +288,11 @@ def fading_propagate_host(
     chunk_links: int = 0,
     return_info=False,
     device: Optional[int] = None,
+    r_rx: Optional[np.ndarray] = None,
+    r_tx: Optional[np.ndarray] = None,
 ):
     """Host-buffer entry (what a drop-in plugin calls): numpy in, numpy out, copies inside the call.
+    ``r_rx`` / ``r_tx``: correlation factors still to be applied to ``spatial`` (mixed on the device by K2 first).
 
     ``x`` is ``[B, Ntx, T]`` complex64 or complex128 (the reference's ``SignalBlock`` dtype).  ``device``: CUDA device
     index the call runs on (``hb_set_device`` on the calling thread; None = the thread's current device).
@@ -297,6 +309,13 @@ def fading_propagate_host(
     phi = np.ascontiguousarray(phi, dtype=np.float64)
     amp = np.ascontiguousarray(amp, dtype=np.float64)
     spatial = np.ascontiguousarray(spatial, dtype=np.complex128)
+    if r_rx is not None or r_tx is not None:
+        torch = _torch()
+        from .montecarlo import kron_mix
+
+        dev = f"cuda:{device}" if device is not None else "cuda"
+        to = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)).to(dev)
+        spatial = kron_mix(to(spatial), to(r_rx), to(r_tx)).cpu().numpy()
     if omega.shape != phi.shape or omega.ndim != 3 or omega.shape[0] != B:
         raise ValueError("omega/phi must have shape [B, L, N+1]")
     L, K = omega.shape[1], omega.shape[2]

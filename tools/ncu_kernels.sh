@@ -1,20 +1,17 @@
 #!/bin/bash
-# `ncu --set full` captures of the kernels the C2 bench does not exercise (run under gpurun, one GPU).
-# usage: tools/ncu_kernels.sh <round-tag>     -> gpurun_out/ncu_<tag>_{gemm,cdl,coef,zmode}*
-TAG=${1:-r01}
+# `ncu --set full` captures of the dominant kernel of every BASELINE config + the launch list of a bench step.
+# usage: tools/ncu_kernels.sh <round-tag>     -> gpurun_out/ncu_<tag>_*   (run under gpurun, one GPU)
+TAG=${1:-r02}
 mkdir -p gpurun_out
-cap() {  # name, kernel regex, skip, command...
-  local name=$1 k=$2 skip=$3; shift 3
-  ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o gpurun_out/ncu_${TAG}_$name "$@" > gpurun_out/ncu_${TAG}_$name.log 2>&1 || tail -3 gpurun_out/ncu_${TAG}_$name.log
-  ncu -i gpurun_out/ncu_${TAG}_$name.ncu-rep --page raw --csv > gpurun_out/ncu_${TAG}_${name}_raw.csv
-  ncu -i gpurun_out/ncu_${TAG}_$name.ncu-rep --page details > gpurun_out/ncu_${TAG}_${name}_details.txt
-  ncu -i gpurun_out/ncu_${TAG}_$name.ncu-rep --page source --csv > gpurun_out/ncu_${TAG}_${name}_src.csv 2>/dev/null
-  rm -f gpurun_out/ncu_${TAG}_$name.ncu-rep
-}
-cap gemm spatial_gemm 2 env B=64 python tools/bench_spatial_gemm.py
-cap cdl_propagate cdl_poly 1 python tools/config_report.py --configs C3 --steps 1
-cap cdl_moment cdl_moment 1 python tools/config_report.py --configs C3 --steps 1
-cap cdl_rays cdl_ray 1 python tools/config_report.py --configs C3 --steps 1
-cap coef sos_poly_coef 2 python bench.py --steps 2 --warmup 3 --links 2048 --no-cpu-baseline --no-e2e
-cap zmode tdl_tma 20 python tools/config_report.py --configs C4 --steps 1
-ls -la gpurun_out | grep ncu_${TAG}
+tools/ncu_one.sh tdl_tma ${TAG}_c2 2 --config C2
+tools/ncu_one.sh sos_poly_coef ${TAG}_c2_coef 2 --config C2
+tools/ncu_one.sh "tdl_tma|fused" ${TAG}_c4 2 --config C4
+tools/ncu_one.sh spatial_gemm ${TAG}_c4_gemm 2 --config C4
+tools/ncu_one.sh tdl_tma ${TAG}_c5 2 --config C5
+tools/ncu_one.sh "cdl_poly|cdl_tc" ${TAG}_c3 1 --config C3
+tools/ncu_one.sh tdl_ ${TAG}_c1 2 --config C1
+for c in C1 C2 C3 C4 C5; do
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${TAG}_$c.csv \
+    python bench.py --config $c --only --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+done
+ls -la gpurun_out | grep ${TAG}
