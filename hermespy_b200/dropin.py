@@ -243,11 +243,20 @@ def _cdl_state(self, num_samples, max_num_taps, interpolation_mode=None):
     return ChannelStateInformation(ChannelStateFormat.IMPULSE_RESPONSE, raw_state)
 
 
-def enable(precision: str = "f32", device: int | None = None, allow_reference_fallback: bool = False) -> None:
+def enabled() -> bool:
+    """True while the reference classes are patched."""
+    return bool(_ORIGINALS)
+
+
+def enable(precision: str = "f32", device: int | None = None, allow_reference_fallback: bool = False,
+           batch_drops: int = 0, workers: int = 0) -> None:
     """Patch the reference classes.  Fails loudly when the library or a CUDA device is missing.
 
     ``device``: CUDA device index every patched call runs on, from whatever thread it is made (None keeps
     ``config.device``; one process per GPU passes its local rank).  ``allow_reference_fallback``: see module docstring.
+    ``batch_drops`` > 0 additionally routes ``Simulation.run()`` through the batched drop runner
+    (``hermespy_b200.runner``): that many drops in flight per actor, their links propagated in one launch per stage;
+    ``workers`` forked helper processes run the lanes' modem / RF stages.
     """
     global _allow_fallback
     from . import _lib
@@ -263,6 +272,13 @@ def enable(precision: str = "f32", device: int | None = None, allow_reference_fa
     config.precision = precision
     _allow_fallback = bool(allow_reference_fallback)
     patch_reference()
+    config.batch_drops, config.workers = max(0, int(batch_drops)), max(0, int(workers))
+    from . import runner
+
+    if config.batch_drops > 0:
+        runner.patch_actor()
+    else:
+        runner.unpatch_actor()
 
 
 def patch_reference() -> None:
@@ -282,6 +298,10 @@ def patch_reference() -> None:
 
 
 def disable() -> None:
+    from . import runner
+
+    runner.unpatch_actor()
+    config.batch_drops = config.workers = 0
     if not _ORIGINALS:
         return
     from hermespy.channel.cdl.cluster_delay_lines import ClusterDelayLineSample  # type: ignore

@@ -45,13 +45,36 @@ def _ready(value: Any) -> ObjectRef:
     return ObjectRef(f)
 
 
+#: first exception raised inside an actor method since the last check.  The reference's driver loop discards the refs
+#: of ``actor.run.remote()`` (monte_carlo.py:385-389) and polls the queue manager for progress: a dead actor would make
+#: it spin forever.  Here the failure surfaces at the driver's next remote call instead.
+_actor_failure: list = []
+
+
+def _guarded(bound, name):
+    def call(*args, **kwargs):
+        try:
+            return bound(*args, **kwargs)
+        except BaseException as e:
+            if not _actor_failure:
+                _actor_failure.append((name, e))
+            raise
+
+    return call
+
+
 class _RemoteMethod(object):
     def __init__(self, handle: "ActorHandle", name: str) -> None:
         self._handle, self._name = handle, name
 
     def remote(self, *args, **kwargs) -> ObjectRef:
+        if _actor_failure and threading.current_thread() is threading.main_thread():
+            name, error = _actor_failure.pop()
+            _actor_failure.clear()
+            raise RuntimeError(f"actor method {name} failed: {error!r}") from error
         bound = getattr(self._handle._instance, self._name)
-        return ObjectRef(self._handle._pool.submit(bound, *args, **kwargs))
+        label = f"{type(self._handle._instance).__name__}.{self._name}"
+        return ObjectRef(self._handle._pool.submit(_guarded(bound, label), *args, **kwargs))
 
 
 def _retire_pool(pool) -> None:
@@ -163,6 +186,7 @@ def shutdown(*args, **kwargs) -> None:
     """End the 'cluster': actor threads are released (pending calls are dropped, running ones finish)."""
     global _initialized
     _initialized = False
+    _actor_failure.clear()
     while _live_pools:
         _live_pools.pop().shutdown(wait=False, cancel_futures=True)
 

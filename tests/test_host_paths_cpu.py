@@ -51,11 +51,13 @@ def test_ray_wait_edge_cases_and_pool_release():
         def f(self, x):
             return x + 1
 
+    import gc
+
+    gc.collect()  # actors of earlier Simulation.run() calls retire here, not inside the measurement
     n0 = len(shim._live_pools)
     h = shim.remote(Actor).remote()
     assert shim.get(h.f.remote(1)) == 2 and len(shim._live_pools) == n0 + 1
     del h
-    import gc
 
     gc.collect()
     assert len(shim._live_pools) == n0

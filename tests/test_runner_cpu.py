@@ -1,0 +1,149 @@
+"""Host logic of the batched drop runner (hermespy_b200/runner.py), no GPU: lanes, the restated link loop, request
+gathering / scattering, helper processes, and ``Simulation.run()`` routed through it -- all against the reference's own
+serial schedule with identical seeds (artifacts must be identical bit for bit)."""
+import numpy as np
+import pytest
+
+from oracle.refload import load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not available")
+
+
+def _simulation(num_samples=6, seed=42, snrs=(20, 10, 0)):
+    """_examples/getting_started/simulation.py, minus the plots, with every random root pinned."""
+    load_reference()
+    from hermespy.channel import TDL, TDLType
+    from hermespy.core import ConsoleMode, dB
+    from hermespy.modem import (BitErrorEvaluator, RootRaisedCosineWaveform, SimplexLink,
+                                SingleCarrierLeastSquaresChannelEstimation, SingleCarrierZeroForcingChannelEqualization)
+    from hermespy.simulation import SNR, Simulation
+
+    simulation = Simulation(console_mode=ConsoleMode.SILENT, num_samples=num_samples, seed=seed)
+    tx = simulation.new_device(oversampling_factor=4)
+    rx = simulation.new_device(oversampling_factor=4)
+    rx.noise_level = SNR(dB(20), tx)
+    simulation.set_channel(tx, rx, TDL(TDLType.A, doppler_frequency=100.0))
+    link = SimplexLink(seed=seed + 1)
+    tx.transmitters.add(link)
+    rx.receivers.add(link)
+    link.waveform = RootRaisedCosineWaveform(num_preamble_symbols=10, num_data_symbols=100, roll_off=0.9)
+    link.waveform.channel_estimation = SingleCarrierLeastSquaresChannelEstimation()
+    link.waveform.channel_equalization = SingleCarrierZeroForcingChannelEqualization()
+    dim = simulation.new_dimension("noise_level", dB(*snrs), rx)
+    ber = BitErrorEvaluator(link, link)
+    simulation.add_evaluator(ber)
+    return simulation, [dim], [ber]
+
+
+def _serial_reference(scenario, grid, evaluators, lane_index, base_seed, sections):
+    """What the reference's actor does with this lane's sections, one after the other (actors.py:367-441)."""
+    from hermespy.simulation.simulation import SimulationRunner
+
+    from hermespy_b200.runner import Lane
+
+    lane = Lane.clone_of(scenario, grid, evaluators, lane_index, base_seed)
+    runner = SimulationRunner(lane.scenario)
+    out = []
+    for s in sections:
+        lane.configure(s)
+        for stage in (runner.realize_channels, runner.sample_states, runner.transmit_operators, runner.generate_outputs,
+                      runner.propagate, runner.process_inputs, runner.receive_operators):
+            stage()
+        out.append([float(e.evaluate().artifact().to_scalar()) for e in lane.evaluators])
+    return out
+
+
+def _oracle_propagate(requests):
+    """Device stand-in for the CPU tests: the numpy restatement of fading.py:293-406 on the request's parameter block."""
+    out = []
+    for kind, blk, x, zero in requests:
+        assert kind == "fading" and not zero
+        T, D = x.shape[1], blk["max_delay"]
+        n = np.arange(T)
+        K = blk["omega"].shape[1]
+        amp = blk["amp"][:, [0] + [1] * (K - 1), None]
+        h = (amp * np.exp(1j * (blk["omega"][:, :, None] * n + blk["phi"][:, :, None]))).sum(1)
+        z = np.zeros((x.shape[0], T + D), complex)
+        for l, d in enumerate(blk["tap_delay"]):
+            z[:, d: d + T] += x * h[l]
+        out.append(blk["spatial"] @ z)
+    return out
+
+
+@pytest.mark.parametrize("workers", [0, 2])
+def test_lanes_reproduce_the_serial_reference_schedule(workers):
+    from hermespy_b200.runner import LaneSet
+
+    simulation, grid, evaluators = _simulation()
+    scenario = simulation.scenario
+    rounds = [[(0,), (1,), (2,)], [(1,), (1,), (0,)], [(2,), (0,)]]
+    lanes = LaneSet(scenario, grid, evaluators, 3, workers, base_seed=99, first_lane_is_original=False)
+    try:
+        got = [lanes.run_round(sections, lambda r: pytest.fail("no device requests expected")) for sections in rounds]
+    finally:
+        lanes.close()
+    for k in range(3):
+        mine = [r[k] for r in rounds if k < len(r)]
+        want = _serial_reference(scenario, grid, evaluators, k, 99, mine)
+        have = [[float(a.to_scalar()) for a in g[k]] for g in got if k < len(g)]
+        assert have == want, (k, have, want)
+    # lanes own independent random roots: three drops of one grid point differ
+    assert len({tuple(_serial_reference(scenario, grid, evaluators, k, 99, [(2,)])[0]) for k in range(3)}) > 1
+
+
+@pytest.mark.parametrize("workers", [0, 2])
+def test_deferred_links_scatter_back_correctly(workers):
+    """With the reference classes patched the fading links leave the lanes as (parameter block, block) requests and come
+    back as propagated blocks; a numpy stand-in for the device must reproduce the unpatched run to rounding."""
+    import hermespy_b200.dropin as dropin
+    from hermespy_b200.runner import LaneSet
+
+    simulation, grid, evaluators = _simulation()
+    scenario = simulation.scenario
+    rounds = [[(0,), (1,), (2,), (2,)], [(2,), (2,), (1,), (0,)]]
+    seen = []
+
+    def propagate(requests):
+        seen.append(len(requests))
+        return _oracle_propagate(requests)
+
+    dropin.patch_reference()  # host-side patch only: makes the sample types "device served" (no launch happens here)
+    try:
+        lanes = LaneSet(scenario, grid, evaluators, 4, workers, base_seed=7, first_lane_is_original=False)
+        try:
+            got = [lanes.run_round(s, propagate) for s in rounds]
+        finally:
+            lanes.close()
+    finally:
+        dropin.disable()
+    assert seen == [8, 8]  # 4 lanes x 2 fading links (both directions), ONE gathered call per round
+    for k in range(4):
+        want = _serial_reference(scenario, grid, evaluators, k, 7, [r[k] for r in rounds])
+        have = [[float(a.to_scalar()) for a in g[k]] for g in got]
+        assert have == want, (k, have, want)  # BER artifacts are decisions: identical although y differs in rounding
+
+
+def test_simulation_run_routed_through_the_runner():
+    load_reference()
+    import ray
+
+    from hermespy_b200 import config, runner
+    from hermespy_b200.shims import ray as shim
+
+    if getattr(ray, "__version__", "") != shim.__version__:
+        pytest.skip("a real ray is installed")
+    simulation, _, _ = _simulation(num_samples=7)
+    config.batch_drops, config.workers = 5, 0
+    runner.patch_actor()
+    runner.stats.update(rounds=0, drops=0, links=0)
+    try:
+        result = simulation.run()
+    finally:
+        runner.unpatch_actor()
+        config.batch_drops = 0
+    ber = np.asarray(result.evaluation_results[0].to_array(), dtype=float).ravel()
+    assert ber.shape == (3,) and np.all((ber >= 0) & (ber <= 0.5 + 1e-9)) and ber[0] < ber[2]
+    assert runner.stats["drops"] == 21 and runner.stats["rounds"] == 5  # 3 grid points x 7 samples, 5 drops per round
+    from hermespy.simulation.simulation import SimulationActor
+
+    assert "run" not in SimulationActor.__dict__  # restored
