@@ -93,6 +93,12 @@ KERNEL_KINDS = ("sos_poly_coef", "tdl_poly", "tdl_direct", "sos_state", "cdl_ray
                 "stats", "misc")
 
 
+class ReceiveInput(C.Structure):
+    """Mirror of ``hb_receive_input``."""
+
+    _fields_ = [("samples", C.c_void_p), ("num_samples", C.c_int32), ("offset", C.c_int32)]
+
+
 class ProfileReport(C.Structure):
     """Mirror of ``hb_profile_report``."""
 
@@ -150,6 +156,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.hb_spatial_gemm_3xtf32.restype = C.c_int
     lib.hb_spatial_gemm_3xtf32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_void_p]
+    lib.hb_receive_combine.restype = C.c_int
+    lib.hb_receive_combine.argtypes = [C.POINTER(ReceiveInput), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.hb_launch_counts.restype = None
     lib.hb_launch_counts.argtypes = [C.POINTER(C.c_int64)]
     lib.hb_profile_begin.restype = C.c_int

@@ -357,7 +357,8 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
   int chunk = chunk_links;
   if (chunk <= 0) {
     chunk = (int)std::max<size_t>(1, (48u << 20) / std::max<size_t>(1, x_link + y_link));
-    chunk = std::min(chunk, std::max(1, (p->batch + kSlots - 1) / kSlots));
+    if ((x_link + y_link) * (size_t)p->batch > (8u << 20))  // small batches: one chunk, one set of launches
+      chunk = std::min(chunk, std::max(1, (p->batch + kSlots - 1) / kSlots));
   }
   chunk = std::min(chunk, p->batch);
   size_t off = 0;

@@ -604,8 +604,10 @@ int hb_fading_propagate_host(const hb_fading_problem* p, const void* x, void* y,
   if (chunk <= 0) {
     const size_t target = 48u << 20;  // ~48 MB of input per chunk keeps the copy engines busy
     chunk = (int)std::max<size_t>(1, target / std::max<size_t>(1, x_link + y_link));
-    // at least kSlots chunks so that copies and kernels overlap
-    chunk = std::min(chunk, std::max(1, (p->batch + kSlots - 1) / kSlots));
+    // at least kSlots chunks so that copies and kernels overlap -- unless the whole batch is a few megabytes, where
+    // the extra launches cost more than the overlap hides (the batched drop runner's rounds of short frames)
+    if ((x_link + y_link) * (size_t)p->batch > (8u << 20))
+      chunk = std::min(chunk, std::max(1, (p->batch + kSlots - 1) / kSlots));
   }
   chunk = std::min(chunk, p->batch);
   // per-slot device layout: x | y | omega | phi | amp | spatial

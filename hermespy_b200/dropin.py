@@ -154,12 +154,59 @@ def cdl_block_from_reference(sample):
         los_amplitude=float((rice_lin / (1 + rice_lin)) ** 0.5), tx_elements=tx_el, rx_elements=rx_el)
 
 
+# ---- device work of the four replacements: plain arrays in, plain arrays out --------------------------------------------
+# Kept apart from the methods because a lane worker of the batched drop runner (a forked helper process, which must not
+# touch CUDA) forwards exactly these calls to the process that owns the GPU (runner.device_call).
+
+def _dev_fading_propagate(b: dict, x: np.ndarray) -> np.ndarray:
+    from .kernels import fading_propagate_host
+
+    return fading_propagate_host(x[None], b["tap_delay"], b["max_delay"], b["omega"][None], b["phi"][None], b["amp"][None],
+                                 b["spatial"][None], omega_max=b["omega_max"], precision=config.precision,
+                                 sos_mode=config.sos_mode, device=config.device)[0]
+
+
+def _dev_fading_state(b: dict, keep: np.ndarray, num_samples: int):
+    from . import _lib
+    from .kernels import FadingBatch, fading_state
+
+    _lib.set_device(config.device)
+    fb = FadingBatch.from_numpy(b["tap_delay"][keep], b["max_delay"], b["omega"][None][:, keep], b["phi"][None][:, keep],
+                                b["amp"][None][:, keep], b["spatial"][None], omega_max=b["omega_max"],
+                                device=f"cuda:{config.device}")
+    h, group_delay = fading_state(fb, int(num_samples), precision=config.precision, io128=True)
+    return h[0].cpu().numpy(), group_delay
+
+
+def _dev_cdl_propagate(blk, x: np.ndarray) -> np.ndarray:
+    from .kernels import cdl_propagate_host
+
+    return cdl_propagate_host(x[None], blk, precision=config.precision, device=config.device)[0]
+
+
+def _dev_cdl_state(blk, num_samples: int):
+    from . import _lib
+    from .kernels import CdlDeviceBlock, cdl_state
+
+    _lib.set_device(config.device)
+    h, gd = cdl_state(CdlDeviceBlock(blk, device=f"cuda:{config.device}"), int(num_samples))
+    return h[0].cpu().numpy(), gd  # [G, Nrx, Ntx, T]
+
+
+DEVICE_CALLS = {"fading_propagate": _dev_fading_propagate, "fading_state": _dev_fading_state,
+                "cdl_propagate": _dev_cdl_propagate, "cdl_state": _dev_cdl_state}
+
+
+def _device(name: str, *args):
+    from . import runner
+
+    return runner.device_call(name, *args)
+
+
 # ---- replacement methods (module level => picklable) ------------------------------------------------------------
 
 def _fading_propagate(self, signal, interpolation):
     from hermespy.core.signal_model import SignalBlock  # type: ignore
-
-    from .kernels import fading_propagate_host
 
     b = fading_block_from_reference(self)
     T = signal.num_samples
@@ -167,10 +214,7 @@ def _fading_propagate(self, signal, interpolation):
     if T + b["max_delay"] <= 0 or nrx == 0:
         out = np.zeros((nrx, T + b["max_delay"]), dtype=np.complex128)
     else:
-        x = np.ascontiguousarray(np.asarray(signal, dtype=np.complex128))[None]
-        out = fading_propagate_host(x, b["tap_delay"], b["max_delay"], b["omega"][None], b["phi"][None], b["amp"][None],
-                                    b["spatial"][None], omega_max=b["omega_max"], precision=config.precision,
-                                    sos_mode=config.sos_mode, device=config.device)[0]
+        out = _device("fading_propagate", b, np.ascontiguousarray(np.asarray(signal, dtype=np.complex128)))
     return SignalBlock(out.shape[0], out.shape[1], signal.offset, out.tobytes())
 
 
@@ -181,9 +225,6 @@ def _fading_state(self, num_samples, max_num_taps, interpolation_mode=None):
     from hermespy.core import ChannelStateFormat, ChannelStateInformation  # type: ignore
     from sparse import GCXS  # type: ignore
 
-    from . import _lib
-    from .kernels import FadingBatch, fading_state
-
     b = fading_block_from_reference(self)
     num_taps = min(1 + b["max_delay"], max_num_taps)
     siso_csi = np.zeros((num_samples, num_taps), dtype=np.complex128)
@@ -191,12 +232,8 @@ def _fading_state(self, num_samples, max_num_taps, interpolation_mode=None):
     if np.any(b["tap_delay"][keep] >= num_taps):  # ... and indexes out of bounds for d_l == num_taps (:358)
         raise IndexError(f"index {num_taps} is out of bounds for axis 1 with size {num_taps}")
     if num_samples >= 1 and num_taps >= 1 and np.any(keep):
-        _lib.set_device(config.device)
-        fb = FadingBatch.from_numpy(b["tap_delay"][keep], b["max_delay"], b["omega"][None][:, keep],
-                                    b["phi"][None][:, keep], b["amp"][None][:, keep], b["spatial"][None],
-                                    omega_max=b["omega_max"], device=f"cuda:{config.device}")
-        h, group_delay = fading_state(fb, int(num_samples), precision=config.precision, io128=True)
-        siso_csi[:, group_delay] = h[0].cpu().numpy().T
+        h, group_delay = _device("fading_state", b, keep, int(num_samples))
+        siso_csi[:, group_delay] = h.T
     mimo_csi = GCXS.from_numpy(np.einsum("ij,kl->ijkl", self.spatial_response, siso_csi), compressed_axes=(0, 1, 2))
     return ChannelStateInformation(ChannelStateFormat.IMPULSE_RESPONSE, mimo_csi, num_delay_taps=num_taps)
 
@@ -205,8 +242,6 @@ def _cdl_propagate(self, signal, interpolation):
     from hermespy.core import InterpolationMode  # type: ignore
     from hermespy.core.signal_model import SignalBlock  # type: ignore
 
-    from .kernels import cdl_propagate_host
-
     try:
         blk = cdl_block_from_reference(self)
     except UnsupportedByKernels as e:
@@ -214,8 +249,7 @@ def _cdl_propagate(self, signal, interpolation):
     if interpolation != InterpolationMode.NEAREST:
         out = np.zeros((self.num_receive_antennas, signal.num_samples + blk.max_delay), dtype=np.complex128)
     else:
-        x = np.ascontiguousarray(np.asarray(signal, dtype=np.complex128))[None]
-        out = cdl_propagate_host(x, blk, precision=config.precision, device=config.device)[0]
+        out = _device("cdl_propagate", blk, np.ascontiguousarray(np.asarray(signal, dtype=np.complex128)))
     return SignalBlock(out.shape[0], out.shape[1], signal._offset, out.tobytes())
 
 
@@ -224,9 +258,6 @@ def _cdl_state(self, num_samples, max_num_taps, interpolation_mode=None):
     ``hb_cdl_state`` (FP64 ray synthesis), scattered into the reference's dense [Nrx, Ntx, T, 1 + D] container."""
     from hermespy.core import ChannelStateFormat, ChannelStateInformation  # type: ignore
 
-    from . import _lib
-    from .kernels import CdlDeviceBlock, cdl_state
-
     try:
         blk = cdl_block_from_reference(self)
     except UnsupportedByKernels as e:
@@ -234,9 +265,7 @@ def _cdl_state(self, num_samples, max_num_taps, interpolation_mode=None):
     D = min(max_num_taps, blk.max_delay)
     raw_state = np.zeros((blk.num_rx, blk.num_tx, num_samples, 1 + D), dtype=np.complex128)
     if num_samples >= 1:
-        _lib.set_device(config.device)
-        h, gd = cdl_state(CdlDeviceBlock(blk, device=f"cuda:{config.device}"), int(num_samples))
-        h = h[0].cpu().numpy()  # [G, Nrx, Ntx, T]
+        h, gd = _device("cdl_state", blk, int(num_samples))
         for g, d in enumerate(gd):
             if d < max_num_taps:  # cluster_delay_lines.py:583-584
                 raw_state[:, :, :, d] = h[g]

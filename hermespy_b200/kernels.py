@@ -397,6 +397,58 @@ def fading_state(batch: FadingBatch, num_samples: int, precision="f32", io128=Tr
     return h, gd
 
 
+def receive_combine(signals, offsets=None, noise_re=None, noise_im=None, noise_power=None, num_samples=None, out=None):
+    """Superimpose the signals impinging on a device and add white Gaussian noise in one pass (``hb_receive_combine``).
+
+    ``signals``: device tensors ``[B, Nrx, T_k]`` of one complex dtype; ``offsets``: their whole-sample delays;
+    ``noise_re`` / ``noise_im``: the standard normals ``rng.standard_normal(shape)`` drawn TWICE in the reference's order
+    (rf/noise/model.py:149-151), float64 ``[B, Nrx, T]`` (host arrays are uploaded); ``noise_power``: scalar or ``[B]``.
+    Counterpart of the superposition in ``SimulatedDevice.process_input`` (simulated_device.py:1899-1915) followed by
+    ``AWGNRealization.add_to`` (model.py:140-160); complex128 results equal numpy's bit for bit.
+    """
+    torch = _torch()
+    lib = _lib.load()
+    signals = list(signals)
+    if not signals:
+        raise ValueError("at least one impinging signal is required")
+    if any(not s.is_cuda for s in signals):
+        raise _lib.HermesB200Error(_lib.HB_ERR_NO_DEVICE, "hb_receive_combine needs device tensors (no CPU fallback)")
+    dt, dev = signals[0].dtype, signals[0].device
+    if dt not in (torch.complex64, torch.complex128) or any(s.dtype != dt or s.dim() != 3 for s in signals):
+        raise ValueError("signals must be [B, Nrx, T] tensors of one complex dtype")
+    B, nrx = int(signals[0].shape[0]), int(signals[0].shape[1])
+    if any(tuple(s.shape[:2]) != (B, nrx) for s in signals):
+        raise ValueError("signals differ in batch size or stream count")
+    offsets = [0] * len(signals) if offsets is None else [int(o) for o in offsets]
+    if len(offsets) != len(signals) or min(offsets) < 0:
+        raise ValueError("one non-negative offset per signal")
+    signals = [s.contiguous() for s in signals]
+    T = max(o + int(s.shape[2]) for o, s in zip(offsets, signals)) if num_samples is None else int(num_samples)
+    desc = (_lib.ReceiveInput * len(signals))()
+    for k, (s, o) in enumerate(zip(signals, offsets)):
+        desc[k].samples, desc[k].num_samples, desc[k].offset = s.data_ptr(), int(s.shape[2]), o
+    nre = nim = scale = None
+    if noise_re is not None:
+        up = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))).to(
+            dev, torch.float64).contiguous()
+        nre, nim = up(noise_re), up(noise_im)
+        if tuple(nre.shape) != (B, nrx, T) or tuple(nim.shape) != (B, nrx, T):
+            raise ValueError(f"noise planes must be [B={B}, Nrx={nrx}, T={T}]")
+        p = np.broadcast_to(np.asarray(noise_power, dtype=np.float64), (B,))
+        scale = torch.from_numpy(np.ascontiguousarray((0.5 * p) ** 0.5)).to(dev)  # (0.5 * power) ** 0.5, model.py:149
+    if out is None:
+        out = torch.empty((B, nrx, T), dtype=dt, device=dev)
+    elif tuple(out.shape) != (B, nrx, T) or out.dtype != dt or not out.is_contiguous():
+        raise ValueError("out has the wrong shape / dtype / layout")
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.hb_receive_combine(desc, len(signals), nre.data_ptr() if nre is not None else None,
+                                          nim.data_ptr() if nim is not None else None,
+                                          scale.data_ptr() if scale is not None else None, out.data_ptr(), B, nrx, T,
+                                          1 if dt == torch.complex128 else 0, C.c_void_p(st)))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 # Cluster delay line
 

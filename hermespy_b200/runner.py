@@ -299,12 +299,35 @@ class Lane(object):
 
 # ---- helper processes for the CPU stages -----------------------------------------------------------------------------------
 
+_rpc_conn = None  # inside a lane worker: the pipe to the process that owns the GPU
+
+
+def device_call(name: str, *args):
+    """Run one of ``dropin.DEVICE_CALLS`` -- here, or, from inside a lane worker (a forked process must not touch CUDA),
+    in the process that owns the GPU.  Serves the calls that are not part of the batched link loop: ``state()`` for ideal
+    channel estimation, ``propagate`` from sample hooks."""
+    if _rpc_conn is None:
+        from . import dropin
+
+        return dropin.DEVICE_CALLS[name](*args)
+    _rpc_conn.send(("rpc", (name, args)))
+    status, reply = _rpc_conn.recv()
+    if status != "rpc_ok":
+        raise RuntimeError(f"device call {name} failed in the GPU process: {reply}")
+    return reply
+
+
 def _worker_main(conn, lanes: dict) -> None:
     """Serve the lanes of one helper process: ('pre', {lane: section}) -> requests; ('post', {lane: results}) -> artifacts."""
-    try:
+    global _rpc_conn
+    _rpc_conn = conn
+    try:  # one thread per helper: the helpers ARE the parallelism (BLAS / OpenMP pools would oversubscribe the cores)
         import torch
 
         torch.set_num_threads(1)
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
     except Exception:
         pass
     while True:
@@ -332,8 +355,10 @@ class LaneSet(object):
     """B lanes, in this process or spread over ``workers`` forked helper processes."""
 
     def __init__(self, scenario, grid, evaluators, num_lanes: int, workers: int, base_seed: int, stage_arguments=None,
-                 first_lane_is_original: bool = True) -> None:
+                 first_lane_is_original: bool = True, propagate=None) -> None:
+        """``propagate(requests) -> results``: the device call of a round (default ``propagate_requests``)."""
         self.num_lanes = max(1, int(num_lanes))
+        self.propagate = propagate_requests if propagate is None else propagate
         lanes = {}
         for k in range(self.num_lanes):
             if k == 0 and first_lane_is_original:
@@ -344,6 +369,12 @@ class LaneSet(object):
         self.procs: list = []
         workers = min(int(workers), self.num_lanes)
         if workers > 0:
+            # One throwaway drop in THIS process first: numba compiles the reference's jitted helpers (resampling, dB
+            # conversions, rotations) on first use, and the helpers inherit the compiled code by fork instead of each
+            # compiling its own copy.  The clone is discarded: no lane's random stream is touched.
+            warm = Lane.clone_of(scenario, grid, evaluators, 10**6, base_seed, stage_arguments)
+            warm.after_propagate(self.propagate(warm.before_propagate()))
+            del warm
             ctx = mp.get_context("fork")  # lanes travel by fork: no pickling of scenarios, exactly the parent's objects
             self.owner = {}
             for w in range(workers):
@@ -357,9 +388,10 @@ class LaneSet(object):
                     self.owner[k] = w
             self.local = {}
 
-    def run_round(self, sections: Sequence[tuple], propagate) -> List[list]:
+    def run_round(self, sections: Sequence[tuple], propagate=None) -> List[list]:
         """One stage-synchronous round: ``sections[k]`` runs on lane k; ``propagate(requests) -> results`` is called ONCE
         with the requests of all lanes.  Returns the artifacts per section."""
+        propagate = self.propagate if propagate is None else propagate
         n = len(sections)
         if n > self.num_lanes:
             raise ValueError("more sections than lanes")
@@ -374,9 +406,7 @@ class LaneSet(object):
                 by_worker.setdefault(self.owner[k], {})[k] = sections[k]
             for w, payload in by_worker.items():
                 self.procs[w][1].send(("pre", payload))
-            got = {}
-            for w in by_worker:
-                got.update(self._recv(w))
+            got = self._gather(by_worker)
             per_lane = [got[k] for k in range(n)]
         flat = [r for reqs in per_lane for r in reqs]
         results = propagate(flat) if flat else []
@@ -391,16 +421,40 @@ class LaneSet(object):
             by_worker.setdefault(self.owner[k], {})[k] = slices[k]
         for w, payload in by_worker.items():
             self.procs[w][1].send(("post", payload))
-        got = {}
-        for w in by_worker:
-            got.update(self._recv(w))
+        got = self._gather(by_worker)
         return [got[k] for k in range(n)]
 
-    def _recv(self, w):
-        status, reply = self.procs[w][1].recv()
-        if status != "ok":
-            raise RuntimeError(f"lane worker {w} failed: {reply}")
-        return reply
+    def _gather(self, workers) -> dict:
+        """Replies of the given workers, serving their device calls (``device_call``) while they work."""
+        from multiprocessing.connection import wait
+
+        from . import dropin
+
+        waiting = {self.procs[w][1]: w for w in workers}
+        got: dict = {}
+        failure = None
+        while waiting:
+            for conn in wait(list(waiting)):
+                try:
+                    status, reply = conn.recv()
+                except EOFError:
+                    failure = failure or f"lane worker {waiting.pop(conn)} died"
+                    continue
+                if status == "rpc":
+                    name, args = reply
+                    try:
+                        conn.send(("rpc_ok", dropin.DEVICE_CALLS[name](*args)))
+                    except Exception as e:
+                        conn.send(("rpc_error", f"{type(e).__name__}: {e}"))
+                    continue
+                w = waiting.pop(conn)
+                if status == "ok":
+                    got.update(reply)
+                else:
+                    failure = failure or f"lane worker {w} failed: {reply}"
+        if failure:
+            raise RuntimeError(failure)
+        return got
 
     def close(self) -> None:
         for p, conn in self.procs:
@@ -434,13 +488,14 @@ def batched_actor_run(self) -> None:
     if stage_arguments:  # stages iterating over argument lists nest drops inside drops: the serial schedule handles them
         return _original_run(self)
     scenario = self._investigated_object
-    lanes = LaneSet(scenario, self._MonteCarloActor__grid, self._MonteCarloActor__evaluators, config.batch_drops,
-                    config.workers, base_seed=scenario.seed if scenario.seed is not None else 0)
 
     def propagate(requests):
         stats["links"] += len(requests)
         stats["max_links_per_round"] = max(stats["max_links_per_round"], len(requests))
         return propagate_requests(requests)
+
+    lanes = LaneSet(scenario, self._MonteCarloActor__grid, self._MonteCarloActor__evaluators, config.batch_drops,
+                    config.workers, base_seed=scenario.seed if scenario.seed is not None else 0)
 
     try:
         exhausted = False
@@ -456,7 +511,7 @@ def batched_actor_run(self) -> None:
             if not group:
                 break
             try:
-                artifacts = lanes.run_round(group, propagate)
+                artifacts = lanes.run_round(group, propagate)  # (the warm-up drop of LaneSet is not counted in stats)
             except Exception as e:
                 if self.catch_exceptions:
                     print(e)

@@ -77,6 +77,9 @@ def make_sparse_module() -> types.ModuleType:
         def __getitem__(self, item):
             return type(self)(self._d[item])
 
+        def copy(self):
+            return type(self)(self._d.copy())
+
         def __array__(self, dtype=None, copy=None):
             return self._d if dtype is None else self._d.astype(dtype)
 

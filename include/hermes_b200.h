@@ -15,6 +15,8 @@
  *                             hermespy/channel/cdl/cluster_delay_lines.py:409-558
  *   hb_stats_accumulate    <- ScalarEvaluationResult.add_artifact  hermespy/core/pymonte/scalar.py:101-125
  *   hb_bit_errors          <- BitErrorEvaluator.evaluate/.artifact hermespy/modem/evaluators.py:231-259
+ *   hb_receive_combine     <- receive superposition + AWGNRealization.add_to
+ *                             hermespy/simulation/simulated_device.py:1899-1915, simulation/rf/noise/model.py:140-160
  *
  * Layouts (row-major, batch first):
  *   x      [B, Ntx, T]        complex64 (float2) or complex128 (double2), read-only
@@ -237,6 +239,24 @@ HB_API int hb_stats_accumulate(const double* artifact, const int32_t* cell, cons
  * out may alias spatial. */
 HB_API int hb_kron_mix(const void* r_rx, const void* spatial, const void* r_tx, void* out, int32_t batch,
                        int32_t num_rx, int32_t num_tx, void* stream);
+
+/* ---- receive side: superposition of the impinging signals + additive white Gaussian noise, one fused pass ------------
+ * out[b, i, m] = sum_k in_k[b, i, m - offset_k]  +  noise_scale[b] (noise_re[b, i, m] + j noise_im[b, i, m])
+ * Replaces, for impinging signals of one sampling rate / carrier frequency with whole-sample delays, the superposition
+ * loop of SimulatedDevice.process_input (hermespy/simulation/simulated_device.py:1899-1915) and AWGNRealization.add_to
+ * (hermespy/simulation/rf/noise/model.py:140-160).  The standard normals come from the caller's numpy generator (noise is
+ * part of the drop's random stream): two DEVICE float64 planes [B, Nrx, T]; noise_scale: DEVICE f64 [B] = sqrt(P_b / 2).
+ * noise_re == NULL: superposition only.  inputs: HOST array of descriptors with DEVICE sample pointers [B, Nrx, T_k]
+ * (element type per io_complex128); out: DEVICE [B, Nrx, num_out_samples].  complex128 results are bit-identical to the
+ * reference's numpy arithmetic (same summation order, no fused multiply-add). */
+typedef struct hb_receive_input {
+  const void* samples;  /* DEVICE [B, Nrx, num_samples] */
+  int32_t num_samples;  /* T_k */
+  int32_t offset;       /* first output sample this signal lands on (delay in samples) */
+} hb_receive_input;
+HB_API int hb_receive_combine(const hb_receive_input* inputs, int32_t num_inputs, const double* noise_re,
+                              const double* noise_im, const double* noise_scale, void* out, int32_t batch, int32_t num_rx,
+                              int32_t num_out_samples, int32_t io_complex128, void* stream);
 
 /* K4 for large arrays (SURVEY 8(b) `hb_spatial_gemm_3xtf32`): y[b] = spatial[b] @ z[b], the `spatial_response @
  * propagated` product of fading.py:395, on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy, FP32

@@ -109,7 +109,8 @@ def test_deferred_links_scatter_back_correctly(workers):
 
     dropin.patch_reference()  # host-side patch only: makes the sample types "device served" (no launch happens here)
     try:
-        lanes = LaneSet(scenario, grid, evaluators, 4, workers, base_seed=7, first_lane_is_original=False)
+        lanes = LaneSet(scenario, grid, evaluators, 4, workers, base_seed=7, first_lane_is_original=False,
+                        propagate=_oracle_propagate)  # (helpers: one warm-up drop in this process before the fork)
         try:
             got = [lanes.run_round(s, propagate) for s in rounds]
         finally:
@@ -147,3 +148,45 @@ def test_simulation_run_routed_through_the_runner():
     from hermespy.simulation.simulation import SimulationActor
 
     assert "run" not in SimulationActor.__dict__  # restored
+
+
+def test_device_calls_from_helper_processes_are_served_by_the_gpu_owner():
+    """``state()`` for ideal channel estimation is called deep inside a lane's receive stage.  A forked helper must not
+    touch CUDA: the call travels to the process that owns the GPU (here a numpy stand-in records where it ran)."""
+    import os
+
+    load_reference()
+    import hermespy_b200.dropin as dropin
+    from hermespy_b200.runner import LaneSet
+    from tests.test_dropin_gpu import _ofdm_2x1_alamouti_tdl_b  # 2x1 Alamouti OFDM, OFDMIdealChannelEstimation -> sample.state()
+
+    scenario, tx, rx, ber = _ofdm_2x1_alamouti_tdl_b(42)
+    grid, evaluators = [], [ber]
+    served = []
+
+    def fake_state(b, keep, num_samples):
+        served.append(os.getpid())
+        n = np.arange(num_samples)
+        K = b["omega"].shape[1]
+        amp = b["amp"][:, [0] + [1] * (K - 1), None]
+        h = (amp * np.exp(1j * (b["omega"][:, :, None] * n + b["phi"][:, :, None]))).sum(1)[keep]
+        gd = np.unique(b["tap_delay"][keep])
+        return np.stack([h[b["tap_delay"][keep] == d].sum(0) for d in gd]), gd
+
+    rounds = [[(), (), ()], [(), (), ()]]  # empty grid: every section is the empty coordinate tuple
+    dropin.patch_reference()
+    real = dropin.DEVICE_CALLS["fading_state"]
+    dropin.DEVICE_CALLS["fading_state"] = fake_state
+    try:
+        lanes = LaneSet(scenario, grid, evaluators, 3, 2, base_seed=3, first_lane_is_original=False, propagate=_oracle_propagate)
+        try:
+            got = [lanes.run_round(s) for s in rounds]
+        finally:
+            lanes.close()
+    finally:
+        dropin.DEVICE_CALLS["fading_state"] = real
+        dropin.disable()
+    assert len(served) >= 1 + 6 and set(served) == {os.getpid()}  # warm-up + one per drop, all in THIS process
+    for k in range(3):
+        want = _serial_reference(scenario, grid, evaluators, k, 3, [r[k] for r in rounds])
+        assert [[float(a.to_scalar()) for a in g[k]] for g in got] == want

@@ -23,7 +23,11 @@ import os
 import sys
 import time
 
-import numpy as np
+os.environ.setdefault("OMP_NUM_THREADS", "1")  # one thread per process in BOTH arms: processes are the parallelism
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
