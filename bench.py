@@ -336,10 +336,10 @@ def run_reference(args):
 class Workload:
     """One config on one rank: device-resident step, end-to-end step, algorithmic work, parity gate."""
 
-    def __init__(self, cfg, precision, rank, dev, links, e2e_links, sos_mode="auto"):
+    def __init__(self, cfg, precision, rank, dev, links, e2e_links, sos_mode="auto", sinc=False):
         import torch
 
-        self.cfg, self.precision, self.dev, self.rank = cfg, precision, dev, rank
+        self.cfg, self.precision, self.dev, self.rank, self.sinc = cfg, precision, dev, rank, sinc
         self.B, self.T, self.ntx, self.nrx = links, cfg["T"], cfg["ntx"], cfg["nrx"]
         self.sos_mode = sos_mode
         self.cdtype = torch.complex128 if precision == "f64" else torch.complex64
@@ -366,6 +366,12 @@ class Workload:
             from hermespy_b200.kernels import FadingBatch
 
             self.blk = sample_fading_links(ch, self.B, self.ntx, self.nrx, cfg["fs"])
+            if self.sinc:
+                # fractional delays (extension): every tap at its true delay -> 12 windowed-sinc taps at integer delays;
+                # the kernels are the NEAREST ones (equal delays merge), the tap table carries the interpolation
+                from hermespy_b200.kernels import sinc_expand
+
+                self.blk.update(sinc_expand(ch.delays, cfg["fs"], self.blk["omega"], self.blk["phi"], self.blk["amp"]))
             self.fb = FadingBatch.from_numpy(device=self.dev, **self.blk)
             self.D = self.blk["max_delay"]
             self.channel = ch
@@ -442,7 +448,7 @@ class Workload:
     def parity(self):
         cfg = self.cfg
         n = cfg["oracle_links"]
-        Tn = min(self.T, cfg.get("oracle_samples", self.T))  # causal channel: a prefix of x determines the same prefix of y
+        Tn = min(self.T, cfg.get("oracle_samples", self.T) // (4 if self.sinc else 1))  # causal channel: a prefix of x determines the same prefix of y
         y = self.y[:n, :, :Tn].cpu().numpy().astype(np.complex128)
         x = self.x[:n, :, :Tn].cpu().numpy().astype(np.complex128)
         worst = 0.0
@@ -471,7 +477,7 @@ class Workload:
                 "ok": bool(worst <= tol), "oracle": "numpy float64 restatement (oracle/), same links and signal as the timed batch"}
 
 
-def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allreduce):
+def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allreduce, sinc=False):
     """One config on this rank (all ranks call it together): returns the record (rank 0) or None."""
     import torch
     import torch.distributed as dist
@@ -482,7 +488,8 @@ def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allre
     links = args.links if (args.links and cfg["id"] == args.config) else cfg["links"]
     if precision == "f64":
         links = max(1, links // 8)  # the FP64 direct kernels are ~10x slower per link: keep the step a fraction of a second
-    wl = Workload(cfg, precision, rank, dev, links, min(args.e2e_links or cfg["e2e_links"], cfg["e2e_links"]), args.sos_mode)
+    wl = Workload(cfg, precision, rank, dev, links, min(args.e2e_links or cfg["e2e_links"], cfg["e2e_links"]), args.sos_mode,
+                  sinc=sinc)
     B, T = wl.B, wl.T
     grid_stats = GridStatistics((7,), device=dev)  # evaluator statistics: the only data that crosses GPUs
     pending, counter = [], [0]
@@ -590,6 +597,8 @@ def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allre
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": precision, "data": "synthetic", "config": public_config(cfg, precision),
+        "delay_interpolation": ("SINC: 12-tap Kaiser-windowed sinc per channel tap at its true delay (extension with its own "
+                                "oracle; the reference rounds delays)") if sinc else "NEAREST (the reference's rounding, parity mode)",
         "run": {"links_per_step_per_gpu": B, "steps_for_whole_job": int(np.ceil(cfg["total_links"] / (B * world))),
                 "l2_policy": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB in + out per step)" if alg_bytes > 2 * 126e6
                 else f"in + out {alg_bytes / 1e6:.0f} MB per step: L2-resident between steps (the whole job of this config is one step)",
@@ -632,21 +641,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         _lib.reserve_sms(args.reserve_sms)  # room for the statistics all-reduce next to the persistent kernels
     allreduce = world > 1 and not os.environ.get("HB_BENCH_SKIP_COLLECTIVE")
-    head = measure(CONFIGS[args.config], args.precision, args, world, rank, dev, args.steps, not args.no_cpu_baseline, allreduce)
+    head = measure(CONFIGS[args.config], args.precision, args, world, rank, dev, args.steps, not args.no_cpu_baseline, allreduce,
+                   sinc=args.sinc)
     subs = {}
     if not args.only:
         sub_steps = max(1, min(args.steps, 20))
-        todo = [(c, "f32") for c in CONFIGS if c != args.config] + [(args.config, "f64" if args.precision == "f32" else "f32")]
-        for cid, prec in todo:
+        todo = [(c, "f32", False) for c in CONFIGS if c != args.config] + \
+               [(args.config, "f64" if args.precision == "f32" else "f32", False), ("C5", "f32", True)]
+        for cid, prec, sinc in todo:
             try:
-                rec = measure(CONFIGS[cid], prec, args, world, rank, dev, sub_steps, not args.no_cpu_baseline and prec == "f32",
-                              allreduce)
+                rec = measure(CONFIGS[cid], prec, args, world, rank, dev, sub_steps,
+                              not args.no_cpu_baseline and prec == "f32" and not sinc, allreduce, sinc=sinc)
             except Exception as e:  # one config must not hide the others; the failure is part of the record
                 rec = {"error": repr(e), "config": public_config(CONFIGS[cid], prec)}
                 if world > 1:
                     raise
             if rank == 0:
-                subs[cid if prec == "f32" or cid != args.config else f"{cid}_{prec}"] = rec
+                subs[f"{cid}_sinc" if sinc else (cid if prec == "f32" or cid != args.config else f"{cid}_{prec}")] = rec
     if rank == 0:
         if subs:
             head["configs"] = subs
@@ -668,6 +679,7 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"],
                     help="f32: complex64 arithmetic (rel-L2 <= 1e-5); f64: float64 parity mode (bit-exact BER counts)")
     ap.add_argument("--only", action="store_true", help="measure the headline config only (no per-config sub-records)")
+    ap.add_argument("--sinc", action="store_true", help="headline config with fractional (windowed-sinc) delays (extension)")
     ap.add_argument("--links", type=int, default=0, help="links per step per GPU of the headline config (0 = config default)")
     ap.add_argument("--e2e-links", type=int, default=0, help="links per end-to-end step per GPU (0 = config default)")
     ap.add_argument("--stats-every", type=int, default=10, help="N > 1: batches between statistics all-reduces")

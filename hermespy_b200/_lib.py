@@ -126,6 +126,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.hb_set_device.argtypes = [C.c_int]
     lib.hb_fading_plan.restype = C.c_int
     lib.hb_fading_plan.argtypes = [C.POINTER(FadingProblem), C.POINTER(FadingPlanInfo)]
+    lib.hb_fading_sinc_taps.restype = C.c_int
+    lib.hb_fading_sinc_taps.argtypes = [C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32)]
     lib.hb_fading_propagate.restype = C.c_int
     lib.hb_fading_propagate.argtypes = [
         C.POINTER(FadingProblem),

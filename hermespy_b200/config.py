@@ -10,6 +10,9 @@ precision = "f32"
 sos_mode = "auto"
 #: CUDA device index used by the host-facing plugin API.
 device = 0
+#: extension (NOT reference behaviour): serve ``InterpolationMode.SINC`` requests to the fading channel with windowed-sinc
+#: fractional delays instead of the reference's rounding (fading.py:297 ignores the interpolation argument)
+sinc_extension = False
 #: batched drop runner (hermespy_b200/runner.py): drops in flight per Simulation actor (0 = the reference's serial loop)
 batch_drops = 0
 #: forked helper processes that run the lanes' CPU stages (0 = lanes run in the actor's own process)

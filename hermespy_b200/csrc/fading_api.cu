@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -665,6 +666,52 @@ int hb_fading_propagate_host(const hb_fading_problem* p, const void* x, void* y,
     if (e != cudaSuccess && rc == HB_OK) rc = cuda_fail(e, "cudaStreamSynchronize(pipeline)");
   }
   return rc;
+}
+
+int hb_fading_sinc_taps(const double* delay_samples, int32_t num_taps, int32_t half_width, double kaiser_beta,
+                        int32_t capacity, int32_t* out_delay, double* out_weight, int32_t* out_source, int32_t* num_out) {
+  if (!delay_samples || !out_delay || !out_weight || !out_source || !num_out || num_taps < 0 || half_width < 1 ||
+      half_width > 64 || !(kaiser_beta >= 0.0)) {
+    set_error("invalid windowed-sinc expansion request (taps=%d half_width=%d beta=%g)", num_taps, half_width, kaiser_beta);
+    return HB_ERR_INVALID;
+  }
+  struct Tap {
+    int32_t delay, source;
+    double weight;
+  };
+  std::vector<Tap> taps;
+  const double i0b = std::cyl_bessel_i(0.0, kaiser_beta);
+  for (int l = 0; l < num_taps; ++l) {
+    const double tau = delay_samples[l];
+    if (!(tau >= 0.0) || tau > 1e9) {
+      set_error("tap %d: delay of %g samples is not a finite non-negative number", l, tau);
+      return HB_ERR_INVALID;
+    }
+    const long long fl = (long long)floor(tau);
+    for (long long j = fl - half_width + 1; j <= fl + half_width; ++j) {
+      if (j < 0) continue;  // non-causal precursor: dropped (documented truncation)
+      const double u = (double)j - tau;
+      if (fabs(u) >= (double)half_width) continue;
+      const double sinc = u == floor(u) ? (u == 0.0 ? 1.0 : 0.0) : sin(M_PI * u) / (M_PI * u);  // exact zeros at integers
+      const double r = u / (double)half_width;
+      const double g = sinc * std::cyl_bessel_i(0.0, kaiser_beta * sqrt(1.0 - r * r)) / i0b;
+      if (g == 0.0) continue;
+      taps.push_back({(int32_t)j, (int32_t)l, g});
+    }
+  }
+  std::stable_sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) { return a.delay < b.delay; });
+  *num_out = (int32_t)taps.size();
+  if ((int)taps.size() > capacity) {
+    set_error("windowed-sinc expansion needs %zu taps, capacity is %d (HB_MAX_TAPS = %d per launch)", taps.size(), capacity,
+              HB_MAX_TAPS);
+    return HB_ERR_UNSUPPORTED;
+  }
+  for (size_t t = 0; t < taps.size(); ++t) {
+    out_delay[t] = taps[t].delay;
+    out_weight[t] = taps[t].weight;
+    out_source[t] = taps[t].source;
+  }
+  return HB_OK;
 }
 
 int hb_fading_state(const hb_fading_problem* p, void* h, int32_t* group_delay_out, void* stream) {

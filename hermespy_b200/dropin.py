@@ -59,9 +59,10 @@ def _unsupported(kind: str, why: str, self, *args):
 
 # ---- parameter extraction from reference objects (pure host code, testable without a GPU) --------------------
 
-def fading_block_from_reference(sample) -> dict:
-    """Kernel parameter block of a reference ``MultipathFadingSample`` (same layout as the mirror class)."""
-    from .kernels import fading_param_block
+def fading_block_from_reference(sample, sinc: bool = False) -> dict:
+    """Kernel parameter block of a reference ``MultipathFadingSample`` (same layout as the mirror class).
+    ``sinc``: fractional-delay extension -- taps at their true delays, expanded to windowed-sinc filters."""
+    from .kernels import fading_param_block, sinc_expand
 
     fs = sample.bandwidth
     omega, phi, amp = fading_param_block(sample.power_profile, sample.delay_profile, sample.los_gains,
@@ -70,6 +71,10 @@ def fading_block_from_reference(sample) -> dict:
     spatial = np.ascontiguousarray(
         np.asarray(sample.spatial_response)[: sample.num_receive_antennas, : sample.num_transmit_antennas],
         dtype=np.complex128)
+    if sinc:
+        blk = sinc_expand(np.asarray(sample.delay_profile, dtype=np.float64), fs, omega, phi, amp)
+        blk.update(spatial=spatial, omega_max=float(max(abs(sample.los_doppler), abs(sample.nlos_doppler)) / fs))
+        return blk
     tap_delay = np.rint(np.asarray(sample.delay_profile) * fs).astype(np.int32)
     if np.any(np.diff(tap_delay) < 0):
         # a sample built by hand (the reference's own unit tests do) may list its taps in any order; the channel classes
@@ -206,9 +211,12 @@ def _device(name: str, *args):
 # ---- replacement methods (module level => picklable) ------------------------------------------------------------
 
 def _fading_propagate(self, signal, interpolation):
+    from hermespy.core import InterpolationMode  # type: ignore
     from hermespy.core.signal_model import SignalBlock  # type: ignore
 
-    b = fading_block_from_reference(self)
+    # the reference ignores `interpolation` here (fading.py:371-406 rounds every delay): so does this path, unless the
+    # fractional-delay extension was switched on explicitly
+    b = fading_block_from_reference(self, sinc=config.sinc_extension and interpolation == InterpolationMode.SINC)
     T = signal.num_samples
     nrx = b["spatial"].shape[0]
     if T + b["max_delay"] <= 0 or nrx == 0:
@@ -278,14 +286,16 @@ def enabled() -> bool:
 
 
 def enable(precision: str = "f32", device: int | None = None, allow_reference_fallback: bool = False,
-           batch_drops: int = 0, workers: int = 0) -> None:
+           batch_drops: int = 0, workers: int = 0, sinc_extension: bool = False) -> None:
     """Patch the reference classes.  Fails loudly when the library or a CUDA device is missing.
 
     ``device``: CUDA device index every patched call runs on, from whatever thread it is made (None keeps
     ``config.device``; one process per GPU passes its local rank).  ``allow_reference_fallback``: see module docstring.
     ``batch_drops`` > 0 additionally routes ``Simulation.run()`` through the batched drop runner
     (``hermespy_b200.runner``): that many drops in flight per actor, their links propagated in one launch per stage;
-    ``workers`` forked helper processes run the lanes' modem / RF stages.
+    ``workers`` forked helper processes run the lanes' modem / RF stages.  ``sinc_extension``: fading samples asked to
+    propagate with ``InterpolationMode.SINC`` use windowed-sinc fractional delays (an extension: the reference rounds
+    whatever the mode, and that stays the default).
     """
     global _allow_fallback
     from . import _lib
@@ -299,6 +309,7 @@ def enable(precision: str = "f32", device: int | None = None, allow_reference_fa
             raise ValueError(f"device {device} outside the {_lib.device_count()} visible CUDA devices")
         config.device = int(device)
     config.precision = precision
+    config.sinc_extension = bool(sinc_extension)
     _allow_fallback = bool(allow_reference_fallback)
     patch_reference()
     config.batch_drops, config.workers = max(0, int(batch_drops)), max(0, int(workers))
@@ -331,6 +342,7 @@ def disable() -> None:
 
     runner.unpatch_actor()
     config.batch_drops = config.workers = 0
+    config.sinc_extension = False
     if not _ORIGINALS:
         return
     from hermespy.channel.cdl.cluster_delay_lines import ClusterDelayLineSample  # type: ignore

@@ -72,6 +72,41 @@ def fading_param_block(
     return omega, phi, amp
 
 
+SINC_HALF_WIDTH = 6     # 12-tap fractional-delay filters: 20 COST259 taps expand to 240 <= HB_MAX_TAPS
+SINC_KAISER_BETA = 6.0
+
+
+def sinc_expand(delay_seconds: np.ndarray, fs: float, omega: np.ndarray, phi: np.ndarray, amp: np.ndarray,
+                half_width: int = SINC_HALF_WIDTH, beta: float = SINC_KAISER_BETA) -> dict:
+    """Fractional-delay (``InterpolationMode.SINC``) form of a fading parameter block: every tap at its TRUE delay
+    ``delay * fs`` becomes up to ``2 * half_width`` Kaiser-windowed-sinc taps at integer delays (``hb_fading_sinc_taps``).
+
+    ``omega / phi [..., L, N+1]`` and ``amp [..., L, 2]`` are gathered per expanded tap, amplitudes scaled by the filter
+    weight.  Returns ``dict(tap_delay, max_delay, omega, phi, amp)`` for ``FadingBatch.from_numpy`` /
+    ``fading_propagate_host`` -- the propagation kernels are the NEAREST ones (equal delays merge into one group); the
+    extension lives entirely in the tap table.  The reference itself rounds delays (fading.py:297): this is an extension
+    with its own oracle (``oracle.fading_oracle.propagate_sinc``)."""
+    lib = _lib.load()
+    d = np.ascontiguousarray(np.asarray(delay_seconds, dtype=np.float64) * float(fs))
+    L = d.shape[0]
+    cap = 2 * int(half_width) * L
+    od, ow, osrc = np.zeros(cap, np.int32), np.zeros(cap, np.float64), np.zeros(cap, np.int32)
+    n = C.c_int32(0)
+    _lib.check(lib.hb_fading_sinc_taps(d.ctypes.data_as(C.POINTER(C.c_double)), L, int(half_width), float(beta), cap,
+                                       od.ctypes.data_as(C.POINTER(C.c_int32)), ow.ctypes.data_as(C.POINTER(C.c_double)),
+                                       osrc.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)))
+    n = int(n.value)
+    if n > _lib.HB_MAX_TAPS:
+        raise _lib.HermesB200Error(_lib.HB_ERR_UNSUPPORTED, f"windowed-sinc expansion yields {n} taps (limit {_lib.HB_MAX_TAPS}); "
+                                   "use a smaller half_width")
+    od, ow, osrc = od[:n], ow[:n], osrc[:n]
+    omega, phi, amp = (np.asarray(a, dtype=np.float64) for a in (omega, phi, amp))
+    # output length T + D_s with D_s = max floor(delay) + half_width, whether or not the last filter taps are non-zero
+    return dict(tap_delay=od.copy(), max_delay=int(np.floor(d).max()) + int(half_width) if L else 0,
+                omega=np.ascontiguousarray(omega[..., osrc, :]), phi=np.ascontiguousarray(phi[..., osrc, :]),
+                amp=np.ascontiguousarray(amp[..., osrc, :] * ow[:, None]))
+
+
 @dataclass
 class FadingBatch:
     """Parameters of B fading links that share one delay profile (one kernel launch).

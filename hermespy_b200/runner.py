@@ -95,7 +95,11 @@ def _submit(matrix, pending, requests, row, col, sample, transmission, interpola
         raise ValueError("Number of signal streams to be propagated does not match the number of transmitter antennas "
                          f"({signal.num_streams} != {sample.num_transmit_antennas}))")
     try:
-        block = dropin.fading_block_from_reference(sample) if kind == "fading" else dropin.cdl_block_from_reference(sample)
+        if kind == "fading":
+            block = dropin.fading_block_from_reference(
+                sample, sinc=config.sinc_extension and interpolation == InterpolationMode.SINC)
+        else:
+            block = dropin.cdl_block_from_reference(sample)
     except dropin.UnsupportedByKernels as e:
         matrix[row, col] = _serve_unsupported(kind, e, sample, signal, interpolation)
         return

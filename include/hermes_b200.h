@@ -124,6 +124,19 @@ HB_API int hb_set_device(int device);
 
 HB_API int hb_fading_plan(const hb_fading_problem* p, hb_fading_plan_info* info);
 
+/* Fractional delays (extension; the reference rounds, fading.py:297): polyphase expansion of L taps with real-valued
+ * delays into windowed-sinc integer-delay taps.  Tap l at delay_samples[l] = floor + eps becomes the 2 W taps
+ *   j = floor - W + 1 .. floor + W   with weight  g(j - delay) = sinc(u) I0(beta sqrt(1 - (u / W)^2)) / I0(beta),
+ * taps at negative delays (non-causal precursor) and zero-weight taps are dropped, integer delays stay single taps.
+ * HOST arrays: out_delay / out_weight / out_source hold up to `capacity` entries, sorted by delay (stable in l):
+ * expanded tap t has integer delay out_delay[t], the sinusoid parameters of tap out_source[t] and its amplitudes
+ * scaled by out_weight[t].  Feeding the expanded set to hb_fading_propagate* (whose kernels merge equal delays) IS the
+ * InterpolationMode.SINC path (hermespy/core/definitions.py:82-93).  Returns the number of expanded taps through
+ * num_out, HB_ERR_UNSUPPORTED when it exceeds capacity. */
+HB_API int hb_fading_sinc_taps(const double* delay_samples, int32_t num_taps, int32_t half_width, double kaiser_beta,
+                               int32_t capacity, int32_t* out_delay, double* out_weight, int32_t* out_source,
+                               int32_t* num_out);
+
 /* Device-resident propagation.  x, y and all DEVICE members of p live on the current device;
  * the work is enqueued on `stream` (a cudaStream_t; NULL = legacy default stream) and the call
  * returns without synchronizing. */

@@ -508,3 +508,29 @@ def test_baseline_shapes_from_reference_samples(ref, build):
     assert y0.shape == y64.shape == y32.shape
     assert rel_l2(y64, y0) < tol64
     assert rel_l2(y32, y0) < 1e-5
+
+
+def test_sinc_extension_is_opt_in_and_matches_its_oracle(ref):
+    """The reference rounds fading delays whatever the interpolation mode (fading.py:297): so does the drop-in, unless
+    ``enable(sinc_extension=True)``; then ``InterpolationMode.SINC`` requests get windowed-sinc fractional delays."""
+    import hermespy.channel as RC
+    import hermespy.simulation as S
+    from hermespy.core import InterpolationMode, Signal
+    from oracle import fading_oracle as fo
+    from oracle.ref_extract import fading_params_from_reference_sample
+
+    dev = lambda: S.SimulatedDevice(bandwidth=30.72e6, oversampling_factor=1, carrier_frequency=3.5e9)
+    s = RC.Cost259(RC.Cost259Type.URBAN, doppler_frequency=50, seed=9).realize().sample(dev(), dev())
+    sig = Signal.Create(golden_signal(800, 1, 4096), 30.72e6, 3.5e9)
+    ref.disable()
+    y_ref = np.asarray(s.propagate(sig, InterpolationMode.SINC).view(np.ndarray))  # the reference: rounds anyway
+    ref.enable(precision="f64")
+    y_default = np.asarray(s.propagate(sig, InterpolationMode.SINC).view(np.ndarray))
+    ref.enable(precision="f64", sinc_extension=True)
+    y_sinc = np.asarray(s.propagate(sig, InterpolationMode.SINC).view(np.ndarray))
+    y_nearest = np.asarray(s.propagate(sig, InterpolationMode.NEAREST).view(np.ndarray))
+    ref.disable()
+    assert rel_l2(y_default, y_ref) < 1e-12 and rel_l2(y_nearest, y_ref) < 1e-12
+    want = fo.propagate_sinc(fading_params_from_reference_sample(s), np.asarray(sig.view(np.ndarray)))
+    assert y_sinc.shape == want.shape and rel_l2(y_sinc, want) < 1e-12
+    assert rel_l2(y_sinc[:, : y_ref.shape[1]], y_ref) > 1e-2  # fractional delays do change the signal

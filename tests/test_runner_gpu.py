@@ -61,4 +61,4 @@ def test_simulation_run_batched_on_the_gpu():
     assert runner.stats["drops"] == 48 and runner.stats["links"] == 96 and runner.stats["rounds"] == 4
     assert runner.stats["max_links_per_round"] == 24
     launches = sum(after.values()) - sum(before.values())
-    assert 4 <= launches <= 8, launches  # coefficient + propagate kernel per round -- not per drop
+    assert 4 <= launches <= 12, launches  # coefficient + propagate kernel per round (+ the warm-up drop) -- not per drop
