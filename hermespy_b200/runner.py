@@ -339,7 +339,7 @@ def _worker_main(conn, lanes: dict) -> None:
             msg = conn.recv()
         except EOFError:
             return
-        op, payload = msg
+        op, tag, payload = msg
         try:
             if op == "stop":
                 return
@@ -350,9 +350,9 @@ def _worker_main(conn, lanes: dict) -> None:
                     reply[lid] = lanes[lid].before_propagate()
             else:
                 reply = {lid: lanes[lid].after_propagate(results) for lid, results in payload.items()}
-            conn.send(("ok", reply))
+            conn.send(("ok", (op, tag, reply)))
         except Exception as e:  # ship the failure to the owner of the GPU; it decides (catch_exceptions)
-            conn.send(("error", f"{type(e).__name__}: {e}\n{traceback.format_exc()}"))
+            conn.send(("error", (op, tag, f"{type(e).__name__}: {e}\n{traceback.format_exc()}")))
 
 
 class LaneSet(object):
@@ -371,6 +371,7 @@ class LaneSet(object):
                 lanes[k] = Lane.clone_of(scenario, grid, evaluators, k, base_seed, stage_arguments)
         self.local = lanes
         self.procs: list = []
+        self._mail: dict = {}
         workers = min(int(workers), self.num_lanes)
         if workers > 0:
             # One throwaway drop in THIS process first: numba compiles the reference's jitted helpers (resampling, dB
@@ -399,71 +400,112 @@ class LaneSet(object):
         n = len(sections)
         if n > self.num_lanes:
             raise ValueError("more sections than lanes")
-        if not self.procs:
-            per_lane = []
-            for k in range(n):
-                self.local[k].configure(sections[k])
-                per_lane.append(self.local[k].before_propagate())
-        else:
-            by_worker: dict = {}
-            for k in range(n):
-                by_worker.setdefault(self.owner[k], {})[k] = sections[k]
-            for w, payload in by_worker.items():
-                self.procs[w][1].send(("pre", payload))
-            got = self._gather(by_worker)
-            per_lane = [got[k] for k in range(n)]
+        lanes = list(range(n))
+        self._send("pre", 0, lanes, sections)
+        per_lane = self._await("pre", 0, lanes)
+        self._send("post", 0, lanes, self._propagate_split(per_lane, propagate))
+        return self._await("post", 0, lanes)
+
+    def run_stream(self, sections, propagate=None, groups: int = 2):
+        """Pipelined rounds: the lanes are split into ``groups`` lane groups that alternate, so the helpers compute one
+        group's stages while the GPU owner gathers, launches and scatters the other's.  ``sections``: iterable of grid
+        sections; yields ``(section, artifacts)`` in completion order."""
+        propagate = self.propagate if propagate is None else propagate
+        groups = max(1, min(int(groups), self.num_lanes)) if self.procs else 1
+        size = (self.num_lanes + groups - 1) // groups
+        it = iter(sections)
+        pre: dict = {}   # group -> (lanes, sections) whose stages 0-3 are running
+        post: dict = {}  # group -> (lanes, sections) whose stages 5-6 are running
+
+        def start(g):
+            lanes, secs = [], []
+            for lane in range(g * size, min(self.num_lanes, (g + 1) * size)):
+                try:
+                    secs.append(next(it))
+                except StopIteration:
+                    break
+                lanes.append(lane)
+            if lanes:
+                self._send("pre", g, lanes, secs)
+                pre[g] = (lanes, secs)
+
+        for g in range(groups):
+            start(g)
+        while pre or post:
+            for g in range(groups):
+                if g in post:
+                    lanes, secs = post.pop(g)
+                    for sec, art in zip(secs, self._await("post", g, lanes)):
+                        yield sec, art
+                if g in pre:
+                    lanes, secs = pre.pop(g)
+                    per_lane = self._await("pre", g, lanes)
+                    self._send("post", g, lanes, self._propagate_split(per_lane, propagate))
+                    post[g] = (lanes, secs)
+                    start(g)  # queued behind the post message: the helpers run it as soon as they are through
+
+    @staticmethod
+    def _propagate_split(per_lane, propagate):
         flat = [r for reqs in per_lane for r in reqs]
-        results = propagate(flat) if flat else []
+        results = propagate(flat)  # also for an empty round: the caller's accounting sees every round
         slices, o = [], 0
         for reqs in per_lane:
             slices.append(results[o: o + len(reqs)])
             o += len(reqs)
-        if not self.procs:
-            return [self.local[k].after_propagate(slices[k]) for k in range(n)]
-        by_worker = {}
-        for k in range(n):
-            by_worker.setdefault(self.owner[k], {})[k] = slices[k]
-        for w, payload in by_worker.items():
-            self.procs[w][1].send(("post", payload))
-        got = self._gather(by_worker)
-        return [got[k] for k in range(n)]
+        return slices
 
-    def _gather(self, workers) -> dict:
-        """Replies of the given workers, serving their device calls (``device_call``) while they work."""
+    def _send(self, op: str, tag: int, lanes, payloads) -> None:
+        """Hand ``payloads[i]`` to lane ``lanes[i]``: a message per helper process, or -- lanes in this process -- run it."""
+        if not self.procs:
+            out = []
+            for lane, payload in zip(lanes, payloads):
+                if op == "pre":
+                    self.local[lane].configure(payload)
+                    out.append(self.local[lane].before_propagate())
+                else:
+                    out.append(self.local[lane].after_propagate(payload))
+            self._mail[(op, tag)] = dict(zip(lanes, out))
+            return
+        by_worker: dict = {}
+        for lane, payload in zip(lanes, payloads):
+            by_worker.setdefault(self.owner[lane], {})[lane] = payload
+        for w, payload in by_worker.items():
+            self.procs[w][1].send((op, tag, payload))
+
+    def _await(self, op: str, tag: int, lanes) -> list:
+        """Replies for ``lanes`` to the (op, tag) message, serving the helpers' device calls (``device_call``) and stashing
+        replies to other messages while waiting."""
         from multiprocessing.connection import wait
 
         from . import dropin
 
-        waiting = {self.procs[w][1]: w for w in workers}
-        got: dict = {}
-        failure = None
-        while waiting:
-            for conn in wait(list(waiting)):
+        box = self._mail.setdefault((op, tag), {})
+        conns = {conn: w for w, (_, conn) in enumerate(self.procs)}
+        while any(lane not in box for lane in lanes):
+            if not conns:
+                raise RuntimeError("lane workers are gone")
+            for conn in wait(list(conns)):
                 try:
                     status, reply = conn.recv()
                 except EOFError:
-                    failure = failure or f"lane worker {waiting.pop(conn)} died"
-                    continue
+                    raise RuntimeError(f"lane worker {conns.pop(conn)} died") from None
                 if status == "rpc":
                     name, args = reply
                     try:
                         conn.send(("rpc_ok", dropin.DEVICE_CALLS[name](*args)))
                     except Exception as e:
                         conn.send(("rpc_error", f"{type(e).__name__}: {e}"))
-                    continue
-                w = waiting.pop(conn)
-                if status == "ok":
-                    got.update(reply)
+                elif status == "ok":
+                    rop, rtag, payload = reply
+                    self._mail.setdefault((rop, rtag), {}).update(payload)
                 else:
-                    failure = failure or f"lane worker {w} failed: {reply}"
-        if failure:
-            raise RuntimeError(failure)
-        return got
+                    raise RuntimeError(f"lane worker {conns[conn]} failed in {reply[0]}: {reply[2]}")
+        return [box.pop(lane) for lane in lanes]
 
     def close(self) -> None:
         for p, conn in self.procs:
             try:
-                conn.send(("stop", None))
+                conn.send(("stop", 0, None))
             except (BrokenPipeError, OSError):
                 pass
         for p, conn in self.procs:
@@ -494,6 +536,7 @@ def batched_actor_run(self) -> None:
     scenario = self._investigated_object
 
     def propagate(requests):
+        stats["rounds"] += 1
         stats["links"] += len(requests)
         stats["max_links_per_round"] = max(stats["max_links_per_round"], len(requests))
         return propagate_requests(requests)
@@ -502,28 +545,28 @@ def batched_actor_run(self) -> None:
                     config.workers, base_seed=scenario.seed if scenario.seed is not None else 0)
 
     try:
-        exhausted = False
-        backlog: list = []
-        while backlog or not exhausted:
-            while not exhausted and len(backlog) < lanes.num_lanes:  # the queue hands out one section per active grid point per call
+        def sections():  # the queue hands out one section per active grid point per call, until the campaign is served
+            while True:
                 batch = get(queue.next_batch.remote())
                 if len(batch) < 1:
-                    exhausted = True
-                else:
-                    backlog.extend(tuple(s) for s in batch)
-            group, backlog = backlog[: lanes.num_lanes], backlog[lanes.num_lanes:]
-            if not group:
-                break
-            try:
-                artifacts = lanes.run_round(group, propagate)  # (the warm-up drop of LaneSet is not counted in stats)
-            except Exception as e:
-                if self.catch_exceptions:
-                    print(e)
-                    continue
+                    return
+                for s_ in batch:
+                    yield tuple(s_)
+
+        done: list = []
+        try:
+            for section, artifacts in lanes.run_stream(sections(), propagate):
+                done.append(MonteCarloSample(section, 0, artifacts))
+                stats["drops"] += 1
+                if len(done) >= lanes.num_lanes:
+                    results.append(put(done))
+                    done = []
+        except Exception as e:
+            if not self.catch_exceptions:
                 raise UnmatchableException(f"Actor #{self.index} encountered an error during run: {e}") from e
-            stats["rounds"] += 1
-            stats["drops"] += len(group)
-            results.append(put([MonteCarloSample(s, 0, a) for s, a in zip(group, artifacts)]))
+            print(e)
+        if done:
+            results.append(put(done))
     finally:
         lanes.close()
 

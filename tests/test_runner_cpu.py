@@ -79,7 +79,8 @@ def test_lanes_reproduce_the_serial_reference_schedule(workers):
     rounds = [[(0,), (1,), (2,)], [(1,), (1,), (0,)], [(2,), (0,)]]
     lanes = LaneSet(scenario, grid, evaluators, 3, workers, base_seed=99, first_lane_is_original=False)
     try:
-        got = [lanes.run_round(sections, lambda r: pytest.fail("no device requests expected")) for sections in rounds]
+        got = [lanes.run_round(sections, lambda r: pytest.fail("no device requests expected") if r else [])
+               for sections in rounds]
     finally:
         lanes.close()
     for k in range(3):
@@ -190,3 +191,35 @@ def test_device_calls_from_helper_processes_are_served_by_the_gpu_owner():
     for k in range(3):
         want = _serial_reference(scenario, grid, evaluators, k, 3, [r[k] for r in rounds])
         assert [[float(a.to_scalar()) for a in g[k]] for g in got] == want
+
+
+def test_pipelined_stream_over_helper_processes():
+    """``run_stream``: two lane groups alternate so that helpers always have a group's stages to run; every section is
+    served exactly once and every lane's drops equal the serial reference schedule of that lane."""
+    from hermespy_b200.runner import LaneSet
+
+    simulation, grid, evaluators = _simulation()
+    scenario = simulation.scenario
+    todo = [(i % 3,) for i in range(13)]
+    lanes = LaneSet(scenario, grid, evaluators, 4, 2, base_seed=21, first_lane_is_original=False)
+    calls = []
+    try:
+        got = list(lanes.run_stream(iter(todo), lambda r: calls.append(len(r)) or [], groups=2))
+    finally:
+        lanes.close()
+    assert sorted(s for s, _ in got) == sorted(todo) and len(calls) == 7  # 13 sections in groups of 2
+    # the deterministic hand-out: groups take turns, two sections at a time
+    per_lane = {k: [] for k in range(4)}
+    for turn, o in enumerate(range(0, 13, 2)):
+        g = turn % 2
+        for i, sec in enumerate(todo[o: o + 2]):
+            per_lane[2 * g + i].append(sec)
+    have = {k: [] for k in range(4)}
+    order = {k: iter(v) for k, v in per_lane.items()}
+    by_section = {}
+    for sec, art in got:
+        by_section.setdefault(sec, []).append([float(a.to_scalar()) for a in art])
+    want_all = []
+    for k in range(4):
+        want_all.extend(zip(per_lane[k], _serial_reference(scenario, grid, evaluators, k, 21, per_lane[k])))
+    assert sorted((s, tuple(a)) for s, a in want_all) == sorted((s, tuple(a)) for s, v in by_section.items() for a in v)
