@@ -405,6 +405,8 @@ class Workload:
         """(accounting kind, kernel name, bound) of the step's dominant kernel."""
         if self.cfg["kind"] == "cdl":
             return "cdl_propagate", ("cdl_poly_kernel" if info.get("mode") == "poly" else "cdl_direct_f64_kernel"), "fp32"
+        if info.get("variant") == "fused":
+            return "spatial_gemm", "fused_gemm_tdl_kernel", "hbm"
         if prof["tdl_poly"]["launches"]:
             if prof["spatial_gemm"]["launches"] and prof["spatial_gemm"]["ms"] > prof["tdl_poly"]["ms"]:
                 return "spatial_gemm", "spatial_gemm_3xtf32_kernel", "hbm"

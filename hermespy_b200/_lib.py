@@ -29,6 +29,7 @@ HB_SOS_POLY_TMA = 5
 HB_VARIANT_GATHER = 0
 HB_VARIANT_WINDOW = 1
 HB_VARIANT_TMA = 2
+HB_VARIANT_FUSED = 3
 
 HB_MAX_TAPS = 256
 HB_CDL_MAX_TERMS = 1024

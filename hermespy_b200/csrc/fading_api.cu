@@ -7,6 +7,7 @@
 #include <mutex>
 #include <vector>
 
+#include "fading_fused.cuh"
 #include "fading_tma.cuh"
 
 namespace hb {
@@ -72,6 +73,7 @@ static int pick_ntx_template(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 
 struct Plan {
   int mode, tile, P, ntiles, Dpad, ntx_tpl, taps_per_chunk;
   int large_array;  // TMA variant only: z = tap delay lines per transmit antenna, then y = S z on the tensor cores
+  int fused;        // large arrays up to 64 x 64: u = S x on the tensor cores with the delay lines on its accumulator (ONE kernel)
   int variant, poly_tile, npoly, threads, large_halo, lin;  // POLY: kernel variant, Taylor window, windows per link, CTA size
   size_t smem;
   double bound;
@@ -222,6 +224,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
   bool poly = !f64 && p->sos_mode != HB_SOS_DIRECT;
   pl->variant = HB_VARIANT_GATHER;
   pl->large_array = 0;
+  pl->fused = 0;
   pl->poly_tile = 0;
   pl->npoly = 0;
   pl->threads = kThreads;
@@ -283,7 +286,20 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
       pl->smem = poly_smem(pl->ntx_tpl, pl->tile, pl->Dpad, dt.num_groups, pl->P, p->num_rx);
       pl->taps_per_chunk = 0;
       const double bound0 = pl->bound;
-      if (tma_shape && pl->poly_tile % kTmaTile == 0) {
+      // 16..64 antennas per side, delays within the on-chip history: spatial GEMM first, delay lines on its accumulator
+      // (fading_fused.cuh).  HB_SOS_POLY_TMA keeps the two-kernel z-mode path for A/B measurements.
+      const int dmax_f = dt.group_delay[dt.num_groups - 1];
+      if (!p->io_complex128 && p->num_tx >= 16 && p->num_rx >= 16 && p->num_tx <= kGemmMaxAnt && p->num_rx <= kGemmMaxAnt &&
+          dmax_f <= kFusedMaxDelay && dt.num_groups <= kFusedMaxGroups && pl->P <= 4 && pl->poly_tile % kGemmTileSamples == 0 &&
+          p->sos_mode != HB_SOS_POLY_TMA && p->sos_mode != HB_SOS_POLY_GATHER && p->sos_mode != HB_SOS_POLY_WINDOW) {
+        pl->fused = 1;
+        pl->variant = HB_VARIANT_FUSED;
+        pl->tile = kGemmTileSamples;
+        pl->threads = kGemmThreads;
+        pl->smem = kFusedSmemBytes;
+        pl->ntx_tpl = kGemmMaxAnt;
+        pl->npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
+      } else if (tma_shape && pl->poly_tile % kTmaTile == 0) {
         const int tpl0 = pl->ntx_tpl;
         pl->ntx_tpl = tpl_tma;
         plan_tma(p, dt, pl);
@@ -329,7 +345,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
                            ((size_t)(pl->tile + pl->Dpad) + p->num_rx);
     pl->smem -= per_ant * (old - pl->ntx_tpl);
   }
-  if (pl->variant != HB_VARIANT_TMA && pl->smem > kSmemHardLimit) {
+  if (pl->variant != HB_VARIANT_TMA && pl->variant != HB_VARIANT_FUSED && pl->smem > kSmemHardLimit) {
     set_error("delay spread of %d samples needs %zu bytes of shared memory per CTA (limit %zu)", p->max_delay,
               pl->smem, kSmemHardLimit);
     return HB_ERR_UNSUPPORTED;
@@ -347,8 +363,9 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
   info->poly_order = pl.P;
   info->num_groups = dt.num_groups;
   info->num_tiles = pl.ntiles;
-  info->launches = (pl.mode == HB_SOS_POLY ? 1 : 0) + (pl.large_array ? 1 : chunks) +
-                   (pl.large_array ? ((p->num_rx + 63) / 64) * ((p->num_tx + 63) / 64) : 0);
+  info->launches = pl.fused ? 2
+                            : (pl.mode == HB_SOS_POLY ? 1 : 0) + (pl.large_array ? 1 : chunks) +
+                                  (pl.large_array ? ((p->num_rx + 63) / 64) * ((p->num_tx + 63) / 64) : 0);
   info->error_bound = pl.bound;
   info->variant = pl.mode == HB_SOS_POLY ? pl.variant : 0;
   info->poly_tile = pl.mode == HB_SOS_POLY ? pl.poly_tile : pl.tile;
@@ -357,7 +374,8 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
 template <int P>
 static int launch_coef(const FadingArgs& a, const DelayTable& dt, cudaStream_t st) {
   ProfileScope prof(KIND_SOS_COEF, st);
-  sos_poly_coef_kernel<P><<<(unsigned)((size_t)a.ntiles * a.B), 128, 0, st>>>(a, dt);
+  const size_t items = (size_t)a.ntiles * a.B * dt.num_groups;  // one warp per (link, window, delay group)
+  sos_poly_coef_kernel<P><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(a, dt);
   HB_CUDA(cudaGetLastError());
   return HB_OK;
 }
@@ -478,7 +496,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
 #ifdef HB_ATTRIBUTION
   if (const char* ev = getenv("HB_DBG")) a.dbg = atoi(ev);
 #endif
-  if ((size_t)a.ntiles * a.B > 0x7fffffffull) {
+  if ((size_t)a.ntiles * a.B * std::max(1, dt.num_groups) > 0x7fffffffull * 4ull || (size_t)a.ntiles * a.B > 0x7fffffffull) {
     set_error("grid of %zu CTAs exceeds the launch limit; split the batch", (size_t)a.ntiles * a.B);
     return HB_ERR_UNSUPPORTED;
   }
@@ -507,6 +525,27 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
       cudaFreeAsync(coef, st);
       return e;
     }
+  }
+  if (pl.fused) {
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.S = a.spatial;
+    fa.x = reinterpret_cast<const float2*>(x);
+    fa.y = reinterpret_cast<float2*>(y);
+    fa.coef = coef;
+    fa.B = a.B;
+    fa.T = a.T;
+    fa.D = a.D;
+    fa.ntx = a.ntx;
+    fa.nrx = a.nrx;
+    fa.poly_tile = pl.poly_tile;
+    fa.npoly = pl.npoly;
+    fa.coef_stride = a.coef_stride;
+    fa.num_groups = dt.num_groups;
+    for (int g = 0; g < dt.num_groups; ++g) fa.group_delay[g] = dt.group_delay[g];
+    const int rcf = launch_fused_gemm_tdl(pl.P, fa, st);
+    cudaFreeAsync(coef, st);
+    return rcf;
   }
   int rc = HB_OK;
   CUtensorMap xmap;

@@ -49,18 +49,24 @@ struct FadingArgs {
 template <int P>
 __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
                                                             const __grid_constant__ DelayTable dt) {
-  const int b = blockIdx.x / a.ntiles, q = blockIdx.x - b * a.ntiles;
+  // Work item = (link, Taylor window, delay group), one warp each, four consecutive items per CTA: channels whose taps
+  // all share one delay (C1: 23 taps, G = 1) keep every warp busy instead of one in four.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = a.K, G = dt.num_groups;
+  const long long item = (long long)blockIdx.x * 4 + warp;
+  if (item >= (long long)a.B * a.ntiles * G) return;
+  const long long bq = item / G;
+  const int g = (int)(item - bq * G);
+  const int b = (int)(bq / a.ntiles), q = (int)(bq - (long long)b * a.ntiles);
   const double centre = (double)q * a.tile + 0.5 * a.tile;
   const double* om_b = a.omega + (size_t)b * a.L * K;
   const double* ph_b = a.phi + (size_t)b * a.L * K;
   const double* am_b = a.amp + (size_t)b * a.L * 2;
-  if (blockIdx.x == 0 && a.tile_counters != nullptr)
-    for (int i = threadIdx.x; i < a.num_counters; i += blockDim.x) a.tile_counters[i] = 0u;
-  if (q == 0 && a.spatial32 != nullptr && a.s32_tpl > 0) {  // FP32 spatial matrix, chunked, for the bulk-copy staged kernel
+  if (item == 0 && a.tile_counters != nullptr)
+    for (int i = lane; i < a.num_counters; i += 32) a.tile_counters[i] = 0u;
+  if (q == 0 && g == 0 && a.spatial32 != nullptr && a.s32_tpl > 0) {  // FP32 spatial matrix, chunked, for the bulk-copy staged kernel
     const int tpl = a.s32_tpl, nch = (a.ntx + tpl - 1) / tpl, per = a.nrx * tpl;
-    for (int i = threadIdx.x; i < nch * per; i += blockDim.x) {
+    for (int i = lane; i < nch * per; i += 32) {
       const int c = i / per, r = i - c * per, irx = r / tpl, j = c * tpl + (r - irx * tpl);
       float2 v = make_float2(0.f, 0.f);
       if (j < a.ntx) v = to_c32(a.spatial[((size_t)b * a.nrx + irx) * a.ntx + j]);
@@ -68,36 +74,35 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
     }
   }
   constexpr int NV = 2 * P <= 2 ? 2 : (2 * P <= 4 ? 4 : (2 * P <= 8 ? 8 : 16));  // values to reduce, padded to 2^k
-  for (int g = warp; g < G; g += 4) {
+  {
     const int l0 = dt.group_start[g], l1 = dt.group_start[g + 1];
     const double shift = centre - (double)dt.group_delay[g];
     float v[NV];  // v[2p] = Re, v[2p+1] = Im of moment p
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = 0.f;
-    for (int l = l0; l < l1; ++l) {
-      const float a_los = (float)am_b[2 * l], a_nlos = (float)am_b[2 * l + 1];
-      for (int k = lane; k < K; k += 32) {  // fixed (tap, sinusoid) -> lane assignment: deterministic sums
-        const int idx = l * K + k;
-        const double om = om_b[idx];
-        const double th = fma(om, shift, ph_b[idx]);
-        double t = th * kInvTwoPi;
-        t -= rint(t);
-        float s, c;
-        sincosf((float)(t * kTwoPi), &s, &c);
-        const float am = k != 0 ? a_nlos : a_los;
-        float tr = am * c, ti = am * s;
-        const float u = (float)(om * (double)a.tile);
-        v[0] += tr;
-        v[1] += ti;
+    // the (tap, sinusoid) pairs of the group, flattened over the lanes (K = 21 alone would idle a third of them); the
+    // pair -> lane assignment is fixed: deterministic sums
+    for (int idx = l0 * K + lane; idx < l1 * K; idx += 32) {
+      const int l = idx / K, k = idx - l * K;
+      const double om = om_b[idx];
+      const double th = fma(om, shift, ph_b[idx]);
+      double t = th * kInvTwoPi;
+      t -= rint(t);
+      float s, c;
+      sincosf((float)(t * kTwoPi), &s, &c);
+      const float am = (float)am_b[2 * l + (k != 0 ? 1 : 0)];
+      float tr = am * c, ti = am * s;
+      const float u = (float)(om * (double)a.tile);
+      v[0] += tr;
+      v[1] += ti;
 #pragma unroll
-        for (int p = 1; p < P; ++p) {
-          const float f = u * (1.0f / (float)p);
-          const float nr = -ti * f, ni = tr * f;  // times (j u / p)
-          tr = nr;
-          ti = ni;
-          v[2 * p] += tr;
-          v[2 * p + 1] += ti;
-        }
+      for (int p = 1; p < P; ++p) {
+        const float f = u * (1.0f / (float)p);
+        const float nr = -ti * f, ni = tr * f;  // times (j u / p)
+        tr = nr;
+        ti = ni;
+        v[2 * p] += tr;
+        v[2 * p + 1] += ti;
       }
     }
     // Transposing butterfly: at every step a lane keeps one half of its values and sends the other half, so the NV

@@ -1,9 +1,46 @@
 // C-ABI entry of the tensor-core spatial GEMM (K4 for large arrays).
 #include <algorithm>
 
-#include "spatial_gemm.cuh"
+#include "fading_fused.cuh"
 
 namespace hb {
+
+template <int P>
+static int launch_fused_p(const FusedArgs& a, unsigned grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    HB_CUDA(cudaFuncSetAttribute(fused_gemm_tdl_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes));
+    attr_set = true;
+  }
+  ProfileScope prof(KIND_SPATIAL_GEMM, st);
+  fused_gemm_tdl_kernel<P><<<grid, kGemmThreads, kFusedSmemBytes, st>>>(a);
+  HB_CUDA(cudaGetLastError());
+  return HB_OK;
+}
+
+// Fused spatial GEMM + tap delay lines (fading_fused.cuh).  `a` comes with everything but the work split filled in.
+int launch_fused_gemm_tdl(int P, const FusedArgs& args, cudaStream_t st) {
+  FusedArgs a = args;
+  if (a.B == 0 || a.T + a.D == 0 || a.nrx == 0) return HB_OK;
+  const int sms = persistent_sm_count();
+  a.ntiles = (a.T + a.D + kGemmTileSamples - 1) / kGemmTileSamples;
+  // work items: enough per SM to balance the tail, long enough to amortize the conversion of S and the two history tiles
+  const long long want_items = 4ll * sms;
+  int seg = (int)std::max<long long>(32, ((long long)a.ntiles * a.B + want_items - 1) / want_items);
+  seg = std::min(seg, a.ntiles);
+  a.seg_tiles = seg;
+  a.nseg = (a.ntiles + seg - 1) / seg;
+  const long long items = (long long)a.B * a.nseg;
+  const unsigned grid = (unsigned)std::min<long long>(items, sms);
+  switch (P) {
+    case 1: return launch_fused_p<1>(a, grid, st);
+    case 2: return launch_fused_p<2>(a, grid, st);
+    case 3: return launch_fused_p<3>(a, grid, st);
+    case 4: return launch_fused_p<4>(a, grid, st);
+  }
+  set_error("fused large-array kernel: polynomial order %d outside the compiled set", P);
+  return HB_ERR_UNSUPPORTED;
+}
 
 int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int nrx, int ntx, int T, cudaStream_t st) {
   if (B == 0 || T == 0 || nrx == 0) return HB_OK;

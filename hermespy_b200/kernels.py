@@ -219,7 +219,7 @@ def _problem(
 def _info_dict(info: FadingPlanInfo) -> dict:
     d = info.as_dict()
     d["mode"] = _SOS_NAME.get(d["mode"], d["mode"])
-    d["variant"] = ("gather", "window", "tma")[d["variant"]] if d["mode"] == "poly" else None
+    d["variant"] = ("gather", "window", "tma", "fused")[d["variant"]] if d["mode"] == "poly" else None
     return d
 
 

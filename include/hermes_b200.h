@@ -77,7 +77,9 @@ typedef enum hb_sos_mode {
 typedef enum hb_poly_variant {
   HB_VARIANT_GATHER = 0, /* tdl_poly_kernel: one shared-memory read per (delay group, antenna, output)  */
   HB_VARIANT_WINDOW = 1, /* tdl_window_kernel: register sliding window along the delay axis            */
-  HB_VARIANT_TMA = 2     /* tdl_tma_kernel: the same walk, persistent CTAs fed by TMA (swizzled time-pair loads) */
+  HB_VARIANT_TMA = 2,    /* tdl_tma_kernel: the same walk, persistent CTAs fed by TMA (swizzled time-pair loads) */
+  HB_VARIANT_FUSED = 3   /* fused_gemm_tdl_kernel (16..64 antennas per side): spatial GEMM on tcgen05, delay lines on its
+                            accumulator through a shared-memory history ring -- the intermediate never reaches HBM */
 } hb_poly_variant;
 
 /* Launch-uniform description of one batched fading propagation. */

@@ -113,19 +113,41 @@ def test_tma_variant(ntx, nrx, T, B, max_delay_s, doppler):
 
 @pytest.mark.parametrize("ntx,nrx,T,B", [(16, 16, 2048, 2), (64, 64, 4096, 2), (24, 40, 2048, 1), (33, 17, 3072, 1), (70, 66, 2048, 1)])
 def test_large_array_tensor_core_path(ntx, nrx, T, B):
-    """Config C4 shape and friends: tap delay lines per transmit antenna (z mode of the TMA kernel, chunks of 4), then
-    the spatial product on the tcgen05 tensor cores in 3xTF32 -- one fused C-ABI call, same tolerance."""
-    err, info = _run_case(B=B, L=12, N=20, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=100.0, max_delay_s=1.5e-6,
-                          precision="f32", sos_mode="auto", io=np.complex64, seed=ntx, rice=np.r_[3.0, np.zeros(11)], large=True)
-    assert info["variant"] == "tma", info
+    """Config C4 shape and friends.  Up to 64 x 64 antennas: ONE kernel after K1 -- the spatial GEMM on the tcgen05 tensor
+    cores (3xTF32) with the tap delay lines run on its accumulator (fused_gemm_tdl_kernel).  Larger arrays, and
+    ``sos_mode="poly_tma"``: tap delay lines per transmit antenna (z mode of the TMA kernel), then the GEMM blocks."""
+    kw = dict(B=B, L=12, N=20, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=100.0, max_delay_s=1.5e-6, precision="f32",
+              io=np.complex64, seed=ntx, rice=np.r_[3.0, np.zeros(11)], large=True)
+    err, info = _run_case(sos_mode="auto", **kw)
     gemms = ((nrx + 63) // 64) * ((ntx + 63) // 64)
-    assert info["launches"] == 2 + gemms, info  # K1, one z-mode launch over all antenna chunks, GEMM blocks
+    if ntx <= 64 and nrx <= 64:
+        assert info["variant"] == "fused" and info["launches"] == 2, info
+    else:
+        assert info["variant"] == "tma" and info["launches"] == 2 + gemms, info
     assert err < F32_TOL, (err, info)
-    # the same problem through the chunked fused kernels (no tensor cores)
-    err2, info2 = _run_case(B=B, L=12, N=20, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=100.0, max_delay_s=1.5e-6,
-                            precision="f32", sos_mode="poly_window", io=np.complex64, seed=ntx, rice=np.r_[3.0, np.zeros(11)],
-                            large=True)
+    # the two-kernel tensor-core path (z through HBM)
+    err1, info1 = _run_case(sos_mode="poly_tma", **kw)
+    assert info1["variant"] == "tma" and info1["launches"] == 2 + gemms, info1  # K1, one z-mode launch, GEMM blocks
+    assert err1 < F32_TOL, (err1, info1)
+    # the same problem through the chunked kernels (no tensor cores)
+    err2, info2 = _run_case(sos_mode="poly_window", **kw)
     assert info2["variant"] in ("window", "gather") and err2 < F32_TOL
+
+
+@pytest.mark.parametrize("ntx,nrx,T,B,L,delay_s,doppler", [
+    (64, 64, 16384, 3, 23, 3.7e-6, 100.0),   # C4 shape: D = 114, 258 tiles, three links
+    (64, 64, 1000, 1, 4, 4.1e-6, 0.0),       # static channel (P = 1), delay 126 of the 128-sample history, T % 64 != 0
+    (32, 48, 70000, 1, 9, 1e-6, 3e3),        # one long link: several segments with history tiles, faster Doppler
+    (17, 64, 4096 + 37, 5, 6, 2e-6, 800.0),  # odd sizes, K and N padding
+    (64, 16, 64, 2, 3, 0.0, 50.0),           # one tile, all taps at delay 0
+])
+def test_fused_gemm_delay_line_kernel(ntx, nrx, T, B, L, delay_s, doppler):
+    """fused_gemm_tdl_kernel against the oracle: segment starts (history tiles), ring wrap-around, the frame tail where u
+    is zero, padded antenna counts, every polynomial order the planner picks."""
+    err, info = _run_case(B=B, L=L, N=12, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=doppler, max_delay_s=delay_s,
+                          precision="f32", sos_mode="auto", io=np.complex64, seed=7 * ntx + nrx, large=True)
+    assert info["variant"] == "fused" and info["launches"] == 2, info
+    assert err < F32_TOL, (err, info)
 
 
 def test_tma_matches_window_kernel_bitwise_model():
