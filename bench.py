@@ -349,8 +349,9 @@ class Workload:
         self.x = torch.view_as_complex(torch.randn((self.B, self.ntx, self.T, 2), device=dev, generator=gen, dtype=rdtype)
                                        * (0.5 ** 0.5))
         t0 = time.perf_counter()
+        self.device_sampling_s = None
         self._sample_links(42 + rank * 12345678)  # rank-dependent seed as simulation.py:220-223
-        self.host_sampling_s = time.perf_counter() - t0
+        self.host_sampling_s = time.perf_counter() - t0 - (self.device_sampling_s or 0.0)
         self.y = torch.empty((self.B, self.nrx, self.T + self.D), dtype=self.cdtype, device=dev)
         self.Be = max(1, min(self.B, e2e_links))
 
@@ -362,9 +363,16 @@ class Workload:
         cfg = self.cfg
         ch = make_channel(cfg, MC, seed)
         if cfg["kind"] == "fading":
-            from hermespy_b200.batch import sample_fading_links
+            from hermespy_b200.batch import sample_fading_links, sample_fading_links_device
             from hermespy_b200.kernels import FadingBatch
 
+            # the timed batch is realized by the DEVICE sampler (hb_fading_sample + hb_kron_mix: host draws the normals
+            # only); the host sampler below supplies the parameter block of the end-to-end leg and of the parity oracle
+            # from an identically seeded channel -- the two agree to a few ulp (tests/test_sampling_gpu.py)
+            t1 = time.perf_counter()
+            fb_dev = None if self.sinc else sample_fading_links_device(make_channel(cfg, MC, seed), self.B, self.ntx, self.nrx,
+                                                                       cfg["fs"], device=self.dev)
+            self.device_sampling_s = time.perf_counter() - t1
             self.blk = sample_fading_links(ch, self.B, self.ntx, self.nrx, cfg["fs"])
             if self.sinc:
                 # fractional delays (extension): every tap at its true delay -> 12 windowed-sinc taps at integer delays;
@@ -372,7 +380,7 @@ class Workload:
                 from hermespy_b200.kernels import sinc_expand
 
                 self.blk.update(sinc_expand(ch.delays, cfg["fs"], self.blk["omega"], self.blk["phi"], self.blk["amp"]))
-            self.fb = FadingBatch.from_numpy(device=self.dev, **self.blk)
+            self.fb = fb_dev if fb_dev is not None else FadingBatch.from_numpy(device=self.dev, **self.blk)
             self.D = self.blk["max_delay"]
             self.channel = ch
         else:
@@ -590,7 +598,7 @@ def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allre
                "timing": "host wall clock around the blocking C-ABI call, max over ranks"}
 
     cpu = cpu_baseline(cfg) if (with_cpu and rank == 0 and world == 1) else None
-    host_sampling_s = wl.host_sampling_s
+    host_sampling_s, device_sampling_s = wl.host_sampling_s, wl.device_sampling_s
     del wl
     torch.cuda.empty_cache()
     if rank != 0:
@@ -605,6 +613,7 @@ def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allre
                 "l2_policy": f"inputs larger than L2 ({alg_bytes / 1e6:.0f} MB in + out per step)" if alg_bytes > 2 * 126e6
                 else f"in + out {alg_bytes / 1e6:.0f} MB per step: L2-resident between steps (the whole job of this config is one step)",
                 "plan": info, "host_sampling_s": round(host_sampling_s, 3),
+                "device_sampling_s": None if device_sampling_s is None else round(device_sampling_s, 4),
                 "stats_allreduce": (f"NCCL, packed [7, 5] float64, every {args.stats_every} steps + once at the end, inside "
                                     "the timed region") if stats_allreduce else "none"},
         "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -688,7 +697,7 @@ def main():
     ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs left to the NCCL all-reduce of the statistics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
-    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "poly_tma", "direct"],
+    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "poly_tma", "poly_fused", "direct"],
                     help="kernel selection (profiling / A-B runs); the default lets the planner choose")
     args = ap.parse_args()
     if args.impl == "reference":

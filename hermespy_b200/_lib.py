@@ -25,6 +25,7 @@ HB_SOS_DIRECT = 2
 HB_SOS_POLY_GATHER = 3
 HB_SOS_POLY_WINDOW = 4
 HB_SOS_POLY_TMA = 5
+HB_SOS_POLY_FUSED = 6
 
 HB_VARIANT_GATHER = 0
 HB_VARIANT_WINDOW = 1
@@ -155,6 +156,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.hb_stats_accumulate.restype = C.c_int
     lib.hb_stats_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
+    lib.hb_fading_sample.restype = C.c_int
+    lib.hb_fading_sample.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
     lib.hb_kron_mix.restype = C.c_int
     lib.hb_kron_mix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p]

@@ -13,7 +13,8 @@
 namespace hb {
 
 // tensor-core spatial product of the large-array path (spatial_gemm.cu)
-int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int nrx, int ntx, int T, cudaStream_t st);
+int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int nrx, int ntx, int T, cudaStream_t st,
+                        int z_pitch = 0);
 
 // ---- problem validation / delay groups -------------------------------------------------------------
 static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
@@ -39,7 +40,7 @@ static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
     set_error("unknown precision %d", p->precision);
     return HB_ERR_INVALID;
   }
-  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_TMA) {
+  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_FUSED) {
     set_error("unknown sos_mode %d", p->sos_mode);
     return HB_ERR_INVALID;
   }
@@ -222,6 +223,10 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
   const int tile_cap = std::max(kThreads, ((Tout + kThreads - 1) / kThreads) * kThreads);
 
   bool poly = !f64 && p->sos_mode != HB_SOS_DIRECT;
+  if (f64 && p->sos_mode == HB_SOS_POLY_FUSED) {
+    set_error("HB_F64 parity mode only supports direct evaluation");
+    return HB_ERR_UNSUPPORTED;
+  }
   pl->variant = HB_VARIANT_GATHER;
   pl->large_array = 0;
   pl->fused = 0;
@@ -286,16 +291,17 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
       pl->smem = poly_smem(pl->ntx_tpl, pl->tile, pl->Dpad, dt.num_groups, pl->P, p->num_rx);
       pl->taps_per_chunk = 0;
       const double bound0 = pl->bound;
-      // 16..64 antennas per side, delays within the on-chip history: spatial GEMM first, delay lines on its accumulator
-      // (fading_fused.cuh).  HB_SOS_POLY_TMA keeps the two-kernel z-mode path for A/B measurements.
+      // HB_SOS_POLY_FUSED, 16..64 antennas per side, delays within the on-chip history: spatial GEMM first, delay lines
+      // on its accumulator, ONE kernel (fading_fused.cuh).  Not what AUTO picks: on B200 the shared-memory pipe (MMA operand
+      // reads + history-ring reads) makes it 8 % slower than the two-kernel path (profiles/r02_c4.md).
       const int dmax_f = dt.group_delay[dt.num_groups - 1];
-      if (!p->io_complex128 && p->num_tx >= 16 && p->num_rx >= 16 && p->num_tx <= kGemmMaxAnt && p->num_rx <= kGemmMaxAnt &&
-          dmax_f <= kFusedMaxDelay && dt.num_groups <= kFusedMaxGroups && pl->P <= 4 && pl->poly_tile % kGemmTileSamples == 0 &&
-          p->sos_mode != HB_SOS_POLY_TMA && p->sos_mode != HB_SOS_POLY_GATHER && p->sos_mode != HB_SOS_POLY_WINDOW) {
+      if (p->sos_mode == HB_SOS_POLY_FUSED && !p->io_complex128 && p->num_tx >= 16 && p->num_rx >= 16 &&
+          p->num_tx <= kGemmMaxAnt && p->num_rx <= kGemmMaxAnt && dmax_f <= kFusedMaxDelay && dt.num_groups <= kFusedMaxGroups &&
+          pl->P <= 4 && pl->poly_tile % kGemmTileSamples == 0) {
         pl->fused = 1;
         pl->variant = HB_VARIANT_FUSED;
         pl->tile = kGemmTileSamples;
-        pl->threads = kGemmThreads;
+        pl->threads = kFusedThreads;
         pl->smem = kFusedSmemBytes;
         pl->ntx_tpl = kGemmMaxAnt;
         pl->npoly = std::max(1, (Tout + pl->poly_tile - 1) / pl->poly_tile);
@@ -553,7 +559,10 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   int tma_grid = 0;
   float2* zbuf = nullptr;
   if (use_tma && pl.large_array) {
-    const cudaError_t ce = cudaMallocAsync((void**)&zbuf, sizeof(float2) * (size_t)a.B * a.ntx * Tout, st);
+    // even row pitch: every z row starts 16-byte aligned, so the kernel stores pairs of samples (Tout itself is odd for
+    // C4: 16 384 + 115)
+    a.ypitch = (Tout + 1) & ~1;
+    const cudaError_t ce = cudaMallocAsync((void**)&zbuf, sizeof(float2) * (size_t)a.B * a.ntx * a.ypitch, st);
     if (ce != cudaSuccess) {
       if (coef) cudaFreeAsync(coef, st);
       return cuda_fail(ce, "cudaMallocAsync(z workspace of the large-array path)");
@@ -581,7 +590,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   }
   if (zbuf) {
     if (rc == HB_OK)
-      rc = launch_spatial_gemm(a.spatial, zbuf, reinterpret_cast<float2*>(y), a.B, a.nrx, a.ntx, Tout, st);
+      rc = launch_spatial_gemm(a.spatial, zbuf, reinterpret_cast<float2*>(y), a.B, a.nrx, a.ntx, Tout, st, a.ypitch);
     cudaFreeAsync(zbuf, st);
   }
   if (coef) cudaFreeAsync(coef, st);

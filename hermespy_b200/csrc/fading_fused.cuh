@@ -25,11 +25,13 @@
 
 namespace hb {
 
+constexpr int kFusedThreads = 512;  // 16 warps at <= 128 registers: the delay line is latency bound, warps hide it
 constexpr int kFusedRingTiles = 3;
 constexpr int kFusedRing = kFusedRingTiles * kGemmTileSamples;  // 192 samples of u history per receive stream
 constexpr int kFusedMaxDelay = kFusedRing - kGemmTileSamples;   // 128
 constexpr int kFusedMaxGroups = 64;
-constexpr size_t kFusedSmemBytes = 4 * (size_t)kGemmOperandBytes + (size_t)kGemmMaxAnt * kFusedRing * 8 + 1024;
+constexpr int kFusedMaxOrder = 4;
+constexpr size_t kFusedSmemBytes = 4 * (size_t)kGemmOperandBytes + (size_t)kGemmMaxAnt * kFusedRing * 8 + 128;
 
 struct FusedArgs {
   const double2* S;   // [B, nrx, ntx] complex128
@@ -45,13 +47,14 @@ struct FusedArgs {
 };
 
 template <int P>
-__global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const __grid_constant__ FusedArgs a) {
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_gemm_tdl_kernel(const __grid_constant__ FusedArgs a) {
   using namespace umma;
   extern __shared__ unsigned char fused_smem_raw[];
   __shared__ uint64_t mma_done;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float2 coef_s[kFusedMaxGroups * kFusedMaxOrder];  // Taylor coefficients of the tile the delay line works on
 
-  const uint32_t smem0 = (smem_addr(fused_smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem0 = (smem_addr(fused_smem_raw) + 127u) & ~127u;  // no swizzle: operand tiles need 16-byte alignment only
   const uint32_t sB_hi = smem0, sB_lo = smem0 + kGemmOperandBytes;
   const uint32_t sA_hi = smem0 + 2 * kGemmOperandBytes, sA_lo = smem0 + 3 * kGemmOperandBytes;
   float2* ring = reinterpret_cast<float2*>(fused_smem_raw + (smem0 - smem_addr(fused_smem_raw)) + 4 * kGemmOperandBytes);
@@ -77,18 +80,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
   const uint32_t tmem = tmem_base_slot;
   const uint32_t idesc = instr_desc_tf32(128, Np);
 
-  // staging task of this thread in pass p: K chunk kc = 4 p + (warp >> 1), sample ms = 32 (warp & 1) + lane
+  // staging task of this thread in pass p: K chunk kc = 8 p + (warp >> 1), sample ms = 32 (warp & 1) + lane
   const int ms = ((warp & 1) << 5) + lane;
   const int kc0 = warp >> 1;
-  constexpr int kMaxPass = kGemmMaxAnt / 4 / 4;
+  constexpr int kChunksPerPass = kFusedThreads / 64;                  // 8
+  constexpr int kMaxPass = kGemmMaxAnt / 4 / kChunksPerPass;          // 2 passes cover 64 antennas
   const uint32_t a_off = (uint32_t)(ms >> 2) * kGemmSbo + (uint32_t)(ms & 3) * 32;  // rows 2 ms, 2 ms + 1
 
-  // accumulator read-out role: TMEM lane quadrant and column half
-  const int quad = warp & 3, chalf = warp >> 2;
+  // accumulator read-out role: TMEM lane quadrant (warp % 4, as the hardware demands) and 32-column group
+  const int quad = warp & 3, cgrp = warp >> 2;
   const int em = (quad << 4) + (lane >> 1);  // sample of this thread's TMEM lane inside the tile
   const int comp = lane & 1;                 // 0: real row, 1: imaginary row
 
-  // delay-line role: output sample dm of the tile, receive streams [16 rq, 16 rq + 16)
+  // delay-line role: output sample dm of the tile, receive streams [8 rq, 8 rq + 8)
+  constexpr int kRxPerThread = kGemmMaxAnt / (kFusedThreads / 64);  // 8
   const int dm = tid & 63, rq = tid >> 6;
   const float inv_poly = 1.0f / (float)a.poly_tile;
 
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
     // ---- B operand: S, converted, split, zero padded; u ring cleared (no MMA in flight, no reader of the ring) -------
     {
       const double2* Sb = a.S + (size_t)b * a.nrx * a.ntx;
-      for (int i = tid; i < (Np >> 1) * Kp; i += kGemmThreads) {
+      for (int i = tid; i < (Np >> 1) * Kp; i += kFusedThreads) {
         const int j = i / Kp, k = i - j * Kp;
         float re = 0.f, im = 0.f;
         if (j < a.nrx && k < a.ntx) {
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sB_lo + o + 16), "f"(l) : "memory");
       }
       float4* r4 = reinterpret_cast<float4*>(ring);
-      for (int i = tid; i < kGemmMaxAnt * kFusedRing / 2; i += kGemmThreads) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < kGemmMaxAnt * kFusedRing / 2; i += kFusedThreads) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
     float2 zr[kMaxPass][4];  // prefetched x elements of the next tile to stage
@@ -134,12 +139,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
 #pragma unroll
         for (int p = 0; p < kMaxPass; ++p)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) zr[p][i] = ldg_stream(xp + (size_t)(16 * p + i) * a.T);
+          for (int i = 0; i < 4; ++i) zr[p][i] = ldg_stream(xp + (size_t)(4 * kChunksPerPass * p + i) * a.T);
         return;
       }
 #pragma unroll
       for (int p = 0; p < kMaxPass; ++p) {
-        const int kc = 4 * p + kc0;
+        const int kc = kChunksPerPass * p + kc0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int k = 4 * kc + i;
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
       const uint32_t hi0 = sA_hi + a_off, lo0 = sA_lo + a_off;
 #pragma unroll
       for (int p = 0; p < kMaxPass; ++p) {
-        const int kc = 4 * p + kc0;
+        const int kc = kChunksPerPass * p + kc0;
         if (kc < kchunks) {
           float hr[4], lr[4], hi_[4], li[4];
 #pragma unroll
@@ -189,21 +194,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
       phase ^= 1u;
       fence_after_sync();
       float* rbase = reinterpret_cast<float*>(ring) + ((t % kFusedRingTiles) * kGemmTileSamples + em) * 2 + comp;
-      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)chalf * 64;
+      if (cgrp * 32 < Np) {  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)cgrp * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (chalf * 64 + h * 32 < Np) {  // warp-uniform
-          uint32_t v[32];
-          tmem_ld32(taddr + h * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const float keep = __uint_as_float(v[2 * jj]);
-            const float recv = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[2 * jj + 1]), 1);
-            const float out = comp ? keep + recv : keep - recv;
-            const int j = chalf * 32 + h * 16 + jj;
-            if (j < a.nrx) rbase[(size_t)j * (kFusedRing * 2)] = out;
-          }
+        for (int jj = 0; jj < 16; ++jj) {
+          const float keep = __uint_as_float(v[2 * jj]);
+          const float recv = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[2 * jj + 1]), 1);
+          const float out = comp ? keep + recv : keep - recv;
+          const int j = cgrp * 16 + jj;
+          if (j < a.nrx) rbase[(size_t)j * (kFusedRing * 2)] = out;
         }
       }
     };
@@ -213,29 +214,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
       if (m >= Tout) return;
       const int qp = (t * kGemmTileSamples) / a.poly_tile;  // a tile never straddles a Taylor window (64 | poly_tile)
       const float r = ((float)(m - qp * a.poly_tile) - 0.5f * (float)a.poly_tile) * inv_poly;
-      const float2* cq = cb + (size_t)qp * a.coef_stride;
-      float2 acc[16];
+      float2 acc[kRxPerThread];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < kRxPerThread; ++j) acc[j] = make_float2(0.f, 0.f);
       const int slot = (t % kFusedRingTiles) * kGemmTileSamples + dm + kFusedRing;  // + ring: keeps the difference positive
-      const float2* rrow = ring + (size_t)(16 * rq) * kFusedRing;
+      const float2* rrow = ring + (size_t)(kRxPerThread * rq) * kFusedRing;
+#pragma unroll 2
       for (int g = 0; g < a.num_groups; ++g) {
-        float2 hv = __ldg(cq + g * P + (P - 1));
+        float2 hv = coef_s[g * P + (P - 1)];
 #pragma unroll
         for (int p = P - 2; p >= 0; --p) {
-          const float2 c = __ldg(cq + g * P + p);
+          const float2 c = coef_s[g * P + p];
           hv.x = fmaf(hv.x, r, c.x);
           hv.y = fmaf(hv.y, r, c.y);
         }
         // samples before the frame read ring slots no tile of this item has written yet: cleared at item start = zeros
         const int idx = (slot - a.group_delay[g]) % kFusedRing;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) cmac<float>(acc[j], rrow[(size_t)j * kFusedRing + idx], hv);
+        for (int j = 0; j < kRxPerThread; ++j) cmac<float>(acc[j], rrow[(size_t)j * kFusedRing + idx], hv);
       }
-      float2* yp = yb + (size_t)(16 * rq) * Tout + m;
+      float2* yp = yb + (size_t)(kRxPerThread * rq) * Tout + m;
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (16 * rq + j < a.nrx) stg_stream(yp + (size_t)j * Tout, acc[j]);
+      for (int j = 0; j < kRxPerThread; ++j)
+        if (kRxPerThread * rq + j < a.nrx) stg_stream(yp + (size_t)j * Tout, acc[j]);
+    };
+    // Taylor coefficients of tile t into shared memory (made visible by the barrier that precedes delay_line(t))
+    auto load_coef = [&](int t) {
+      const int qp = (t * kGemmTileSamples) / a.poly_tile;
+      if (tid < a.num_groups * P) coef_s[tid] = __ldg(cb + (size_t)qp * a.coef_stride + tid);
     };
 
     // ---- pipeline over the tiles of this item ----------------------------------------------------------------
@@ -244,6 +250,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
     for (int t = t_first; t < t_end; ++t) {
       stage_tile();  // A operand of tile t (the MMAs of tile t - 1 were waited for in its drain)
       if (t + 1 < t_end) load_tile(t + 1);
+      if (t - 1 >= t_begin) load_coef(t - 1);  // the previous delay_line finished before the barrier that ended tile t - 1
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
@@ -256,8 +263,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fused_gemm_tdl_kernel(const _
       __syncthreads();  // ring slot t visible; accumulator and A operand free
       fence_after_sync();
     }
-    if (t_end - 1 >= t_begin) delay_line(t_end - 1);
-    __syncthreads();  // ring and B operand are rewritten by the next item
+    if (t_end - 1 >= t_begin) {
+      load_coef(t_end - 1);
+      __syncthreads();
+      delay_line(t_end - 1);
+    }
+    __syncthreads();  // ring, coefficients and B operand are rewritten by the next item
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }

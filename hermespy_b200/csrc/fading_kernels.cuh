@@ -33,6 +33,7 @@ struct FadingArgs {
   int B, ntx, nrx, T, D, L, K;
   int tile, ntiles, Dpad;
   int tx0, ntx_chunk, accumulate;
+  int ypitch;   // z mode: samples between consecutive rows of the z workspace (even, >= T + D); 0 = T + D
   int z_mode;   // large arrays: skip the spatial mix, store the chunk's tap-delay-line outputs z[b, tx0 + j, :] (y has ntx rows)
   int dbg;  // attribution builds only (-DHB_ATTRIBUTION, env HB_DBG: 1 skip staging, 2 skip stores, 4 skip walk)
 };

@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     if (lane == 0) asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(ticket) : "r"(next0) : "memory");
 
     if (active) {
-      const bool vec_ok = ((Tout & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && (m0 + R <= Tout) &&
+      const int pitch = (ZMODE && a.ypitch > 0) ? a.ypitch : Tout;  // rows of the z workspace start 16-byte aligned
+      const bool vec_ok = ((pitch & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) && (m0 + R <= Tout) &&
                           !a.accumulate;
       auto store_row = [&](float2* dst, const u64 (&yv)[R]) {
         if (vec_ok) {
@@ -339,14 +340,14 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       };
       if constexpr (ZMODE) {
         // ---- large arrays: the spatial product runs on the tensor cores (spatial_gemm.cuh); store z itself ----------
-        float2* zb = reinterpret_cast<float2*>(a.y) + ((size_t)b * a.ntx + tx0) * Tout + m0;
+        float2* zb = reinterpret_cast<float2*>(a.y) + ((size_t)b * a.ntx + tx0) * pitch + m0;
 #pragma unroll
         for (int j = 0; j < NTX; ++j) {
           if (tx0 + j < a.ntx) {
             u64 yv[R];
 #pragma unroll
             for (int u = 0; u < R; ++u) yv[u] = acc[u][j];
-            store_row(zb + (size_t)j * Tout, yv);
+            store_row(zb + (size_t)j * pitch, yv);
           }
         }
       } else {

@@ -13,7 +13,7 @@ static int launch_fused_p(const FusedArgs& a, unsigned grid, cudaStream_t st) {
     attr_set = true;
   }
   ProfileScope prof(KIND_SPATIAL_GEMM, st);
-  fused_gemm_tdl_kernel<P><<<grid, kGemmThreads, kFusedSmemBytes, st>>>(a);
+  fused_gemm_tdl_kernel<P><<<grid, kFusedThreads, kFusedSmemBytes, st>>>(a);
   HB_CUDA(cudaGetLastError());
   return HB_OK;
 }
@@ -42,7 +42,8 @@ int launch_fused_gemm_tdl(int P, const FusedArgs& args, cudaStream_t st) {
   return HB_ERR_UNSUPPORTED;
 }
 
-int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int nrx, int ntx, int T, cudaStream_t st) {
+int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int nrx, int ntx, int T, cudaStream_t st,
+                        int z_pitch) {
   if (B == 0 || T == 0 || nrx == 0) return HB_OK;
   static bool attr_set = false;
   if (!attr_set) {
@@ -56,6 +57,7 @@ int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int
   GemmArgs a;
   a.S = S;
   a.z = z;
+  a.ldz = z_pitch > 0 ? z_pitch : T;
   a.y = y;
   a.B = B;
   a.T = T;
@@ -105,5 +107,5 @@ extern "C" int hb_spatial_gemm_3xtf32(const void* spatial, const void* z, void* 
     return HB_ERR_INVALID;
   }
   return launch_spatial_gemm((const double2*)spatial, (const float2*)z, (float2*)y, batch, num_rx, num_tx, num_samples,
-                             (cudaStream_t)stream);
+                             (cudaStream_t)stream, 0);
 }

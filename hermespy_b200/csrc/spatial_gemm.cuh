@@ -35,7 +35,8 @@ constexpr size_t kGemmSmemBytes = 6 * (size_t)kGemmOperandBytes + 1024;  // B hi
 
 struct GemmArgs {
   const double2* S;  // [B, nrx_total, ntx_total] complex128
-  const float2* z;   // [B, ntx_total, T]
+  const float2* z;   // [B, ntx_total, ldz]  (ldz >= T samples per row)
+  int ldz;
   float2* y;         // [B, nrx_total, T]
   int B, T;
   int nrx_total, ntx_total;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
     const int b = item / a.nseg, seg = item - b * a.nseg;
     const int t_begin = seg * a.seg_tiles, t_end = min(a.ntiles, t_begin + a.seg_tiles);
     const int ntile = t_end - t_begin;
-    const float2* zb = a.z + ((size_t)b * a.ntx_total + a.tx0) * a.T;
+    const float2* zb = a.z + ((size_t)b * a.ntx_total + a.tx0) * a.ldz;
     float* yb = reinterpret_cast<float*>(a.y + ((size_t)b * a.nrx_total + a.rx0) * a.T);
 
     // ---- B operand: S block, converted, split, zero padded (no MMA is in flight here) -----------------------------
@@ -199,11 +200,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
     auto load_tile = [&](int t) {
       const int n = t * kGemmTileSamples + ms;
       if (FULL && (t + 1) * kGemmTileSamples <= a.T) {  // CTA-uniform
-        const float2* zp = zb + (size_t)(4 * kc0) * a.T + n;
+        const float2* zp = zb + (size_t)(4 * kc0) * a.ldz + n;
 #pragma unroll
         for (int p = 0; p < kMaxPass; ++p)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) zr[p][i] = ldg_stream(zp + (size_t)(16 * p + i) * a.T);
+          for (int i = 0; i < 4; ++i) zr[p][i] = ldg_stream(zp + (size_t)(16 * p + i) * a.ldz);
         return;
       }
 #pragma unroll
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
         for (int i = 0; i < 4; ++i) {
           const int k = 4 * kc + i;
           float2 v = make_float2(0.f, 0.f);
-          if (kc < kchunks && k < a.ntx && n < a.T) v = ldg_stream(zb + (size_t)k * a.T + n);
+          if (kc < kchunks && k < a.ntx && n < a.T) v = ldg_stream(zb + (size_t)k * a.ldz + n);
           zr[p][i] = v;
         }
       }

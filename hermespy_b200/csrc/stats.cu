@@ -118,11 +118,115 @@ __global__ void __launch_bounds__(256) kron_mix_kernel(const double2* __restrict
   }
 }
 
+// a3 on the device: the standard normals a static realization drew (host numpy generator: draw order is parity) ->
+// kernel parameter block of every link.  MultipathFadingRealization._sample (fading.py:468-515) with
+// ConsistentUniform.sample = norm.cdf (consistent.py:475-485):  u = Phi(g) = erfc(-g / sqrt 2) / 2,
+//   S[i, j] = exp(2j pi u_ant[i, j]),  los_angle = 2 pi u,  nlos_angle = los_phase = nlos_phase = -pi + 2 pi u,
+//   omega[l, 0] = w_los cos(los_angle_l) / fs,  omega[l, k] = w_nlos cos((2 pi k + nlos_angle_lk) / N) / fs  (fading.py:326-339)
+// Variable layout of the normals: antenna (dim x dim) | los angles (L) | nlos angles (L, N) | los phases (L) | nlos phases (L, N)
+// (declaration order, fading.py:742-754).  One thread per output element; trivially parallel, FP64 throughout.
+struct SampleArgs {
+  const double* normals;  // [B, S]
+  const double* amp_tab;  // [L, 2] los / nlos amplitude incl. sqrt(gain * power_l), shared by the batch
+  double* omega;          // [B, L, N + 1]
+  double* phi;            // [B, L, N + 1]
+  double* amp;            // [B, L, 2]
+  double2* spatial;       // [B, nrx, ntx]
+  double w_los, w_nlos;   // Doppler rates per SAMPLE (rad): doppler / fs
+  int B, S, dim, nrx, ntx, L, N, transpose;
+};
+
+__device__ __forceinline__ double std_normal_cdf(double g) { return 0.5 * erfc(-g * 0.70710678118654752440); }
+
+__global__ void __launch_bounds__(256) fading_sample_kernel(const SampleArgs a) {
+  const int K = a.N + 1;
+  const int per_link = a.L * K + a.nrx * a.ntx;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)a.B * per_link) return;
+  const int b = (int)(e / per_link), r = (int)(e - (long long)b * per_link);
+  const double* g = a.normals + (size_t)b * a.S;
+  const int o_los_ang = a.dim * a.dim, o_nlos_ang = o_los_ang + a.L, o_los_ph = o_nlos_ang + a.L * a.N,
+            o_nlos_ph = o_los_ph + a.L;
+  if (r < a.L * K) {
+    const int l = r / K, k = r - l * K;
+    double om, ph;
+    if (k == 0) {
+      const double ang = kTwoPi * std_normal_cdf(g[o_los_ang + l]);
+      om = a.w_los * cos(ang);
+      ph = -M_PI + kTwoPi * std_normal_cdf(g[o_los_ph + l]);
+      a.amp[((size_t)b * a.L + l) * 2 + 0] = a.amp_tab[2 * l];
+      a.amp[((size_t)b * a.L + l) * 2 + 1] = a.amp_tab[2 * l + 1];
+    } else {
+      const double ang = -M_PI + kTwoPi * std_normal_cdf(g[o_nlos_ang + l * a.N + (k - 1)]);
+      om = a.w_nlos * cos((kTwoPi * (double)k + ang) / (double)a.N);
+      ph = -M_PI + kTwoPi * std_normal_cdf(g[o_nlos_ph + l * a.N + (k - 1)]);
+    }
+    a.omega[(size_t)b * a.L * K + r] = om;
+    a.phi[(size_t)b * a.L * K + r] = ph;
+  } else {
+    const int s = r - a.L * K, i = s / a.ntx, j = s - i * a.ntx;
+    // reciprocal direction: the transposed antenna matrix (fading.py:517-538)
+    const double u = std_normal_cdf(a.transpose ? g[j * a.dim + i] : g[i * a.dim + j]);
+    double sn, cs;
+    sincospi(2.0 * u, &sn, &cs);
+    a.spatial[(size_t)b * a.nrx * a.ntx + s] = make_double2(cs, sn);
+  }
+}
+
 }  // namespace hb
 
 using namespace hb;
 
 extern "C" {
+
+int hb_fading_sample(const double* normals, int32_t batch, int32_t num_scalars, int32_t antenna_dim, int32_t num_rx,
+                     int32_t num_tx, int32_t num_taps, int32_t num_sinusoids, const double* amp_table, double los_rate,
+                     double nlos_rate, int32_t reciprocal, double* omega, double* phi, double* amp, void* spatial,
+                     void* stream) {
+  if (batch < 0 || num_taps < 1 || num_sinusoids < 0 || num_rx < 1 || num_tx < 1 || antenna_dim < 1) {
+    set_error("invalid sampling shape (B=%d L=%d N=%d Nrx=%d Ntx=%d dim=%d)", batch, num_taps, num_sinusoids, num_rx, num_tx,
+              antenna_dim);
+    return HB_ERR_INVALID;
+  }
+  const long long need = (long long)antenna_dim * antenna_dim + 2ll * num_taps + 2ll * num_taps * num_sinusoids;
+  if (num_scalars != need) {
+    set_error("a realization of this channel holds %lld normals, got %d", need, num_scalars);
+    return HB_ERR_INVALID;
+  }
+  if (num_rx > antenna_dim || num_tx > antenna_dim) {
+    set_error("antenna variable is %d x %d, link needs %d x %d", antenna_dim, antenna_dim, num_rx, num_tx);
+    return HB_ERR_INVALID;
+  }
+  if (batch == 0) return HB_OK;
+  if (int e = require_device()) return e;
+  if (!normals || !amp_table || !omega || !phi || !amp || !spatial) {
+    set_error("NULL device pointer in sampling request");
+    return HB_ERR_INVALID;
+  }
+  SampleArgs a;
+  a.normals = normals;
+  a.amp_tab = amp_table;
+  a.omega = omega;
+  a.phi = phi;
+  a.amp = amp;
+  a.spatial = (double2*)spatial;
+  a.w_los = los_rate;
+  a.w_nlos = nlos_rate;
+  a.B = batch;
+  a.S = num_scalars;
+  a.dim = antenna_dim;
+  a.nrx = num_rx;
+  a.ntx = num_tx;
+  a.L = num_taps;
+  a.N = num_sinusoids;
+  a.transpose = reciprocal ? 1 : 0;
+  const long long total = (long long)batch * (num_taps * (num_sinusoids + 1) + num_rx * num_tx);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfileScope prof(KIND_MISC, st);
+  fading_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  HB_CUDA(cudaGetLastError());
+  return HB_OK;
+}
 
 int hb_bit_errors(const uint8_t* tx_bits, const uint8_t* rx_bits, const int32_t* tx_len, const int32_t* rx_len,
                   int32_t num_drops, int32_t num_bits, int64_t* errors, int64_t* bits, double* artifact, void* stream) {

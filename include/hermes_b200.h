@@ -11,6 +11,7 @@
  *                             + MultipathFadingSample.__path_impulse_generator        fading.py:293-343
  *   hb_fading_state        <- MultipathFadingSample.state (SISO tap gains)            fading.py:345-358
  *   hb_kron_mix            <- antenna-correlation mixing  R_rx @ S @ R_tx             fading.py:480-489
+ *   hb_fading_sample       <- MultipathFadingRealization._sample (normals -> parameters)  fading.py:468-515
  *   hb_cdl_*               <- ClusterDelayLineSample.__ray_impulse_generator / _propagate
  *                             hermespy/channel/cdl/cluster_delay_lines.py:409-558
  *   hb_stats_accumulate    <- ScalarEvaluationResult.add_artifact  hermespy/core/pymonte/scalar.py:101-125
@@ -70,8 +71,11 @@ typedef enum hb_sos_mode {
   HB_SOS_DIRECT = 2, /* one sincos per sinusoid per sample (MUFU pipe)             */
   HB_SOS_POLY_GATHER = 3, /* POLY, forcing the per-group gather kernel (sparse / very long delay spreads) */
   HB_SOS_POLY_WINDOW = 4, /* POLY, forcing the cp.async-staged sliding-window kernel where it is eligible  */
-  HB_SOS_POLY_TMA = 5     /* POLY, preferring the persistent TMA-pipelined window kernel (what AUTO/POLY pick
+  HB_SOS_POLY_TMA = 5,    /* POLY, preferring the persistent TMA-pipelined window kernel (what AUTO/POLY pick
                              for complex64 frames with T % 16 == 0, T + D >= 2048 and delays below 128 samples) */
+  HB_SOS_POLY_FUSED = 6   /* POLY, large arrays (16..64 antennas per side): the single-kernel GEMM + delay-line variant
+                             (fading_fused.cuh).  Measured slower than the two-kernel path on B200 (profiles/r02_c4.md),
+                             therefore not what AUTO picks; kept selectable */
 } hb_sos_mode;
 
 typedef enum hb_poly_variant {
@@ -272,6 +276,19 @@ typedef struct hb_receive_input {
 HB_API int hb_receive_combine(const hb_receive_input* inputs, int32_t num_inputs, const double* noise_re,
                               const double* noise_im, const double* noise_scale, void* out, int32_t batch, int32_t num_rx,
                               int32_t num_out_samples, int32_t io_complex128, void* stream);
+
+/* a3 on the device: the standard normals of B static realizations (drawn by the caller's numpy generator -- the draw
+ * order is part of parity) -> the kernel parameter blocks of B links.  Replaces MultipathFadingRealization._sample
+ * (hermespy/channel/fading/fading.py:468-515) with ConsistentUniform.sample = norm.cdf (hermespy/channel/consistent.py:475-485)
+ * for decorrelation distance = inf.  normals: DEVICE f64 [B, num_scalars], num_scalars = dim^2 + 2 L + 2 L N in declaration
+ * order (fading.py:742-754); amp_table: DEVICE f64 [L, 2] = (los_gain_l, nlos_gain_l) sqrt(gain power_l); los_rate / nlos_rate:
+ * Doppler "frequencies" divided by the sampling rate (used as angular rates); reciprocal: transpose the antenna
+ * phases (fading.py:517-538).  Outputs (DEVICE): omega, phi [B, L, N + 1], amp [B, L, 2], spatial complex128 [B, Nrx, Ntx]
+ * (before antenna correlation: follow with hb_kron_mix). */
+HB_API int hb_fading_sample(const double* normals, int32_t batch, int32_t num_scalars, int32_t antenna_dim, int32_t num_rx,
+                            int32_t num_tx, int32_t num_taps, int32_t num_sinusoids, const double* amp_table,
+                            double los_rate, double nlos_rate, int32_t reciprocal, double* omega, double* phi, double* amp,
+                            void* spatial, void* stream);
 
 /* K4 for large arrays (SURVEY 8(b) `hb_spatial_gemm_3xtf32`): y[b] = spatial[b] @ z[b], the `spatial_response @
  * propagated` product of fading.py:395, on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy, FP32
