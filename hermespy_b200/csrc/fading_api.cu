@@ -380,8 +380,10 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
 template <int P>
 static int launch_coef(const FadingArgs& a, const DelayTable& dt, cudaStream_t st) {
   ProfileScope prof(KIND_SOS_COEF, st);
-  const size_t items = (size_t)a.ntiles * a.B * dt.num_groups;  // one warp per (link, window, delay group)
-  sos_poly_coef_kernel<P><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(a, dt);
+  FadingArgs ak = a;
+  ak.coef_flat = dt.num_groups < 4;  // few delay groups: one warp per (link, window, group), see the kernel
+  const size_t blocks = ak.coef_flat ? ((size_t)a.ntiles * a.B * dt.num_groups + 3) / 4 : (size_t)a.ntiles * a.B;
+  sos_poly_coef_kernel<P><<<(unsigned)blocks, 128, 0, st>>>(ak, dt);
   HB_CUDA(cudaGetLastError());
   return HB_OK;
 }

@@ -29,6 +29,7 @@ struct FadingArgs {
                            // s32_tpl transmit antennas (zero padded), written by K1 when not NULL
   unsigned int* tile_counters;  // [num_counters] work counters of the persistent kernels, zeroed by K1 when not NULL
   int num_counters;
+  int coef_flat;  // K1 work split: 1 = one warp per (link, window, group) with flattened (tap, sinusoid) lanes (G < 4)
   int coef_stride, s32_tpl, s32_stride;
   int B, ntx, nrx, T, D, L, K;
   int tile, ntiles, Dpad;
@@ -50,24 +51,40 @@ struct FadingArgs {
 template <int P>
 __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
                                                             const __grid_constant__ DelayTable dt) {
-  // Work item = (link, Taylor window, delay group), one warp each, four consecutive items per CTA: channels whose taps
-  // all share one delay (C1: 23 taps, G = 1) keep every warp busy instead of one in four.
+  // Two work splits (a.coef_flat, chosen by the launcher):
+  //  * G >= 4: CTA = (link, Taylor window), its 4 warps stride over the delay groups -- the per-CTA set-up (pointers,
+  //    FP32 spatial matrix) is paid once per window;
+  //  * G < 4 (C1: 23 taps share ONE delay): warp = (link, window, group), 4 consecutive items per CTA, the (tap, sinusoid)
+  //    pairs of the group flattened over the lanes -- otherwise three warps in four would idle and K = 21 sinusoids would
+  //    leave a third of the remaining lanes empty.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = a.K, G = dt.num_groups;
-  const long long item = (long long)blockIdx.x * 4 + warp;
-  if (item >= (long long)a.B * a.ntiles * G) return;
-  const long long bq = item / G;
-  const int g = (int)(item - bq * G);
-  const int b = (int)(bq / a.ntiles), q = (int)(bq - (long long)b * a.ntiles);
+  int b, q, g_first, g_step;
+  if (a.coef_flat) {
+    const long long item = (long long)blockIdx.x * 4 + warp;
+    if (item >= (long long)a.B * a.ntiles * G) return;
+    const long long bq = item / G;
+    g_first = (int)(item - bq * G);
+    g_step = G;  // one group per warp
+    b = (int)(bq / a.ntiles);
+    q = (int)(bq - (long long)b * a.ntiles);
+  } else {
+    b = blockIdx.x / a.ntiles;
+    q = blockIdx.x - b * a.ntiles;
+    g_first = warp;
+    g_step = 4;
+  }
   const double centre = (double)q * a.tile + 0.5 * a.tile;
   const double* om_b = a.omega + (size_t)b * a.L * K;
   const double* ph_b = a.phi + (size_t)b * a.L * K;
   const double* am_b = a.amp + (size_t)b * a.L * 2;
-  if (item == 0 && a.tile_counters != nullptr)
-    for (int i = lane; i < a.num_counters; i += 32) a.tile_counters[i] = 0u;
-  if (q == 0 && g == 0 && a.spatial32 != nullptr && a.s32_tpl > 0) {  // FP32 spatial matrix, chunked, for the bulk-copy staged kernel
+  if (blockIdx.x == 0 && a.tile_counters != nullptr)
+    for (int i = threadIdx.x; i < a.num_counters; i += blockDim.x) a.tile_counters[i] = 0u;
+  if (q == 0 && a.spatial32 != nullptr && a.s32_tpl > 0 && (!a.coef_flat || g_first == 0)) {
+    // FP32 spatial matrix, chunked, for the bulk-copy staged kernel (flat split: the warp that owns group 0 converts it)
     const int tpl = a.s32_tpl, nch = (a.ntx + tpl - 1) / tpl, per = a.nrx * tpl;
-    for (int i = lane; i < nch * per; i += 32) {
+    const int i0 = a.coef_flat ? lane : (int)threadIdx.x, di = a.coef_flat ? 32 : (int)blockDim.x;
+    for (int i = i0; i < nch * per; i += di) {
       const int c = i / per, r = i - c * per, irx = r / tpl, j = c * tpl + (r - irx * tpl);
       float2 v = make_float2(0.f, 0.f);
       if (j < a.ntx) v = to_c32(a.spatial[((size_t)b * a.nrx + irx) * a.ntx + j]);
@@ -75,16 +92,16 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
     }
   }
   constexpr int NV = 2 * P <= 2 ? 2 : (2 * P <= 4 ? 4 : (2 * P <= 8 ? 8 : 16));  // values to reduce, padded to 2^k
-  {
+  for (int g = g_first; g < G; g += g_step) {
     const int l0 = dt.group_start[g], l1 = dt.group_start[g + 1];
     const double shift = centre - (double)dt.group_delay[g];
     float v[NV];  // v[2p] = Re, v[2p+1] = Im of moment p
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = 0.f;
-    // the (tap, sinusoid) pairs of the group, flattened over the lanes (K = 21 alone would idle a third of them); the
-    // pair -> lane assignment is fixed: deterministic sums
-    for (int idx = l0 * K + lane; idx < l1 * K; idx += 32) {
-      const int l = idx / K, k = idx - l * K;
+    // one (tap, sinusoid) pair: theta reduced in FP64, sincos + moment recurrence in FP32.  Fixed pair -> lane assignment
+    // in both splits: deterministic sums.
+    auto pair = [&](int l, int k) {
+      const int idx = l * K + k;
       const double om = om_b[idx];
       const double th = fma(om, shift, ph_b[idx]);
       double t = th * kInvTwoPi;
@@ -105,6 +122,12 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
         v[2 * p] += tr;
         v[2 * p + 1] += ti;
       }
+    };
+    if (a.coef_flat) {
+      for (int idx = l0 * K + lane; idx < l1 * K; idx += 32) pair(idx / K, idx % K);
+    } else {
+      for (int l = l0; l < l1; ++l)
+        for (int k = lane; k < K; k += 32) pair(l, k);
     }
     // Transposing butterfly: at every step a lane keeps one half of its values and sends the other half, so the NV
     // sums cost NV - 1 + (5 - log2 NV) shuffles instead of 5 NV.  Value i ends up in the lanes whose top log2(NV)

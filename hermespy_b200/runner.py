@@ -26,6 +26,8 @@ from __future__ import annotations
 
 import copy
 import multiprocessing as mp
+import queue
+import threading
 import traceback
 from typing import Any, List, Sequence
 
@@ -304,6 +306,7 @@ class Lane(object):
 # ---- helper processes for the CPU stages -----------------------------------------------------------------------------------
 
 _rpc_conn = None  # inside a lane worker: the pipe to the process that owns the GPU
+_rpc_stash: list = []  # work messages that arrived while a device call was waiting for its answer (pipelined rounds)
 
 
 def device_call(name: str, *args):
@@ -315,10 +318,14 @@ def device_call(name: str, *args):
 
         return dropin.DEVICE_CALLS[name](*args)
     _rpc_conn.send(("rpc", (name, args)))
-    status, reply = _rpc_conn.recv()
-    if status != "rpc_ok":
-        raise RuntimeError(f"device call {name} failed in the GPU process: {reply}")
-    return reply
+    while True:
+        msg = _rpc_conn.recv()
+        if msg[0] in ("rpc_ok", "rpc_error"):
+            break
+        _rpc_stash.append(msg)  # the owner already queued this helper's next stage: keep it for the main loop
+    if msg[0] != "rpc_ok":
+        raise RuntimeError(f"device call {name} failed in the GPU process: {msg[1]}")
+    return msg[1]
 
 
 def _worker_main(conn, lanes: dict) -> None:
@@ -336,7 +343,7 @@ def _worker_main(conn, lanes: dict) -> None:
         pass
     while True:
         try:
-            msg = conn.recv()
+            msg = _rpc_stash.pop(0) if _rpc_stash else conn.recv()
         except EOFError:
             return
         op, tag, payload = msg
@@ -355,6 +362,20 @@ def _worker_main(conn, lanes: dict) -> None:
             conn.send(("error", (op, tag, f"{type(e).__name__}: {e}\n{traceback.format_exc()}")))
 
 
+def _writer_main(conn, outbox) -> None:
+    """Messages to one helper leave through this thread: the GPU owner must keep READING the helpers' replies while a
+    large payload (propagated blocks) is still draining into a pipe whose other end is busy sending its own reply --
+    two blocking sends facing each other would never finish."""
+    while True:
+        msg = outbox.get()
+        if msg is None:
+            return
+        try:
+            conn.send(msg)
+        except (BrokenPipeError, OSError):
+            return
+
+
 class LaneSet(object):
     """B lanes, in this process or spread over ``workers`` forked helper processes."""
 
@@ -371,6 +392,7 @@ class LaneSet(object):
                 lanes[k] = Lane.clone_of(scenario, grid, evaluators, k, base_seed, stage_arguments)
         self.local = lanes
         self.procs: list = []
+        self.outbox: list = []
         self._mail: dict = {}
         workers = min(int(workers), self.num_lanes)
         if workers > 0:
@@ -389,6 +411,9 @@ class LaneSet(object):
                 p.start()
                 child.close()
                 self.procs.append((p, parent))
+                box: queue.SimpleQueue = queue.SimpleQueue()
+                threading.Thread(target=_writer_main, args=(parent, box), daemon=True).start()
+                self.outbox.append(box)
                 for k in mine:
                     self.owner[k] = w
             self.local = {}
@@ -470,7 +495,7 @@ class LaneSet(object):
         for lane, payload in zip(lanes, payloads):
             by_worker.setdefault(self.owner[lane], {})[lane] = payload
         for w, payload in by_worker.items():
-            self.procs[w][1].send((op, tag, payload))
+            self.outbox[w].put((op, tag, payload))
 
     def _await(self, op: str, tag: int, lanes) -> list:
         """Replies for ``lanes`` to the (op, tag) message, serving the helpers' device calls (``device_call``) and stashing
@@ -503,17 +528,15 @@ class LaneSet(object):
         return [box.pop(lane) for lane in lanes]
 
     def close(self) -> None:
-        for p, conn in self.procs:
-            try:
-                conn.send(("stop", 0, None))
-            except (BrokenPipeError, OSError):
-                pass
+        for box in self.outbox:
+            box.put(("stop", 0, None))
+            box.put(None)
         for p, conn in self.procs:
             p.join(timeout=5)
             if p.is_alive():
                 p.terminate()
             conn.close()
-        self.procs = []
+        self.procs, self.outbox = [], []
 
 
 # ---- the actor's run loop (replaces MonteCarloActor.run for SimulationActor while the runner is enabled) -----------------

@@ -277,3 +277,39 @@ def test_dropin_extracts_element_tables_of_non_ideal_arrays(ref):
         dev(SimulatedUniformArray(Cardioid, 0.04, (2, 1, 1)), (0, 0, 10.0)), dev(SimulatedUniformArray(SimulatedIdealAntenna, 0.04, (1, 1, 1)), (40.0, 5.0, 1.5)))
     with pytest.raises(dropin.UnsupportedByKernels):
         dropin.cdl_block_from_reference(s)
+
+
+def test_delay_radar_and_ideal_channels_pass_through_the_dropin_untouched(ref):
+    """SURVEY 8(f)-4 / DESIGN section 7: delay, radar and ideal channels carry no sum-of-sinusoids stage (one static tap: a
+    small matmul and a shift that numpy runs at memory speed) -- the drop-in leaves their sample classes alone.  Pinned
+    here: with the patch applied their ``_propagate`` / ``state`` are still the reference's own functions and their
+    outputs are bit-identical; the batched runner classifies them as not device-served."""
+    import hermespy_b200.dropin as dropin
+    from hermespy.channel import IdealChannel, RandomDelayChannel, SingleTargetRadarChannel, SpatialDelayChannel
+    from hermespy.channel.delay.delay import DelayChannelSample
+    from hermespy.channel.ideal import IdealChannelSample
+    from hermespy.channel.radar.radar import RadarChannelSample
+    from hermespy_b200 import runner
+
+    Signal, device = ref["Signal"], ref["device"]
+    fs = 1e8
+    classes = (DelayChannelSample, RadarChannelSample, IdealChannelSample)
+    before = {c: (c.__dict__.get("_propagate"), c.__dict__.get("state")) for c in classes}
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 200)) + 1j * rng.standard_normal((2, 200))
+    sig = Signal.Create(x, fs, 3.5e9)
+    tx, rx = device(2, fs, (0, 0, 0)), device(2, fs, (30.0, 4.0, 0))
+    channels = [SpatialDelayChannel(seed=1), RandomDelayChannel(3e-8, seed=2), IdealChannel(seed=3),
+                SingleTargetRadarChannel(25.0, 1.0, seed=4)]
+    samples = [ch.realize().sample(tx, rx if not isinstance(ch, SingleTargetRadarChannel) else tx) for ch in channels]
+    want = [np.asarray(s.propagate(sig).view(np.ndarray)) for s in samples]
+    dropin.patch_reference()
+    try:
+        for c in classes:
+            assert (c.__dict__.get("_propagate"), c.__dict__.get("state")) == before[c]  # untouched
+        got = [np.asarray(s.propagate(sig).view(np.ndarray)) for s in samples]
+        assert all(runner._gpu_kind(s) is None for s in samples)
+    finally:
+        dropin.disable()
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.array_equal(a, b)

@@ -223,3 +223,41 @@ def test_pipelined_stream_over_helper_processes():
     for k in range(4):
         want_all.extend(zip(per_lane[k], _serial_reference(scenario, grid, evaluators, k, 21, per_lane[k])))
     assert sorted((s, tuple(a)) for s, a in want_all) == sorted((s, tuple(a)) for s, v in by_section.items() for a in v)
+
+
+def test_large_payloads_do_not_deadlock_the_pipeline():
+    """Requests and results far larger than a pipe buffer, two lane groups in flight: the GPU owner keeps reading replies
+    while its own payloads drain (writer threads), so helper and owner never block on each other's send."""
+    import hermespy_b200.dropin as dropin
+    from hermespy_b200.runner import LaneSet
+    from tests.test_dropin_gpu import _ofdm_2x1_alamouti_tdl_b
+
+    load_reference()
+    scenario, tx, rx, ber = _ofdm_2x1_alamouti_tdl_b(42)  # 2 x 816-sample streams per link: ~26 KB per request, x 2 links x 4 lanes
+    served = {"n": 0}
+
+    def propagate(requests):
+        served["n"] += len(requests)
+        return [np.concatenate([r, r, r, r], axis=1) for r in _oracle_propagate(requests)] if False else _oracle_propagate(requests)
+
+    def fake_state(b, keep, num_samples):
+        n = np.arange(num_samples)
+        K = b["omega"].shape[1]
+        amp = b["amp"][:, [0] + [1] * (K - 1), None]
+        h = (amp * np.exp(1j * (b["omega"][:, :, None] * n + b["phi"][:, :, None]))).sum(1)[keep]
+        gd = np.unique(b["tap_delay"][keep])
+        return np.stack([h[b["tap_delay"][keep] == d].sum(0) for d in gd]), gd
+
+    dropin.patch_reference()
+    real = dropin.DEVICE_CALLS["fading_state"]
+    dropin.DEVICE_CALLS["fading_state"] = fake_state
+    try:
+        lanes = LaneSet(scenario, [], [ber], 8, 2, base_seed=5, first_lane_is_original=False, propagate=_oracle_propagate)
+        try:
+            got = list(lanes.run_stream(iter([()] * 24), propagate, groups=2))
+        finally:
+            lanes.close()
+    finally:
+        dropin.DEVICE_CALLS["fading_state"] = real
+        dropin.disable()
+    assert len(got) == 24 and served["n"] == 48

@@ -142,7 +142,7 @@ int main() {
   CK(cudaMalloc(&dA, M * 64 * 4)); CK(cudaMalloc(&dB, 256 * 64 * 4)); CK(cudaMalloc(&dD, M * 256 * 4)); CK(cudaMalloc(&dcyc, 8));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int fails = 0;
-  for (int N : {64, 128, 256}) for (int K : {8, 16, 64}) for (int a_mn = 0; a_mn < 2; ++a_mn) for (int b_mn = 0; b_mn < 2; ++b_mn) for (int sw = 0; sw < 1; ++sw) {
+  for (int N : {32, 64, 128, 256}) for (int K : {8, 16, 64}) for (int a_mn = 0; a_mn < 2; ++a_mn) for (int b_mn = 0; b_mn < 2; ++b_mn) for (int sw = 0; sw < 1; ++sw) {
     if (a_mn || b_mn) continue;  // MN-major tf32 operands returned zeros with these strides; the kernels use K-major only
     std::vector<float> A(M * K), B(N * K), D(M * N), R(M * N);
     srand(1234 + N + K);
@@ -162,7 +162,7 @@ int main() {
     if (!sw) fails += bad != 0;
   }
   // issue-rate: many back-to-back MMAs, one CTA (per-SM rate)
-  for (int N : {64, 128, 256}) for (int a_mn = 0; a_mn < 2; ++a_mn) {
+  for (int N : {16, 32, 64, 128, 256}) for (int a_mn = 0; a_mn < 1; ++a_mn) {  // K-major only (see above)
     Cfg c{N, 64, a_mn, 0, 0};
     int reps = 2000;
     probe_kernel<<<1, 128, (M + N) * 64 * 4 + 1024>>>(dA, dB, dD, c, reps, dcyc);
