@@ -635,6 +635,48 @@ def _traffic(cfg, kname, B):
     return None
 
 
+def measure_simulation(args, world, rank, dev):
+    """End to end through the UNMODIFIED ``Simulation.run()`` API (north_star): drops/s of the reference's own scripts with
+    the channel on the GPU and the batched drop runner (hermespy_b200/runner.py).  Two scripts: BASELINE config C1 (SISO RRC
+    over TDL-A, 11 SNR points) and the C2 frame through a modem the reference can demodulate (2x1 Alamouti OFDM, 1024
+    subcarriers, ideal CSI, TDL-B).  N = 1: helper processes on the host cores, and the stock reference on all host cores
+    beside it.  N > 1: every rank runs its own campaign share with in-process lanes (no fork next to NCCL)."""
+    import torch
+    import torch.distributed as dist
+
+    from oracle.refload import load_reference, reference_available
+
+    if not reference_available():
+        return {"unavailable": "no reference install (baseline/_ref)"}
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import simulation_campaign as sc
+
+    load_reference()
+    from hermespy_b200 import config as hb_config
+
+    hb_config.device = dev.index
+    cores = os.cpu_count() or 1
+    workers = max(1, cores - 1) if world == 1 else 0
+    out = {"api": "hermespy.simulation.Simulation.run() (unmodified script), dropin.enable(precision='f64', batch_drops, workers)",
+           "host_cores": cores, "helper_processes_per_rank": workers}
+    for name, samples, lanes in (("c1", 200 if world == 1 else 40, 128 if world == 1 else 32),
+                                 ("ofdm", 32 if world == 1 else 8, 64 if world == 1 else 16)):
+        rec = sc.run_gpu(name, samples, "f64", lanes, workers)
+        t = torch.tensor([rec["seconds"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        entry = {"drops_per_s": world * rec["drops"] / float(t.item()), "drops_per_rank": rec["drops"], "lanes": lanes,
+                 "links_per_launch_round": rec["links_per_round"], "kernel_launches_per_rank": rec["kernel_launches"],
+                 "ber": rec["ber"], "owner_seconds": rec.get("owner_seconds")}
+        if world == 1 and not args.no_cpu_baseline:
+            ref = sc.run_reference(name, max(cores, samples), cores)
+            entry["reference_all_host_cores_drops_per_s"] = ref["drops_per_s"]
+            entry["reference_ber"] = ref["ber"]
+            entry["speedup_vs_reference_all_host_cores"] = entry["drops_per_s"] / ref["drops_per_s"]
+        out[name] = entry
+    return out if rank == 0 else None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -669,7 +711,17 @@ def run_ours(args):
                     raise
             if rank == 0:
                 subs[f"{cid}_sinc" if sinc else (cid if prec == "f32" or cid != args.config else f"{cid}_{prec}")] = rec
+    sim = None
+    if not args.only and not args.no_simulation:
+        try:
+            sim = measure_simulation(args, world, rank, dev)
+        except Exception as e:
+            sim = {"error": repr(e)}
+            if world > 1:
+                raise
     if rank == 0:
+        if sim is not None:
+            head["simulation_api"] = sim
         if subs:
             head["configs"] = subs
             head["gpu_launches_all_configs"] = head["gpu_launches"] + sum(r.get("gpu_launches", 0) for r in subs.values())
@@ -697,6 +749,7 @@ def main():
     ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs left to the NCCL all-reduce of the statistics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--no-simulation", action="store_true", help="skip the Simulation.run() drops/s record")
     ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "poly_tma", "poly_fused", "direct"],
                     help="kernel selection (profiling / A-B runs); the default lets the planner choose")
     args = ap.parse_args()

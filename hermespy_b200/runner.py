@@ -28,6 +28,7 @@ import copy
 import multiprocessing as mp
 import queue
 import threading
+import time
 import traceback
 from typing import Any, List, Sequence
 
@@ -328,10 +329,13 @@ def device_call(name: str, *args):
     return msg[1]
 
 
-def _worker_main(conn, lanes: dict) -> None:
-    """Serve the lanes of one helper process: ('pre', {lane: section}) -> requests; ('post', {lane: results}) -> artifacts."""
+def _worker_main(conn, make_lanes) -> None:
+    """Serve the lanes of one helper process: ('pre', {lane: section}) -> requests; ('post', {lane: results}) -> artifacts.
+    The helper builds its own lanes (``make_lanes()``: deep copies of the tuple it inherited by fork), so the copies of all
+    helpers are made in parallel instead of one after the other in the parent."""
     global _rpc_conn
     _rpc_conn = conn
+    lanes = make_lanes()
     try:  # one thread per helper: the helpers ARE the parallelism (BLAS / OpenMP pools would oversubscribe the cores)
         import torch
 
@@ -372,7 +376,7 @@ def _writer_main(conn, outbox) -> None:
             return
         try:
             conn.send(msg)
-        except (BrokenPipeError, OSError):
+        except Exception:  # the helper is gone or the pipe was closed under us: nothing left to deliver
             return
 
 
@@ -384,16 +388,20 @@ class LaneSet(object):
         """``propagate(requests) -> results``: the device call of a round (default ``propagate_requests``)."""
         self.num_lanes = max(1, int(num_lanes))
         self.propagate = propagate_requests if propagate is None else propagate
-        lanes = {}
-        for k in range(self.num_lanes):
+        t_setup = time.perf_counter()
+
+        def make(k):
             if k == 0 and first_lane_is_original:
-                lanes[k] = Lane(scenario, grid, evaluators, stage_arguments)  # lane 0 IS the actor's own tuple and seed
-            else:
-                lanes[k] = Lane.clone_of(scenario, grid, evaluators, k, base_seed, stage_arguments)
-        self.local = lanes
+                return Lane(scenario, grid, evaluators, stage_arguments)  # lane 0 IS the actor's own tuple and seed
+            return Lane.clone_of(scenario, grid, evaluators, k, base_seed, stage_arguments)
+
+        self.local: dict = {}
         self.procs: list = []
         self.outbox: list = []
+        self.writers: list = []
         self._mail: dict = {}
+        #: where the GPU owner's wall time went (run_stream): waiting for the helpers' stages, the device call, hand-over
+        self.seconds = {"setup": 0.0, "wait_pre": 0.0, "propagate": 0.0, "send": 0.0, "wait_post": 0.0}
         workers = min(int(workers), self.num_lanes)
         if workers > 0:
             # One throwaway drop in THIS process first: numba compiles the reference's jitted helpers (resampling, dB
@@ -405,18 +413,22 @@ class LaneSet(object):
             ctx = mp.get_context("fork")  # lanes travel by fork: no pickling of scenarios, exactly the parent's objects
             self.owner = {}
             for w in range(workers):
-                mine = {k: lanes[k] for k in range(w, self.num_lanes, workers)}
+                mine = list(range(w, self.num_lanes, workers))
                 parent, child = ctx.Pipe()
-                p = ctx.Process(target=_worker_main, args=(child, mine), daemon=True)
+                p = ctx.Process(target=_worker_main, args=(child, lambda mine=mine: {k: make(k) for k in mine}), daemon=True)
                 p.start()
                 child.close()
                 self.procs.append((p, parent))
                 box: queue.SimpleQueue = queue.SimpleQueue()
-                threading.Thread(target=_writer_main, args=(parent, box), daemon=True).start()
+                th = threading.Thread(target=_writer_main, args=(parent, box), daemon=True)
+                th.start()
                 self.outbox.append(box)
+                self.writers.append(th)
                 for k in mine:
                     self.owner[k] = w
-            self.local = {}
+        else:
+            self.local = {k: make(k) for k in range(self.num_lanes)}
+        self.seconds["setup"] = time.perf_counter() - t_setup
 
     def run_round(self, sections: Sequence[tuple], propagate=None) -> List[list]:
         """One stage-synchronous round: ``sections[k]`` runs on lane k; ``propagate(requests) -> results`` is called ONCE
@@ -456,18 +468,29 @@ class LaneSet(object):
 
         for g in range(groups):
             start(g)
+        clock = time.perf_counter
         while pre or post:
             for g in range(groups):
                 if g in post:
                     lanes, secs = post.pop(g)
-                    for sec, art in zip(secs, self._await("post", g, lanes)):
+                    t0 = clock()
+                    arts = self._await("post", g, lanes)
+                    self.seconds["wait_post"] += clock() - t0
+                    for sec, art in zip(secs, arts):
                         yield sec, art
                 if g in pre:
                     lanes, secs = pre.pop(g)
+                    t0 = clock()
                     per_lane = self._await("pre", g, lanes)
-                    self._send("post", g, lanes, self._propagate_split(per_lane, propagate))
+                    t1 = clock()
+                    slices = self._propagate_split(per_lane, propagate)
+                    t2 = clock()
+                    self._send("post", g, lanes, slices)
                     post[g] = (lanes, secs)
                     start(g)  # queued behind the post message: the helpers run it as soon as they are through
+                    self.seconds["wait_pre"] += t1 - t0
+                    self.seconds["propagate"] += t2 - t1
+                    self.seconds["send"] += clock() - t2
 
     @staticmethod
     def _propagate_split(per_lane, propagate):
@@ -531,12 +554,14 @@ class LaneSet(object):
         for box in self.outbox:
             box.put(("stop", 0, None))
             box.put(None)
+        for th in self.writers:  # the stop messages are on their way before any pipe is closed
+            th.join(timeout=5)
         for p, conn in self.procs:
             p.join(timeout=5)
             if p.is_alive():
                 p.terminate()
             conn.close()
-        self.procs, self.outbox = [], []
+        self.procs, self.outbox, self.writers = [], [], []
 
 
 # ---- the actor's run loop (replaces MonteCarloActor.run for SimulationActor while the runner is enabled) -----------------
@@ -590,6 +615,7 @@ def batched_actor_run(self) -> None:
             print(e)
         if done:
             results.append(put(done))
+        stats["seconds"] = dict(lanes.seconds)
     finally:
         lanes.close()
 

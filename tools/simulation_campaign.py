@@ -151,6 +151,7 @@ def run_gpu(cfg, samples, precision, lanes, workers):
                 seconds=dt, drops_per_s=samples * points / dt, kernel_launches=launches,
                 links=runner.stats["links"] if lanes else None, rounds=runner.stats["rounds"] if lanes else None,
                 links_per_round=runner.stats["max_links_per_round"] if lanes else 1,
+                owner_seconds=runner.stats.get("seconds") if lanes else None,
                 ber=np.asarray(res.evaluation_results[0].to_array(), dtype=float).ravel().tolist())
 
 
