@@ -672,6 +672,8 @@ def measure_simulation(args, world, rank, dev):
             ref = sc.run_reference(name, max(cores, samples), cores)
             entry["reference_all_host_cores_drops_per_s"] = ref["drops_per_s"]
             entry["reference_ber"] = ref["ber"]
+            entry["reference_propagate_share_of_run"] = ref["propagate_share_of_run"]
+            entry["amdahl_bound_if_propagate_were_free"] = ref["amdahl_bound_if_propagate_were_free"]
             entry["speedup_vs_reference_all_host_cores"] = entry["drops_per_s"] / ref["drops_per_s"]
         out[name] = entry
     return out if rank == 0 else None

@@ -401,7 +401,7 @@ class LaneSet(object):
         self.writers: list = []
         self._mail: dict = {}
         #: where the GPU owner's wall time went (run_stream): waiting for the helpers' stages, the device call, hand-over
-        self.seconds = {"setup": 0.0, "wait_pre": 0.0, "propagate": 0.0, "send": 0.0, "wait_post": 0.0}
+        self.seconds = {"setup": 0.0, "sections": 0.0, "wait_pre": 0.0, "propagate": 0.0, "send": 0.0, "wait_post": 0.0}
         workers = min(int(workers), self.num_lanes)
         if workers > 0:
             # One throwaway drop in THIS process first: numba compiles the reference's jitted helpers (resampling, dB
@@ -456,12 +456,14 @@ class LaneSet(object):
 
         def start(g):
             lanes, secs = [], []
+            t_s = time.perf_counter()
             for lane in range(g * size, min(self.num_lanes, (g + 1) * size)):
                 try:
                     secs.append(next(it))
                 except StopIteration:
                     break
                 lanes.append(lane)
+            self.seconds["sections"] += time.perf_counter() - t_s
             if lanes:
                 self._send("pre", g, lanes, secs)
                 pre[g] = (lanes, secs)

@@ -109,11 +109,27 @@ def _reference_process(args):
     from oracle.refload import load_reference
 
     load_reference()
+    from hermespy.channel.channel import ChannelSample
+
     sim = _fast_polling(BUILDERS[cfg][0](samples, seed))
-    t0 = time.perf_counter()
-    res = sim.run()
-    dt = time.perf_counter() - t0
-    return np.asarray(res.evaluation_results[0].to_array(), dtype=float).ravel().tolist(), dt
+    spent = [0.0]
+    orig = ChannelSample.propagate
+
+    def timed(self, *a, **k):  # share of the run spent inside the channel: what a faster channel can remove (Amdahl)
+        t = time.perf_counter()
+        try:
+            return orig(self, *a, **k)
+        finally:
+            spent[0] += time.perf_counter() - t
+
+    ChannelSample.propagate = timed
+    try:
+        t0 = time.perf_counter()
+        res = sim.run()
+        dt = time.perf_counter() - t0
+    finally:
+        ChannelSample.propagate = orig
+    return np.asarray(res.evaluation_results[0].to_array(), dtype=float).ravel().tolist(), dt, spent[0]
 
 
 def run_reference(cfg, samples, cores):
@@ -126,8 +142,10 @@ def run_reference(cfg, samples, cores):
         out = pool.map(_reference_process, [(cfg, per, 1000 + i) for i in range(cores)])
         dt = time.perf_counter() - t0
     points = BUILDERS[cfg][1]
+    share = float(np.mean([o[2] / o[1] for o in out]))  # includes the ideal self-links; channel-model share is below it
     return dict(processes=cores, samples_per_point=per * cores, drops=per * cores * points, seconds=dt,
-                drops_per_s=per * cores * points / dt, ber=np.mean([o[0] for o in out], axis=0).tolist())
+                drops_per_s=per * cores * points / dt, ber=np.mean([o[0] for o in out], axis=0).tolist(),
+                propagate_share_of_run=share, amdahl_bound_if_propagate_were_free=1.0 / max(1e-9, 1.0 - share))
 
 
 def run_gpu(cfg, samples, precision, lanes, workers):
