@@ -127,6 +127,14 @@ def measured_peaks():
     return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
+def _measured_bf16_tflops():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["bf16_tflops"]), "measured burst, MEASURED_PEAKS.json"
+    except Exception:
+        return 2250.0, "fallback: nominal dense bf16 (B200_PROFILING.md)"
+
+
 # ---- clocks ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """Samples SM clock / power / throttle reasons through NVML (ctypes calls release the GIL; no fork inside
@@ -412,6 +420,8 @@ class Workload:
     def dominant(self, prof, info):
         """(accounting kind, kernel name, bound) of the step's dominant kernel."""
         if self.cfg["kind"] == "cdl":
+            if info.get("variant") == "umma":
+                return "cdl_propagate", "cdl_umma_kernel", "tensor"
             return "cdl_propagate", ("cdl_poly_kernel" if info.get("mode") == "poly" else "cdl_direct_f64_kernel"), "fp32"
         if info.get("variant") == "fused":
             return "spatial_gemm", "fused_gemm_tdl_kernel", "hbm"
@@ -559,6 +569,22 @@ def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allre
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": _traffic(cfg, kname, B), "peak_source": peak_src}
+    elif bound == "tensor":
+        # CDL contraction on tcgen05 (cdl_umma_kernel): ALGORITHMIC flops = 8 P G Nrx Ntx per output sample; the kernel runs
+        # them as 3xTF32 (three TF32 products per FP32 product), so the tensor pipe executes 3x that.  Peak: dense TF32 =
+        # half the measured cuBLAS bf16 burst figure of MEASURED_PEAKS.json (the kernel is timed alone per launch).
+        flops = 8.0 * info["poly_order"] * info["num_groups"] * wl.nrx * wl.ntx * B * (T + wl.D)
+        bf16_tf = _measured_bf16_tflops()
+        peak_tf = 0.5 * bf16_tf[0]
+        achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None,
+                    "peak_source": f"dense TF32 = 0.5 x bf16_tflops ({bf16_tf[1]})",
+                    "tensor_flops_executed_per_algorithmic_flop": 3.0,
+                    "tensor_pipe_frac_3xtf32": 3.0 * achieved / peak_tf,
+                    "binding_unit": "shared-memory operand reads of the MMAs (128 B/clk/SM; N = 64 columns per instruction): "
+                                    "88 clk per (delay group, 4 antennas, 128 samples) pair measured by tools/microbench/umma_shift_probe.cu",
+                    "hbm_frac_of_step": alg_bytes / (ms_total / steps * 1e-3) / 1e9 / hbm_peak}
     else:
         # CDL contraction: 8 P G Nrx Ntx real flop per output sample, on the FP32 pipe
         flops = 8.0 * info["poly_order"] * info["num_groups"] * wl.nrx * wl.ntx * B * (T + wl.D) if info.get("mode") == "poly" else 0.0

@@ -266,7 +266,7 @@ class CdlProblem(C.Structure):
         ("tx_topology", C.c_void_p),
         ("rx_topology", C.c_void_p),
         ("element_mode", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("variant", C.c_int32),
         ("tx_elements", C.c_void_p),
         ("rx_elements", C.c_void_p),
     ]

@@ -5,11 +5,13 @@
 #include <vector>
 
 #include "cdl_kernels.cuh"
+#include "cdl_umma.cuh"
 
 namespace hb {
 
 struct CdlPlan {
   int mode, tile, P, ntiles, Dpad, nrx_tpl, R, threads, max_group_terms;
+  int variant;  // hb_cdl_variant actually used (POLY only)
   size_t smem;
   double bound;
 };
@@ -86,44 +88,91 @@ static size_t cdl_smem(int tile, int Dpad, int G, int P, int nrx_tpl) {
   return sizeof(float2) * ((size_t)kCdlTxChunk * (tile + Dpad) + (size_t)G * P * nrx_tpl * kCdlTxChunk);
 }
 
+// Truncation bound of a P-term Taylor expansion over windows of `tile` samples.
+static double cdl_poly_bound(const hb_cdl_problem* p, int tile, int P, int max_group_terms) {
+  const double w_max = 2.0 * M_PI * p->max_speed * p->carrier_frequency / kSpeedOfLight / p->sampling_rate;
+  const double u_half = 0.5 * w_max * tile;
+  if (u_half <= 0.0) return 0.0;
+  double t = 1.0;
+  for (int k = 1; k <= P; ++k) t *= u_half / (double)k;
+  const double tail = u_half < P + 1 ? 1.0 / (1.0 - u_half / (P + 1)) : 1e30;
+  return sqrt((double)max_group_terms) * t * tail;
+}
+// smallest P <= 4 meeting the target (0: none)
+static int cdl_poly_order(const hb_cdl_problem* p, int tile, int max_group_terms, double* bound_out) {
+  for (int cand = 1; cand <= 4; ++cand) {
+    const double bound = cdl_poly_bound(p, tile, cand, max_group_terms);
+    if (bound <= kCdlPolyTarget) {
+      *bound_out = bound;
+      return cand;
+    }
+  }
+  return 0;
+}
+
 static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* pl) {
   const int Tout = p->num_samples + p->max_delay;
-  pl->Dpad = (p->max_delay + 1) & ~1;
   pl->nrx_tpl = p->num_rx <= 1 ? 1 : (p->num_rx <= 2 ? 2 : (p->num_rx <= 4 ? 4 : 8));
   pl->threads = 128;
-  pl->R = pl->nrx_tpl <= 4 ? 4 : 2;
-  pl->tile = pl->threads * pl->R;
   pl->bound = 0.0;
+  pl->variant = HB_CDL_VARIANT_GATHER;
   pl->max_group_terms = 1;
   for (int g = 0; g < tb.num_groups; ++g)
     pl->max_group_terms = std::max(pl->max_group_terms, (int)tb.group_start[g + 1] - (int)tb.group_start[g]);
-  bool poly = p->precision == HB_F32;
-  if (poly) {
-    const double w_max = 2.0 * M_PI * p->max_speed * p->carrier_frequency / kSpeedOfLight / p->sampling_rate;
-    const double u_half = 0.5 * w_max * pl->tile;
-    int P = 0;
-    double bound = 0.0;
-    for (int cand = 1; cand <= 4 && !P; ++cand) {
-      double t = 1.0;
-      for (int k = 1; k <= cand; ++k) t *= u_half / (double)k;
-      if (u_half <= 0.0) t = 0.0;
-      const double tail = u_half < cand + 1 ? 1.0 / (1.0 - u_half / (cand + 1)) : 1e30;
-      bound = sqrt((double)pl->max_group_terms) * t * tail;
-      if (bound <= kCdlPolyTarget) P = cand;
+  if (p->variant < HB_CDL_VARIANT_AUTO || p->variant > HB_CDL_VARIANT_UMMA) {
+    set_error("unknown CDL variant %d", p->variant);
+    return HB_ERR_INVALID;
+  }
+  bool poly = false;
+  if (p->precision == HB_F32 && p->variant != HB_CDL_VARIANT_GATHER) {
+    // tensor-core kernel (cdl_umma.cuh): the Taylor window is 128 MT samples, MT fixed by the accumulator width, so the
+    // order is searched with the window it implies.  AUTO takes it from 8 transmit antennas (below, K is too short to pay
+    // for the operand staging).
+    const bool want = p->variant == HB_CDL_VARIANT_UMMA || p->num_tx >= 8;
+    const int Dpad = (p->max_delay + 7) & ~7;
+    for (int cand = 1; cand <= 4 && want && !poly; ++cand) {
+      const int tile = cu_tile(pl->nrx_tpl, cand);
+      const double bound = cdl_poly_bound(p, tile, cand, pl->max_group_terms);
+      const size_t smem = cu_smem_bytes(pl->nrx_tpl, cand, Dpad, tb.num_groups);
+      const bool fits = smem <= 226 * 1024 && tile + Dpad < 16384;  // both operand images of a K stage, two slots
+      if (bound <= kCdlPolyTarget && fits) {
+        pl->mode = HB_SOS_POLY;
+        pl->variant = HB_CDL_VARIANT_UMMA;
+        pl->P = cand;
+        pl->tile = tile;
+        pl->Dpad = Dpad;
+        pl->smem = smem;
+        pl->R = 0;
+        pl->bound = bound;
+        poly = true;
+      }
     }
+    if (!poly && p->variant == HB_CDL_VARIANT_UMMA) {
+      set_error("the tensor-core CDL kernel does not take this problem (Doppler too fast for four Taylor terms, or the "
+                "operand images of %d delay groups and a %d-sample delay halo exceed the shared memory of one SM)",
+                tb.num_groups, Dpad);
+      return HB_ERR_UNSUPPORTED;
+    }
+  }
+  if (!poly && p->precision == HB_F32) {
+    pl->Dpad = (p->max_delay + 1) & ~1;
+    pl->R = pl->nrx_tpl <= 4 ? 4 : 2;
+    pl->tile = pl->threads * pl->R;
+    double bound = 0.0;
+    const int P = cdl_poly_order(p, pl->tile, pl->max_group_terms, &bound);
     pl->smem = P ? cdl_smem(pl->tile, pl->Dpad, tb.num_groups, P, pl->nrx_tpl) : 0;
-    if (!P || pl->smem > 200 * 1024) {
-      poly = false;  // Doppler too fast for four Taylor terms, or delay spread too long for the tile: per-ray path
-    } else {
+    if (P && pl->smem <= 200 * 1024) {
       pl->mode = HB_SOS_POLY;
       pl->P = P;
       pl->bound = bound;
-    }
+      poly = true;
+    }  // else: Doppler too fast for four Taylor terms, or delay spread too long for the tile: per-ray path
   }
   if (!poly) {
     pl->mode = HB_SOS_DIRECT;
     pl->P = 0;
     pl->tile = 128;
+    pl->Dpad = (p->max_delay + 1) & ~1;
     pl->smem = 0;
   }
   pl->ntiles = std::max(1, (Tout + pl->tile - 1) / pl->tile);
@@ -139,7 +188,7 @@ static void fill_cdl_info(const CdlPlan& pl, const CdlTable& tb, const hb_cdl_pr
   info->num_tiles = pl.ntiles;
   info->launches = pl.mode == HB_SOS_POLY ? 2 + (p->num_rx + pl.nrx_tpl - 1) / pl.nrx_tpl : 2;
   info->error_bound = pl.bound;
-  info->variant = 0;
+  info->variant = pl.mode == HB_SOS_POLY ? pl.variant : 0;
   info->poly_tile = pl.tile;
 }
 
@@ -282,8 +331,12 @@ static int cdl_propagate_device(const hb_cdl_problem* p, const CdlTable& tb, con
     for (int rx0 = 0; rx0 < p->num_rx && rc == HB_OK; rx0 += pl.nrx_tpl) {
       a.rx0 = rx0;
       a.nrx_chunk = std::min(pl.nrx_tpl, p->num_rx - rx0);
-      rc = io128 ? launch_poly_nrx<double2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st)
-                 : launch_poly_nrx<float2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st);
+      if (pl.variant == HB_CDL_VARIANT_UMMA)
+        rc = io128 ? launch_cdl_umma_io<double2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st)
+                   : launch_cdl_umma_io<float2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st);
+      else
+        rc = io128 ? launch_poly_nrx<double2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st)
+                   : launch_poly_nrx<float2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st);
     }
   } else if (rc == HB_OK) {
     ProfileScope prof(KIND_CDL_PROPAGATE, st);

@@ -620,10 +620,21 @@ class CdlBlock:
                 self.carrier_frequency, self.sampling_rate, self.line_of_sight, self.los_delay, self.los_amplitude, el)
 
 
-def _cdl_problem(blk: CdlBlock, num_samples: int, precision, io128: bool, ptrs: dict):
+_CDL_VARIANT = {"auto": 0, "gather": 1, "umma": 2}
+
+
+def _cdl_info_dict(info: FadingPlanInfo) -> dict:
+    d = info.as_dict()
+    d["mode"] = _SOS_NAME.get(d["mode"], d["mode"])
+    d["variant"] = {1: "gather", 2: "umma"}.get(d["variant"]) if d["mode"] == "poly" else None
+    return d
+
+
+def _cdl_problem(blk: CdlBlock, num_samples: int, precision, io128: bool, ptrs: dict, variant="auto"):
     from ._lib import CdlProblem
 
     p = CdlProblem()
+    p.variant = _CDL_VARIANT[variant]
     p.batch = blk.batch
     p.num_tx = blk.num_tx
     p.num_rx = blk.num_rx
@@ -653,16 +664,17 @@ def _cdl_problem(blk: CdlBlock, num_samples: int, precision, io128: bool, ptrs: 
     return p
 
 
-def cdl_plan(blk: CdlBlock, num_samples: int, precision="f32") -> dict:
+def cdl_plan(blk: CdlBlock, num_samples: int, precision="f32", variant="auto") -> dict:
+    """What ``hb_cdl_plan`` decides.  ``variant``: "auto" | "gather" (FP32-pipe K6) | "umma" (tensor-core K6)."""
     lib = _lib.load()
-    p = _cdl_problem(blk, num_samples, precision, False, {k: None for k in CdlBlock.ARRAYS})  # planning reads no arrays
+    p = _cdl_problem(blk, num_samples, precision, False, {k: None for k in CdlBlock.ARRAYS}, variant)  # planning reads no arrays
     info = FadingPlanInfo()
     _lib.check(lib.hb_cdl_plan(C.byref(p), C.byref(info)))
-    return _info_dict(info)
+    return _cdl_info_dict(info)
 
 
 def cdl_propagate_host(x: np.ndarray, blk: CdlBlock, precision="f32", out: Optional[np.ndarray] = None,
-                       chunk_links: int = 0, return_info=False, device: Optional[int] = None):
+                       chunk_links: int = 0, return_info=False, device: Optional[int] = None, variant="auto"):
     """Host-buffer CDL propagation: ``x[B, Ntx, T]`` numpy complex64/128 -> ``y[B, Nrx, T + D]``.
 
     GPU counterpart of ``ClusterDelayLineSample._propagate`` (cluster_delay_lines.py:526-558) for a batch.
@@ -683,11 +695,11 @@ def cdl_propagate_host(x: np.ndarray, blk: CdlBlock, precision="f32", out: Optio
         out = np.empty((blk.batch, blk.num_rx, Tout), dtype=x.dtype)
     elif out.shape != (blk.batch, blk.num_rx, Tout) or out.dtype != x.dtype or not out.flags.c_contiguous:
         raise ValueError("out has the wrong shape / dtype / layout")
-    p = _cdl_problem(blk, T, precision, x.dtype == np.complex128, blk.pointers(lambda a: a.ctypes.data))
+    p = _cdl_problem(blk, T, precision, x.dtype == np.complex128, blk.pointers(lambda a: a.ctypes.data), variant)
     info = FadingPlanInfo()
     _lib.check(lib.hb_cdl_propagate_host(C.byref(p), x.ctypes.data, out.ctypes.data, int(chunk_links), C.byref(info)))
     if return_info:
-        return out, _info_dict(info)
+        return out, _cdl_info_dict(info)
     return out
 
 
@@ -702,7 +714,7 @@ class CdlDeviceBlock(object):
         self.device = self.tensors["angles"].device
 
 
-def cdl_propagate(x, dblk: CdlDeviceBlock, precision="f32", out=None, return_info=False):
+def cdl_propagate(x, dblk: CdlDeviceBlock, precision="f32", out=None, return_info=False, variant="auto"):
     """Device-resident CDL propagation on torch's current stream (no synchronization)."""
     torch = _torch()
     lib = _lib.load()
@@ -721,13 +733,14 @@ def cdl_propagate(x, dblk: CdlDeviceBlock, precision="f32", out=None, return_inf
     elif tuple(out.shape) != (blk.batch, blk.num_rx, Tout) or out.dtype != x.dtype or not out.is_contiguous() \
             or out.device != x.device:
         raise ValueError("out has the wrong shape / dtype / layout / device")
-    p = _cdl_problem(blk, T, precision, x.dtype == torch.complex128, {k: v.data_ptr() for k, v in dblk.tensors.items()})
+    p = _cdl_problem(blk, T, precision, x.dtype == torch.complex128, {k: v.data_ptr() for k, v in dblk.tensors.items()},
+                     variant)
     info = FadingPlanInfo()
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(lib.hb_cdl_propagate(C.byref(p), x.data_ptr(), out.data_ptr(), C.c_void_p(stream), C.byref(info)))
     if return_info:
-        return out, _info_dict(info)
+        return out, _cdl_info_dict(info)
     return out
 
 

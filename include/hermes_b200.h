@@ -181,6 +181,12 @@ typedef enum hb_element_kind {
   HB_ELEMENT_DIPOLE = 3  /* F = [cos(pi/2 cos ze) / sin ze, 0] (0 at ze = 0)        core/antennas.py:610-614 */
 } hb_element_kind;
 
+typedef enum hb_cdl_variant {
+  HB_CDL_VARIANT_AUTO = 0,   /* tensor-core kernel from 8 transmit antennas when it takes the problem, else the gather kernel */
+  HB_CDL_VARIANT_GATHER = 1, /* cdl_poly_kernel: FP32 pipe, moments and x tile from shared memory                           */
+  HB_CDL_VARIANT_UMMA = 2    /* cdl_umma_kernel: tcgen05 3xTF32, delay groups folded into K (HB_ERR_UNSUPPORTED if not eligible) */
+} hb_cdl_variant;
+
 typedef struct hb_cdl_problem {
   int32_t batch;            /* B links                                                              */
   int32_t num_tx, num_rx;   /* antenna counts                                                       */
@@ -211,7 +217,7 @@ typedef struct hb_cdl_problem {
    * Row layout (HB_ELEMENT_STRIDE doubles): [0..8] rotation element frame -> array frame (row-major 3x3),
    * [9] hb_element_kind, [10] kind parameter (LinearAntenna: slant in radians), [11] reserved. */
   int32_t element_mode;        /* hb_element_mode                                                   */
-  int32_t reserved0;
+  int32_t variant;             /* hb_cdl_variant: which K6 kernel the POLY mode runs (f32 only)     */
   const double* tx_elements;   /* DEVICE f64 [Ntx or 1, HB_ELEMENT_STRIDE]                          */
   const double* rx_elements;   /* DEVICE f64 [Nrx or 1, HB_ELEMENT_STRIDE]                          */
 } hb_cdl_problem;
@@ -224,7 +230,7 @@ typedef struct hb_cdl_plan_info {
   int32_t num_tiles;
   int32_t launches;
   double error_bound;
-  int32_t variant;     /* reserved (0) */
+  int32_t variant;     /* hb_cdl_variant that runs (POLY only): GATHER or UMMA */
   int32_t poly_tile;   /* == tile */
 } hb_cdl_plan_info;
 

@@ -156,3 +156,46 @@ def test_planner_fuzz_never_crashes_and_respects_its_own_limits():
             accepted["direct"] += 1
             assert info.tile == 256
     assert all(n > 0 for n in accepted.values()), accepted  # the fuzz reaches every kernel family
+
+
+def _cdl_plan(ntx, nrx, T, delays, speed=10.0, precision=0, variant=0, fs=30.72e6, fc=3.5e9):
+    """hb_cdl_plan on a bare problem description (planning reads no device arrays)."""
+    lib = _lib.load()
+    p = _lib.CdlProblem()
+    td = np.asarray(delays, dtype=np.int32)
+    p.batch, p.num_tx, p.num_rx, p.num_samples = 4, ntx, nrx, T
+    p.max_delay, p.num_terms = int(td.max()) + 1, td.size
+    p.precision, p.variant = precision, variant
+    p.carrier_frequency, p.sampling_rate, p.max_speed = fc, fs, speed
+    p.term_delay = td.ctypes.data_as(C.POINTER(C.c_int32))
+    info = _lib.FadingPlanInfo()
+    rc = lib.hb_cdl_plan(C.byref(p), C.byref(info))
+    return rc, info.as_dict()
+
+
+def test_cdl_planner_kernel_variants():
+    """Which K6 kernel the CDL planner picks (include/hermes_b200.h: hb_cdl_variant); 0 AUTO, 1 GATHER, 2 UMMA."""
+    delays = np.repeat(np.arange(0, 80, 4), 20)  # 20 clusters x 20 rays -> 20 delay groups
+    rc, d = _cdl_plan(32, 4, 2048, delays)  # config C3 shape: tensor cores, 4 M-tiles per Taylor window
+    assert rc == 0 and d["mode"] == 1 and d["variant"] == 2 and d["tile"] == 512 and d["num_groups"] == 20
+    assert 1 <= d["poly_order"] <= 4 and d["error_bound"] <= 5e-8
+    rc, d = _cdl_plan(2, 2, 2048, delays)  # short K: the FP32-pipe kernel
+    assert rc == 0 and d["mode"] == 1 and d["variant"] == 1
+    rc, d = _cdl_plan(2, 2, 2048, delays, variant=2)  # ... unless asked for
+    assert rc == 0 and d["variant"] == 2
+    rc, d = _cdl_plan(32, 4, 2048, delays, variant=1)
+    assert rc == 0 and d["variant"] == 1
+    rc, d = _cdl_plan(32, 4, 2048, delays, precision=1)  # f64 parity mode: per-ray kernel
+    assert rc == 0 and d["mode"] == 2 and d["variant"] == 0
+    rc, d = _cdl_plan(32, 4, 2048, delays, speed=0.0)  # static link: one Taylor term
+    assert rc == 0 and d["variant"] == 2 and d["poly_order"] == 1
+    rc, d = _cdl_plan(32, 8, 2048, delays, speed=30.0)  # wider accumulator rows -> fewer M-tiles per window
+    assert rc == 0 and d["variant"] == 2 and d["tile"] in (256, 512)
+    # beyond the staging limits AUTO falls back to the gather kernel, an explicit request is refused
+    long_delays = np.repeat(np.arange(0, 1000, 50), 20)
+    rc, d = _cdl_plan(32, 4, 2048, long_delays)
+    assert rc == 0 and d["variant"] == 1
+    rc, _ = _cdl_plan(32, 4, 2048, long_delays, variant=2)
+    assert rc == _lib.HB_ERR_UNSUPPORTED and "tensor-core" in _lib.load().hb_last_error().decode()
+    rc, _ = _cdl_plan(32, 4, 2048, delays, variant=7)
+    assert rc == _lib.HB_ERR_INVALID

@@ -104,3 +104,47 @@ def test_non_nearest_interpolation_yields_zeros():
     _, s, _, _ = mirror_cdl_sample(CDL_CASES[3])
     y = s.propagate(Signal.Create(np.ones((1, 16), complex), CDL_FS, CDL_FC), InterpolationMode.SINC).view(np.ndarray)
     assert y.shape[1] > 16 and not y.any()
+
+
+@pytest.mark.parametrize("dims_tx,dims_rx,speed,T,cdl_type,io", [
+    ((8, 4, 1), (2, 2, 1), (10.0, -3.0, 0.0), 2048, "C", np.complex64),    # config C3 shape: 4 M-tiles + the delay tail
+    ((8, 4, 1), (2, 2, 1), (10.0, -3.0, 0.0), 700, "C", np.complex128),    # partial window, complex128 frames
+    ((4, 4, 1), (4, 2, 1), (0.0, 0.0, 0.0), 300, "A", np.complex64),       # static: P = 1, 8 receive antennas
+    ((4, 2, 1), (5, 2, 1), (30.0, 15.0, 2.0), 900, "D", np.complex128),     # LOS term, 10 receive antennas = two chunks of 8
+    ((3, 1, 1), (3, 1, 1), (30.0, 0.0, 0.0), 64, "E", np.complex64),       # odd antenna counts, frame shorter than one M-tile
+    ((1, 1, 1), (1, 1, 1), (25.0, 0.0, 0.0), 1500, "B", np.complex64),     # SISO: one half-empty K step
+    ((5, 3, 1), (2, 1, 1), (3.0, 3.0, 0.0), 1100, "C", np.complex64),      # 15 transmit antennas: last K stage ragged
+])
+def test_tensor_core_variant_against_oracle_and_gather(dims_tx, dims_rx, speed, T, cdl_type, io):
+    """K6 on tcgen05 (``variant="umma"``, cdl_umma.cuh) against the float64 oracle (<= 1e-5, north_star) and against the FP32-pipe
+    kernel it replaces; the planner reports which kernel ran."""
+    from hermespy_b200 import _lib
+    from hermespy_b200.kernels import CdlBlock, cdl_plan, cdl_propagate_host
+
+    rng = np.random.default_rng(11)
+    tx = mirror_cdl_device((dims_tx, (0.0, 0.1, 0.0), (0.0, 0.0, 25.0), (0, 0, 0)))
+    ch = MC.CDL(getattr(MC.CDLType, cdl_type), 300e-9, seed=5)
+    ntx = int(np.prod(dims_tx))
+    B = 5
+    samples, xs, refs = [], [], []
+    for b in range(B):
+        rx = mirror_cdl_device((dims_rx, (0, 0, 0.3 * b), (100.0 + 7 * b, 20.0, 1.5), speed))
+        s = ch.realize().sample(tx, rx)
+        x = (rng.standard_normal((ntx, T)) + 1j * rng.standard_normal((ntx, T))) / np.sqrt(2)
+        samples.append(s), xs.append(x), refs.append(co.propagate(oracle_params(s), x))
+    groups = {}
+    for b, s in enumerate(samples):  # realizations of one static CDL table share their delay table
+        groups.setdefault(s.kernel_block().group_key(), []).append(b)
+    for idx in groups.values():
+        blk = CdlBlock.stack([samples[b].kernel_block() for b in idx])
+        x = np.stack([xs[b] for b in idx]).astype(io)
+        assert cdl_plan(blk, T, "f32", variant="umma")["variant"] == "umma"
+        before = _lib.launch_counts()["cdl_propagate"]
+        yu, info = cdl_propagate_host(x, blk, precision="f32", variant="umma", return_info=True)
+        assert info["variant"] == "umma" and _lib.launch_counts()["cdl_propagate"] > before
+        yg, info_g = cdl_propagate_host(x, blk, precision="f32", variant="gather", return_info=True)
+        assert info_g["variant"] == "gather"
+        for k, b in enumerate(idx):
+            assert yu[k].shape == refs[b].shape
+            assert rel_l2(yu[k], refs[b]) < 1e-5
+            assert rel_l2(yu[k], yg[k]) < 3e-6

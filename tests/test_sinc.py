@@ -100,13 +100,13 @@ def test_cost259_urban_sinc_on_the_gpu(T):
     import torch
 
     from hermespy_b200 import _lib
-    from hermespy_b200.channel.fading.profiles import COST259_URBAN_DELAYS, COST259_URBAN_POWERS
+    from hermespy_b200.channel.fading.profiles import COST259_PROFILES
     from hermespy_b200.kernels import FadingBatch, fading_propagate, fading_propagate_host, sinc_expand
 
     rng = np.random.default_rng(5)
     fs = 30.72e6
-    delays = np.asarray(COST259_URBAN_DELAYS, float)
-    powers = np.asarray(COST259_URBAN_POWERS, float)
+    delays = np.asarray(COST259_PROFILES[0]["delay"], float)
+    powers = np.asarray(COST259_PROFILES[0]["power"], float)
     powers = powers / powers.sum()
     plist = [random_fading_params(rng, 20, 20, 1, 1, fs, 50.0, 0.0, delays=delays, powers=powers) for _ in range(3)]
     xs = [random_signal(rng, 1, T) for _ in plist]
