@@ -12,6 +12,7 @@ namespace hb {
 struct CdlPlan {
   int mode, tile, P, ntiles, Dpad, nrx_tpl, R, threads, max_group_terms;
   int variant;  // hb_cdl_variant actually used (POLY only)
+  int ptile, nwin;  // Taylor window (multiple of tile) and windows per frame
   size_t smem;
   double bound;
 };
@@ -130,21 +131,31 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
     // for the operand staging).
     const bool want = p->variant == HB_CDL_VARIANT_UMMA || p->num_tx >= 8;
     const int Dpad = (p->max_delay + 7) & ~7;
-    for (int cand = 1; cand <= 4 && want && !poly; ++cand) {
+    // Joint choice of the Taylor order P and the window (1, 2, 4 or 8 K6 tiles): the K6 cost does not depend on either
+    // (N is padded to 16 columns), the moment kernel's is proportional to windows x P.
+    int best_cost = 1 << 30;
+    for (int cand = 1; cand <= 4 && want; ++cand) {
       const int tile = cu_tile(pl->nrx_tpl, cand);
-      const double bound = cdl_poly_bound(p, tile, cand, pl->max_group_terms);
       const size_t smem = cu_smem_bytes(pl->nrx_tpl, cand, Dpad, tb.num_groups);
-      const bool fits = smem <= 226 * 1024 && tile + Dpad < 16384;  // both operand images of a K stage, two slots
-      if (bound <= kCdlPolyTarget && fits) {
-        pl->mode = HB_SOS_POLY;
-        pl->variant = HB_CDL_VARIANT_UMMA;
-        pl->P = cand;
-        pl->tile = tile;
-        pl->Dpad = Dpad;
-        pl->smem = smem;
-        pl->R = 0;
-        pl->bound = bound;
-        poly = true;
+      if (smem > 226 * 1024 || tile + Dpad >= 16384) continue;  // both operand images of a K stage, two slots
+      for (int tw = 8; tw >= 1; tw >>= 1) {
+        const double bound = cdl_poly_bound(p, tile * tw, cand, pl->max_group_terms);
+        if (bound > kCdlPolyTarget) continue;
+        const int nwin = std::max(1, (Tout + tile * tw - 1) / (tile * tw));
+        if (nwin * cand < best_cost) {
+          best_cost = nwin * cand;
+          pl->mode = HB_SOS_POLY;
+          pl->variant = HB_CDL_VARIANT_UMMA;
+          pl->P = cand;
+          pl->tile = tile;
+          pl->ptile = tile * tw;
+          pl->Dpad = Dpad;
+          pl->smem = smem;
+          pl->R = 0;
+          pl->bound = bound;
+          poly = true;
+        }
+        break;  // smaller windows of this order only cost more
       }
     }
     if (!poly && p->variant == HB_CDL_VARIANT_UMMA) {
@@ -176,6 +187,8 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
     pl->smem = 0;
   }
   pl->ntiles = std::max(1, (Tout + pl->tile - 1) / pl->tile);
+  if (pl->variant != HB_CDL_VARIANT_UMMA || pl->mode != HB_SOS_POLY) pl->ptile = pl->tile;
+  pl->nwin = std::max(1, (Tout + pl->ptile - 1) / pl->ptile);
   return HB_OK;
 }
 
@@ -189,14 +202,19 @@ static void fill_cdl_info(const CdlPlan& pl, const CdlTable& tb, const hb_cdl_pr
   info->launches = pl.mode == HB_SOS_POLY ? 2 + (p->num_rx + pl.nrx_tpl - 1) / pl.nrx_tpl : 2;
   info->error_bound = pl.bound;
   info->variant = pl.mode == HB_SOS_POLY ? pl.variant : 0;
-  info->poly_tile = pl.tile;
+  info->poly_tile = pl.ptile;
 }
 
 template <int P>
 static int launch_moments(const CdlArgs& a, const CdlTable& tb, cudaStream_t st) {
   ProfileScope prof(KIND_CDL_RAYS, st);
-  const size_t blocks = (size_t)a.B * a.ntiles * tb.num_groups;
-  cdl_moment_kernel<P><<<(unsigned)blocks, 128, 0, st>>>(a, tb);
+  const size_t smem = sizeof(float2) * ((size_t)kMomTerms * kMomWin * P + (size_t)kMomTerms * a.rank * (a.nrx + a.ntx));
+  if (smem <= 48 * 1024) {  // one CTA per (link, delay group), all Taylor windows at once
+    cdl_moment_all_kernel<P><<<(unsigned)((size_t)a.B * tb.num_groups), 128, smem, st>>>(a, tb);
+  } else {  // arrays beyond ~80 elements per side: the per-window kernel reads the steering phases from global memory
+    const size_t blocks = (size_t)a.B * a.nwin * tb.num_groups;
+    cdl_moment_kernel<P><<<(unsigned)blocks, 128, 0, st>>>(a, tb);
+  }
   HB_CUDA(cudaGetLastError());
   return HB_OK;
 }
@@ -276,6 +294,8 @@ static void fill_args(const hb_cdl_problem* p, const CdlTable& tb, const CdlPlan
   a->ntiles = pl.ntiles;
   a->Dpad = pl.Dpad;
   a->P = pl.P;
+  a->ptile = pl.ptile;
+  a->nwin = pl.nwin;
 }
 
 static int alloc_rays(CdlArgs* a, CdlWorkspace* ws, cudaStream_t st) {
@@ -316,7 +336,7 @@ static int cdl_propagate_device(const hb_cdl_problem* p, const CdlTable& tb, con
   if (rc == HB_OK) rc = launch_rays(a, tb, st);
   const bool io128 = p->io_complex128 != 0;
   if (rc == HB_OK && pl.mode == HB_SOS_POLY) {
-    const size_t mbytes = sizeof(float2) * (size_t)a.B * a.ntiles * tb.num_groups * pl.P * a.nrx * a.ntx;
+    const size_t mbytes = sizeof(float2) * (size_t)a.B * a.nwin * tb.num_groups * pl.P * a.nrx * a.ntx;
     cudaError_t e = cudaMallocAsync((void**)&ws.moments, mbytes, st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync(moments)");
     a.moments = ws.moments;

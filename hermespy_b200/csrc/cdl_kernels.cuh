@@ -241,7 +241,8 @@ __device__ __forceinline__ double2 ray_entry(const CdlArgs& a, int b, int t, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5b: moments of the group matrices about the tile centre.  grid = B * ntiles * G, 128 threads over (i, j).
+// K5b: moments of the group matrices about the centre of the Taylor window (a.ptile samples).  grid = B * nwin * G,
+// 128 threads over (i, j).
 //   M[g][p][i][j] = sum_{t in g} alpha_t e^{j w_t (centre - k_g)} (j w_t tile)^p / p! * u_t[i] v_t[j]
 template <int P>
 __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
@@ -249,11 +250,11 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
   __shared__ float ut[64];
   const int G = tb.num_groups;
   const int bq = blockIdx.x / G, g = blockIdx.x - bq * G;
-  const int b = bq / a.ntiles, q = bq - b * a.ntiles;
+  const int b = bq / a.nwin, q = bq - b * a.nwin;
   const int t0 = tb.group_start[g], t1 = tb.group_start[g + 1];
-  const double shift = (double)q * a.tile + 0.5 * a.tile - (double)tb.group_delay[g];
+  const double shift = (double)q * a.ptile + 0.5 * a.ptile - (double)tb.group_delay[g];
   const int nij = a.nrx * a.ntx;
-  float2* out = a.moments + ((((size_t)b * a.ntiles + q) * G + g) * P) * nij;
+  float2* out = a.moments + ((((size_t)b * a.nwin + q) * G + g) * P) * nij;
   for (int ij0 = 0; ij0 < nij; ij0 += blockDim.x) {
     const int ij = ij0 + threadIdx.x;
     const int i = ij / a.ntx, j = ij - i * a.ntx;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
         sincospi(2.0 * turns, &s, &c);
         const double2 al = a.alpha[(size_t)b * a.Rt + t];
         beta[threadIdx.x] = make_float2((float)(al.x * c - al.y * s), (float)(al.x * s + al.y * c));
-        ut[threadIdx.x] = (float)(w * (double)a.tile);
+        ut[threadIdx.x] = (float)(w * (double)a.ptile);
       }
       __syncthreads();
       if (ij < nij) {
@@ -298,6 +299,112 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
     if (ij < nij) {
 #pragma unroll
       for (int p = 0; p < P; ++p) out[(size_t)p * nij + ij] = make_float2(accr[p], acci[p]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b, second form: one CTA per (link, delay group) forms the moments of ALL Taylor windows of the frame.
+//   gamma[t][q][p] = alpha_t e^{j w_t (centre_q - k_g)} (j w_t tile)^p / p!     (phase reduced in FP64, stored FP32)
+//   M[q][g][p][i][j] = sum_{t in g} gamma[t][q][p] * (u_t[i] v_t[j])           (FP32 FMA pipe)
+// The steering phases u, v are converted to FP32 once per term and CTA (they are unit-modulus, so the product keeps
+// 2^-24 relative accuracy) and the ray product u_i v_j is formed once per term instead of once per (term, window).
+// Windows are a.ptile samples long (a multiple of the K6 tile).  grid = B * G, 128 threads over (i, j); dynamic shared memory: gamma[kMomTerms][kMomWin][P] | us | vs.
+constexpr int kMomTerms = 32;  // ray terms staged per pass
+constexpr int kMomWin = 8;     // Taylor windows accumulated per pass
+
+template <int P>
+__global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
+  extern __shared__ __align__(16) unsigned char mom_smem[];
+  float2* gam = reinterpret_cast<float2*>(mom_smem);                 // [kMomTerms][kMomWin][P]
+  float2* us = gam + kMomTerms * kMomWin * P;                         // [kMomTerms][nrx * rank]
+  float2* vs = us + kMomTerms * a.nrx * a.rank;                       // [kMomTerms][ntx * rank]
+  const int G = tb.num_groups;
+  const int b = blockIdx.x / G, g = blockIdx.x - b * G;
+  const int t0 = tb.group_start[g], t1 = tb.group_start[g + 1];
+  const int nij = a.nrx * a.ntx;
+  const int nu = a.nrx * a.rank, nv = a.ntx * a.rank;
+  const int tid = threadIdx.x;
+  for (int q0 = 0; q0 < a.nwin; q0 += kMomWin) {
+    const int nq = min(kMomWin, a.nwin - q0);
+    for (int ij0 = 0; ij0 < nij; ij0 += 128) {
+      const int ij = ij0 + tid;
+      const int i = ij / a.ntx, j = ij - i * a.ntx;
+      float2 acc[kMomWin][P];
+#pragma unroll
+      for (int q = 0; q < kMomWin; ++q)
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[q][p] = make_float2(0.f, 0.f);
+      for (int c0 = t0; c0 < t1; c0 += kMomTerms) {
+        const int nc = min(kMomTerms, t1 - c0);
+        __syncthreads();
+        for (int e = tid; e < nc * nq; e += 128) {
+          const int k = e / nq, q = e - k * nq;
+          const int t = tb.term_order[c0 + k];
+          const double w = a.w[(size_t)b * a.Rt + t];
+          const double shift = (double)(q0 + q) * a.ptile + 0.5 * a.ptile - (double)tb.group_delay[g];
+          double turns = w * shift * kInvTwoPi;
+          turns -= rint(turns);
+          double sn, cs;
+          sincospi(2.0 * turns, &sn, &cs);
+          const double2 al = a.alpha[(size_t)b * a.Rt + t];
+          float tr = (float)(al.x * cs - al.y * sn), ti = (float)(al.x * sn + al.y * cs);
+          const float ut = (float)(w * (double)a.ptile);
+          float2* dst = gam + (k * kMomWin + q) * P;
+          dst[0] = make_float2(tr, ti);
+#pragma unroll
+          for (int p = 1; p < P; ++p) {
+            const float f = ut * (1.0f / (float)p);
+            const float nr = -ti * f, ni = tr * f;
+            tr = nr;
+            ti = ni;
+            dst[p] = make_float2(tr, ti);
+          }
+        }
+        for (int e = tid; e < nc * nu; e += 128) {
+          const int k = e / nu, c = e - k * nu;
+          const double2 v = a.u[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nu + c];
+          us[k * nu + c] = make_float2((float)v.x, (float)v.y);
+        }
+        for (int e = tid; e < nc * nv; e += 128) {
+          const int k = e / nv, c = e - k * nv;
+          const double2 v = a.v[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nv + c];
+          vs[k * nv + c] = make_float2((float)v.x, (float)v.y);
+        }
+        __syncthreads();
+        if (ij < nij) {
+          for (int k = 0; k < nc; ++k) {
+            float2 uv;
+            if (a.rank == 1) {
+              const float2 u0 = us[k * nu + i], v0 = vs[k * nv + j];
+              uv = make_float2(u0.x * v0.x - u0.y * v0.y, u0.x * v0.y + u0.y * v0.x);
+            } else {
+              const float2 u0 = us[k * nu + 2 * i], v0 = vs[k * nv + 2 * j];
+              const float2 u1 = us[k * nu + 2 * i + 1], v1 = vs[k * nv + 2 * j + 1];
+              uv = make_float2(u0.x * v0.x - u0.y * v0.y + u1.x * v1.x - u1.y * v1.y,
+                               u0.x * v0.y + u0.y * v0.x + u1.x * v1.y + u1.y * v1.x);
+            }
+            const float2* gk = gam + k * kMomWin * P;
+#pragma unroll
+            for (int q = 0; q < kMomWin; ++q) {
+              if (q < nq) {  // CTA-uniform
+#pragma unroll
+                for (int p = 0; p < P; ++p) cmac<float>(acc[q][p], gk[q * P + p], uv);
+              }
+            }
+          }
+        }
+      }
+      if (ij < nij) {
+#pragma unroll
+        for (int q = 0; q < kMomWin; ++q) {
+          if (q < nq) {
+            float2* out = a.moments + ((((size_t)b * a.nwin + q0 + q) * G + g) * P) * nij + ij;
+#pragma unroll
+            for (int p = 0; p < P; ++p) out[(size_t)p * nij] = acc[q][p];
+          }
+        }
+      }
     }
   }
 }

@@ -41,12 +41,13 @@ struct CdlArgs {
   double* w;       // [B, Rt] rad / sample
   double2* u;      // [B, Rt, Nrx, rank]   receive steering phases (x element polarization when rank == 2)
   double2* v;      // [B, Rt, Ntx, rank]   transmit steering phases (x amp J F_tx when rank == 2)
-  float2* moments; // [B, ntiles, G, P, Nrx, Ntx]
+  float2* moments; // [B, nwin, G, P, Nrx, Ntx]
   double wavelength_factor;  // fc / c0
   double fs;
   double los_amp;
   int B, ntx, nrx, T, D, Rn, Rt;
   int tile, ntiles, Dpad, P;
+  int ptile, nwin;  // Taylor window length (a multiple of tile) and windows per frame: moments are [B, nwin, G, P, Nrx, Ntx]
   int rx0, nrx_chunk;
 };
 

@@ -1,6 +1,7 @@
 // K6 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM), sm_100a only:
 //   y[i, m] = sum_p r(m)^p  sum_g sum_j  M[g, p, i, j] x[j, m - k_g]          (cluster_delay_lines.py:526-558)
-// as ONE real-valued GEMM per Taylor window of 128 MT output samples with the delay groups folded into K:
+// as ONE real-valued GEMM per tile of 128 MT output samples (the Taylor window of the moments is one or several tiles)
+// with the delay groups folded into K:
 //   A (M = 128 time rows, K = (g, j, re/im)):  A[m, (g, j, c)] = x_c[j, m - k_g]
 //   B (N = (p, i, re/im) rows, same K):        Re row = [Mr, -Mi],  Im row = [Mi, Mr]
 //   D[m, (p, i, c')] in TMEM; epilogue = Horner over p in the window coordinate r, then one complex store per thread.
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
 #pragma unroll
         for (int it = 0; it < kCuMaxAIt; ++it)
           load_a(xb, q * S::TILE - a.Dpad, 4 * s + 2 * c, ptid + kCuProducers * it, xa[c][it][0], xa[c][it][1]);
-      const float2* mq = a.moments + (((size_t)b * a.ntiles + q) * G) * P * nij;
+      const float2* mq = a.moments + (((size_t)b * a.nwin + (q * S::TILE) / a.ptile) * G) * P * nij;
 #pragma unroll
       for (int it = 0; it < kCuMaxBIt; ++it) mb[it] = load_b(mq, 4 * s, ptid + kCuProducers * it);
     };
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
             load_a(xb, q * S::TILE - a.Dpad, 4 * s + 2 * c, r, v0, v1);
             store_a(sA, c, r, v0, v1);
           }
-        const float2* mq = a.moments + (((size_t)b * a.ntiles + q) * G) * P * nij;
+        const float2* mq = a.moments + (((size_t)b * a.nwin + (q * S::TILE) / a.ptile) * G) * P * nij;
         for (int e = ptid + kCuProducers * kCuMaxBIt; e < btasks; e += kCuProducers) store_b(sB, e, load_b(mq, 4 * s, e));
       }
     };
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
     }
   } else {
     // ================================ epilogue: warp w reads TMEM lanes 32 w .. 32 w + 31 ============================
-    const float inv_tile = 1.0f / (float)S::TILE, half = 0.5f * (float)S::TILE;
+    const float inv_win = 1.0f / (float)a.ptile, half = 0.5f * (float)a.ptile;
     uint32_t ic = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
       const int b = item / a.ntiles, q = item - b * a.ntiles;
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
           const int il = mt * 128 + warp * 32 + lane;
           if (il < valid) {
             const int m = q * S::TILE + il;
-            const float r = ((float)il - half) * inv_tile;
+            const float r = ((float)(m % a.ptile) - half) * inv_win;  // coordinate inside the Taylor window
 #pragma unroll
             for (int i = 0; i < NRX; ++i) {
               if (i < a.nrx_chunk) {

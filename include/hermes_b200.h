@@ -231,7 +231,7 @@ typedef struct hb_cdl_plan_info {
   int32_t launches;
   double error_bound;
   int32_t variant;     /* hb_cdl_variant that runs (POLY only): GATHER or UMMA */
-  int32_t poly_tile;   /* == tile */
+  int32_t poly_tile;   /* samples per Taylor window of the moments: == tile (GATHER), 1/2/4/8 tiles (UMMA) */
 } hb_cdl_plan_info;
 
 HB_API int hb_cdl_plan(const hb_cdl_problem* p, hb_cdl_plan_info* info);
