@@ -15,6 +15,8 @@
 // a_rx J a_tx^T, is rank one: H_t = alpha_t u_t v_t^T with u, v pure phases.  Terms sharing a delay index are summed
 // into one matrix per delay group before touching the signal, which removes the ray count from the per-sample cost.
 #pragma once
+#include <type_traits>
+
 #include "cdl_types.cuh"
 
 namespace hb {
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
 // 2^-24 relative accuracy) and the ray product u_i v_j is formed once per term instead of once per (term, window).
 // Windows are a.ptile samples long (a multiple of the K6 tile).  grid = B * G, 128 threads over (i, j); dynamic shared memory: gamma[kMomTerms][kMomWin][P] | us | vs.
 constexpr int kMomTerms = 32;  // ray terms staged per pass
-constexpr int kMomWin = 8;     // Taylor windows accumulated per pass
+constexpr int kMomWin = 4;     // Taylor windows accumulated per pass
 
 template <int P>
 __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
@@ -373,25 +375,31 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
         }
         __syncthreads();
         if (ij < nij) {
-          for (int k = 0; k < nc; ++k) {
-            float2 uv;
-            if (a.rank == 1) {
-              const float2 u0 = us[k * nu + i], v0 = vs[k * nv + j];
-              uv = make_float2(u0.x * v0.x - u0.y * v0.y, u0.x * v0.y + u0.y * v0.x);
-            } else {
-              const float2 u0 = us[k * nu + 2 * i], v0 = vs[k * nv + 2 * j];
-              const float2 u1 = us[k * nu + 2 * i + 1], v1 = vs[k * nv + 2 * j + 1];
-              uv = make_float2(u0.x * v0.x - u0.y * v0.y + u1.x * v1.x - u1.y * v1.y,
-                               u0.x * v0.y + u0.y * v0.x + u1.x * v1.y + u1.y * v1.x);
-            }
-            const float2* gk = gam + k * kMomWin * P;
+          auto accumulate = [&](auto nq_tag) {  // fully unrolled over the windows of this pass
+            constexpr int NQ = decltype(nq_tag)::value;
+            for (int k = 0; k < nc; ++k) {
+              float2 uv;
+              if (a.rank == 1) {
+                const float2 u0 = us[k * nu + i], v0 = vs[k * nv + j];
+                uv = make_float2(u0.x * v0.x - u0.y * v0.y, u0.x * v0.y + u0.y * v0.x);
+              } else {
+                const float2 u0 = us[k * nu + 2 * i], v0 = vs[k * nv + 2 * j];
+                const float2 u1 = us[k * nu + 2 * i + 1], v1 = vs[k * nv + 2 * j + 1];
+                uv = make_float2(u0.x * v0.x - u0.y * v0.y + u1.x * v1.x - u1.y * v1.y,
+                                 u0.x * v0.y + u0.y * v0.x + u1.x * v1.y + u1.y * v1.x);
+              }
+              const float2* gk = gam + k * kMomWin * P;
 #pragma unroll
-            for (int q = 0; q < kMomWin; ++q) {
-              if (q < nq) {  // CTA-uniform
+              for (int q = 0; q < NQ; ++q)
 #pragma unroll
                 for (int p = 0; p < P; ++p) cmac<float>(acc[q][p], gk[q * P + p], uv);
-              }
             }
+          };
+          switch (nq) {  // CTA-uniform
+            case 1: accumulate(std::integral_constant<int, 1>{}); break;
+            case 2: accumulate(std::integral_constant<int, 2>{}); break;
+            case 3: accumulate(std::integral_constant<int, 3>{}); break;
+            default: accumulate(std::integral_constant<int, 4>{}); break;
           }
         }
       }

@@ -39,7 +39,7 @@ namespace hb {
 constexpr int kCuThreads = 512;
 constexpr int kCuProducers = 256;
 constexpr int kCuMaxAIt = 3;  // register-prefetched rows per producer thread and antenna pair (tile + Dpad <= 768)
-constexpr int kCuMaxBIt = 4;  // register-prefetched (group, p, i, antenna pair) blocks per producer thread (2 G P NRX <= 1024)
+constexpr int kCuMaxBIt = 6;  // register-prefetched (group, antenna pair, row) entries per producer thread (4 G P NRX <= 1536)
 
 template <int NRX, int P>
 struct CuShape {
@@ -140,11 +140,13 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
     const int ptid = tid - (kCuThreads - kCuProducers);
     float2 xa[2][kCuMaxAIt][2];
     float4 mb[kCuMaxBIt];
-    const int btasks = 2 * G * P * NRX;  // (group, p, i, antenna pair) blocks of the B operand per stage
+    const int btasks = 2 * G * S::N1;  // (group, antenna pair, row) entries of the B operand per stage
     // x[b, ja .. ja + 1, n0 + r] of row r (zero outside the frame / past the last antenna)
-    auto load_a = [&](const IO* xb, int n0, int ja, int r, float2& v0, float2& v1) {
+    // rows the MMAs of window q read: its M-tiles inside the frame plus the delay halo (the last window of a frame is short)
+    auto rows_needed = [&](int q) { return ((min(S::TILE, Tout - q * S::TILE) + 127) & ~127) + a.Dpad; };
+    auto load_a = [&](const IO* xb, int n0, int ja, int r, int wn, float2& v0, float2& v1) {
       const int n = n0 + r;
-      const bool ok = r < W && n >= 0 && n < a.T;
+      const bool ok = r < wn && n >= 0 && n < a.T;
       v0 = make_float2(0.f, 0.f);
       v1 = v0;
       if (ok && ja < a.ntx) v0 = to_c32(ldg_stream(xb + (size_t)ja * a.T + n));
@@ -160,10 +162,11 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
       sts128(o, h0, h1, h2, h3);
       sts128(o + 2u * a_plane, l0, l1, l2, l3);
     };
-    // moments M[g, p, rx0 + i, j .. j + 1] of task e = ((g P + p) NRX + i) 2 + c, j = j0 + 2 c
+    // B task e = (g, c, row): operand row (p, i, re/im) of antenna pair c of delay group g; the 32 lanes of a warp write 32
+    // consecutive 16-byte rows (conflict-free); the two rows of one (p, i) read the same pair of moments
     auto load_b = [&](const float2* mq, int j0, int e) {
-      const int c = e & 1, pi = (e >> 1) % (P * NRX), g = (e >> 1) / (P * NRX);
-      const int p = pi / NRX, i = pi - p * NRX, j = j0 + 2 * c;
+      const int row = e % S::N1, c = (e / S::N1) & 1, g = e / (2 * S::N1);
+      const int pi = row >> 1, p = pi / NRX, i = pi - p * NRX, j = j0 + 2 * c;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g < G && i < a.nrx_chunk) {
         const float2* src = mq + (size_t)(g * P + p) * nij + (size_t)(a.rx0 + i) * a.ntx + j;
@@ -181,26 +184,28 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
       return v;
     };
     auto store_b = [&](uint32_t sB, int e, float4 m) {
-      const int c = e & 1, pi = (e >> 1) % (P * NRX), g = (e >> 1) / (P * NRX);
-      float hr0, hi0, hr1, hi1, lr0, li0, lr1, li1;
-      split_tf32(m.x, hr0, lr0);
-      split_tf32(m.y, hi0, li0);
-      split_tf32(m.z, hr1, lr1);
-      split_tf32(m.w, hi1, li1);
-      const uint32_t o = sB + (uint32_t)g * b_group + (uint32_t)c * b_chunk + (uint32_t)(2 * pi) * 16u;
-      sts128(o, hr0, -hi0, hr1, -hi1);       // Re row:  Mr x_r - Mi x_i
-      sts128(o + 16u, hi0, hr0, hi1, hr1);   // Im row:  Mi x_r + Mr x_i
-      sts128(o + (uint32_t)S::N1P * 16u, lr0, -li0, lr1, -li1);
-      sts128(o + (uint32_t)S::N1P * 16u + 16u, li0, lr0, li1, lr1);
+      const int row = e % S::N1, c = (e / S::N1) & 1, g = e / (2 * S::N1);
+      // Re row: [Mr, -Mi] (Mr x_r - Mi x_i);  Im row: [Mi, Mr] (Mi x_r + Mr x_i)
+      const bool im = row & 1;
+      const float k0 = im ? m.y : m.x, k1 = im ? m.x : -m.y, k2 = im ? m.w : m.z, k3 = im ? m.z : -m.w;
+      float h0, h1, h2, h3, l0, l1, l2, l3;
+      split_tf32(k0, h0, l0);
+      split_tf32(k1, h1, l1);
+      split_tf32(k2, h2, l2);
+      split_tf32(k3, h3, l3);
+      const uint32_t o = sB + (uint32_t)g * b_group + (uint32_t)c * b_chunk + (uint32_t)row * 16u;
+      sts128(o, h0, h1, h2, h3);
+      sts128(o + (uint32_t)S::N1P * 16u, l0, l1, l2, l3);
     };
     auto prefetch = [&](int item, int s) {
       const int b = item / a.ntiles, q = item - b * a.ntiles;
       const IO* xb = reinterpret_cast<const IO*>(a.x) + (size_t)b * a.ntx * a.T;
+      const int wn = rows_needed(q);
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int it = 0; it < kCuMaxAIt; ++it)
-          load_a(xb, q * S::TILE - a.Dpad, 4 * s + 2 * c, ptid + kCuProducers * it, xa[c][it][0], xa[c][it][1]);
+          load_a(xb, q * S::TILE - a.Dpad, 4 * s + 2 * c, ptid + kCuProducers * it, wn, xa[c][it][0], xa[c][it][1]);
       const float2* mq = a.moments + (((size_t)b * a.nwin + (q * S::TILE) / a.ptile) * G) * P * nij;
 #pragma unroll
       for (int it = 0; it < kCuMaxBIt; ++it) mb[it] = load_b(mq, 4 * s, ptid + kCuProducers * it);
@@ -208,12 +213,13 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
     auto store = [&](int slot, int item, int s) {
       const uint32_t sA = smem0 + (uint32_t)slot * stage_bytes;
       const uint32_t sB = sA + a_bytes;
+      const int wn = rows_needed(item % a.ntiles);
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int it = 0; it < kCuMaxAIt; ++it) {
           const int r = ptid + kCuProducers * it;
-          if (r < W) store_a(sA, c, r, xa[c][it][0], xa[c][it][1]);
+          if (r < wn) store_a(sA, c, r, xa[c][it][0], xa[c][it][1]);
         }
 #pragma unroll
       for (int it = 0; it < kCuMaxBIt; ++it) {
@@ -221,13 +227,13 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
         if (e < btasks) store_b(sB, e, mb[it]);
       }
       // long delay spreads / many (group, order, antenna) blocks: the part beyond the register prefetch is loaded here
-      if (W > kCuProducers * kCuMaxAIt || btasks > kCuProducers * kCuMaxBIt) {
+      if (wn > kCuProducers * kCuMaxAIt || btasks > kCuProducers * kCuMaxBIt) {
         const int b = item / a.ntiles, q = item - b * a.ntiles;
         const IO* xb = reinterpret_cast<const IO*>(a.x) + (size_t)b * a.ntx * a.T;
         for (int c = 0; c < 2; ++c)
-          for (int r = ptid + kCuProducers * kCuMaxAIt; r < W; r += kCuProducers) {
+          for (int r = ptid + kCuProducers * kCuMaxAIt; r < wn; r += kCuProducers) {
             float2 v0, v1;
-            load_a(xb, q * S::TILE - a.Dpad, 4 * s + 2 * c, r, v0, v1);
+            load_a(xb, q * S::TILE - a.Dpad, 4 * s + 2 * c, r, wn, v0, v1);
             store_a(sA, c, r, v0, v1);
           }
         const float2* mq = a.moments + (((size_t)b * a.nwin + (q * S::TILE) / a.ptile) * G) * P * nij;
