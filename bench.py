@@ -428,7 +428,7 @@ class Workload:
         if prof["tdl_poly"]["launches"]:
             if prof["spatial_gemm"]["launches"] and prof["spatial_gemm"]["ms"] > prof["tdl_poly"]["ms"]:
                 return "spatial_gemm", "spatial_gemm_3xtf32_kernel", "hbm"
-            name = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel", "tma": "tdl_tma_kernel"}.get(
+            name = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel", "tma": "tdl_tma_kernel", "siso": "tdl_siso_kernel"}.get(
                 info.get("variant"), "tdl_poly_kernel")
             return "tdl_poly", name, "hbm"
         return "tdl_direct", "tdl_direct_kernel", "hbm"
@@ -778,7 +778,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--no-simulation", action="store_true", help="skip the Simulation.run() drops/s record")
-    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "poly_tma", "poly_fused", "direct"],
+    ap.add_argument("--sos-mode", default="auto", choices=["auto", "poly", "poly_window", "poly_gather", "poly_tma", "poly_fused", "poly_siso", "direct"],
                     help="kernel selection (profiling / A-B runs); the default lets the planner choose")
     args = ap.parse_args()
     if args.impl == "reference":

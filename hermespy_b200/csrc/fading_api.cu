@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "fading_fused.cuh"
+#include "fading_siso.cuh"
 #include "fading_tma.cuh"
 
 namespace hb {
@@ -40,7 +41,7 @@ static int build_delay_table(const hb_fading_problem* p, DelayTable* dt) {
     set_error("unknown precision %d", p->precision);
     return HB_ERR_INVALID;
   }
-  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_FUSED) {
+  if (p->sos_mode < HB_SOS_AUTO || p->sos_mode > HB_SOS_POLY_SISO) {
     set_error("unknown sos_mode %d", p->sos_mode);
     return HB_ERR_INVALID;
   }
@@ -235,11 +236,18 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
   pl->threads = kThreads;
   pl->large_halo = 0;
   pl->lin = 0;
-  const bool window = poly && p->sos_mode != HB_SOS_POLY_GATHER && window_eligible(dt, pl->ntx_tpl);
+  // one antenna per side: the time-packed kernel (fading_siso.cuh) on request.  Measured on C5 (profiles/r02_siso.md):
+  // 0.56 ms against 0.535 ms for the window kernel and 0.71 ms for the TMA kernel, so AUTO / POLY take the WINDOW kernel
+  // for 1 x 1 links (the persistent TMA kernel's 12 warps cannot amortize the walk's bookkeeping over one antenna).
+  const bool one_by_one = p->num_tx == 1 && p->num_rx == 1;
+  const bool siso = poly && one_by_one && p->sos_mode == HB_SOS_POLY_SISO;
+  const bool window = poly && p->sos_mode != HB_SOS_POLY_GATHER && p->sos_mode != HB_SOS_POLY_SISO &&
+                      window_eligible(dt, pl->ntx_tpl);
   // large arrays (16 x 16 and more) run the persistent kernel in z mode, chunks of 4 antennas, then the tensor-core GEMM
   const int tpl_tma = (p->num_tx >= 16 && p->num_rx >= 16) ? 4 : pl->ntx_tpl;
   const bool tma_shape = poly && allow_tma && p->sos_mode != HB_SOS_POLY_GATHER && p->sos_mode != HB_SOS_POLY_WINDOW &&
-                         tma_shape_ok(p, dt, tpl_tma);
+                         p->sos_mode != HB_SOS_POLY_SISO && tma_shape_ok(p, dt, tpl_tma) &&
+                         !(one_by_one && p->sos_mode != HB_SOS_POLY_TMA && window_eligible(dt, pl->ntx_tpl));
   if (f64 && (p->sos_mode == HB_SOS_POLY || p->sos_mode == HB_SOS_POLY_GATHER)) {
     set_error("HB_F64 parity mode only supports direct evaluation");
     return HB_ERR_UNSUPPORTED;
@@ -255,9 +263,11 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
         // window variant: CTA tiles are 32/64/128 threads x R outputs and must divide the Taylor window, so the
         // window stays a power of two (not longer than the padded frame)
         int tile = std::min(tile0, tile_cap);
-        if (window || tma_shape) {
+        if (window || tma_shape || siso) {
+          const int floor_tile = siso ? 512 : kThreads;  // the single-antenna kernel's smallest tile is 512 outputs
+          if (tile0 < floor_tile) continue;
           tile = tile0;
-          while (tile > kThreads && tile / 2 >= Tout) tile /= 2;
+          while (tile > floor_tile && tile / 2 >= Tout) tile /= 2;
         }
         if (!window && !tma_shape && poly_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx) > kSmemSoftLimit &&
             tile > kThreads)
@@ -295,7 +305,18 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
       // on its accumulator, ONE kernel (fading_fused.cuh).  Not what AUTO picks: on B200 the shared-memory pipe (MMA operand
       // reads + history-ring reads) makes it 8 % slower than the two-kernel path (profiles/r02_c4.md).
       const int dmax_f = dt.group_delay[dt.num_groups - 1];
-      if (p->sos_mode == HB_SOS_POLY_FUSED && !p->io_complex128 && p->num_tx >= 16 && p->num_rx >= 16 &&
+      int siso_tile = std::min(2048, pl->poly_tile);
+      while (siso_tile > 512 && siso_tile / 2 >= Tout) siso_tile /= 2;
+      const size_t siso_smem = siso_smem_bytes(siso_tile, pl->Dpad, dt.num_groups, pl->P);
+      if (siso && pl->poly_tile >= 512 && siso_smem <= kSmemHardLimit) {
+        pl->variant = HB_VARIANT_SISO;
+        pl->tile = siso_tile;
+        pl->threads = kSisoThreads;
+        pl->smem = siso_smem;
+      } else if (p->sos_mode == HB_SOS_POLY_SISO) {
+        set_error("HB_SOS_POLY_SISO needs one antenna per side and a Taylor window of at least 512 samples");
+        return HB_ERR_UNSUPPORTED;
+      } else if (p->sos_mode == HB_SOS_POLY_FUSED && !p->io_complex128 && p->num_tx >= 16 && p->num_rx >= 16 &&
           p->num_tx <= kGemmMaxAnt && p->num_rx <= kGemmMaxAnt && dmax_f <= kFusedMaxDelay && dt.num_groups <= kFusedMaxGroups &&
           pl->P <= 4 && pl->poly_tile % kGemmTileSamples == 0) {
         pl->fused = 1;
@@ -454,6 +475,8 @@ static int launch_chunk_tma(const Plan& pl, const FadingArgs& a, const TmaPlan& 
 static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& a, const DelayTable& dt,
                         cudaStream_t st) {
   ProfileScope prof(pl.mode == HB_SOS_POLY ? KIND_TDL_POLY : KIND_TDL_DIRECT, st);
+  if (pl.mode == HB_SOS_POLY && pl.variant == HB_VARIANT_SISO)
+    return launch_tdl_siso(pl.P, pl.tile, io128, a, dt, pl.poly_tile, pl.npoly, pl.smem, st);
   if (pl.mode == HB_SOS_POLY && pl.variant == HB_VARIANT_WINDOW) {
     switch (pl.ntx_tpl) {
       case 1: return launch_tdl_window<1>(pl.P, io128, pl.large_halo != 0, pl.lin != 0, a, pl.wp, pl.threads, pl.smem, st);

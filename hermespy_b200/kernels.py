@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import HB_F32, HB_F64, HB_SOS_AUTO, HB_SOS_DIRECT, HB_SOS_POLY, FadingPlanInfo, FadingProblem
 
 _PRECISION = {"f32": HB_F32, "f64": HB_F64, HB_F32: HB_F32, HB_F64: HB_F64}
-_SOS_MODE = {"auto": HB_SOS_AUTO, "poly": HB_SOS_POLY, "direct": HB_SOS_DIRECT, "poly_gather": 3, "poly_window": 4, "poly_tma": 5, "poly_fused": 6}
+_SOS_MODE = {"auto": HB_SOS_AUTO, "poly": HB_SOS_POLY, "direct": HB_SOS_DIRECT, "poly_gather": 3, "poly_window": 4, "poly_tma": 5, "poly_fused": 6, "poly_siso": 7}
 _SOS_NAME = {HB_SOS_POLY: "poly", HB_SOS_DIRECT: "direct"}
 
 
@@ -219,7 +219,7 @@ def _problem(
 def _info_dict(info: FadingPlanInfo) -> dict:
     d = info.as_dict()
     d["mode"] = _SOS_NAME.get(d["mode"], d["mode"])
-    d["variant"] = ("gather", "window", "tma", "fused")[d["variant"]] if d["mode"] == "poly" else None
+    d["variant"] = ("gather", "window", "tma", "fused", "siso")[d["variant"]] if d["mode"] == "poly" else None
     return d
 
 

@@ -73,15 +73,18 @@ typedef enum hb_sos_mode {
   HB_SOS_POLY_WINDOW = 4, /* POLY, forcing the cp.async-staged sliding-window kernel where it is eligible  */
   HB_SOS_POLY_TMA = 5,    /* POLY, preferring the persistent TMA-pipelined window kernel (what AUTO/POLY pick
                              for complex64 frames with T % 16 == 0, T + D >= 2048 and delays below 128 samples) */
-  HB_SOS_POLY_FUSED = 6   /* POLY, large arrays (16..64 antennas per side): the single-kernel GEMM + delay-line variant
+  HB_SOS_POLY_FUSED = 6,  /* POLY, large arrays (16..64 antennas per side): the single-kernel GEMM + delay-line variant
                              (fading_fused.cuh).  Measured slower than the two-kernel path on B200 (profiles/r02_c4.md),
                              therefore not what AUTO picks; kept selectable */
+  HB_SOS_POLY_SISO = 7    /* POLY, forcing the single-antenna time-packed kernel (1 x 1 links; measured level with the window
+                             kernel that AUTO picks there, profiles/r02_siso.md) */
 } hb_sos_mode;
 
 typedef enum hb_poly_variant {
   HB_VARIANT_GATHER = 0, /* tdl_poly_kernel: one shared-memory read per (delay group, antenna, output)  */
   HB_VARIANT_WINDOW = 1, /* tdl_window_kernel: register sliding window along the delay axis            */
   HB_VARIANT_TMA = 2,    /* tdl_tma_kernel: the same walk, persistent CTAs fed by TMA (swizzled time-pair loads) */
+  HB_VARIANT_SISO = 4,   /* tdl_siso_kernel (1 x 1 links): planar staging, FFMA2 packed over pairs of consecutive outputs */
   HB_VARIANT_FUSED = 3   /* fused_gemm_tdl_kernel (16..64 antennas per side): spatial GEMM on tcgen05, delay lines on its
                             accumulator through a shared-memory history ring -- the intermediate never reaches HBM */
 } hb_poly_variant;

@@ -60,7 +60,18 @@ def test_planner_kernel_variants():
     """Which POLY kernel the planner picks (host logic, no GPU): the persistent TMA kernel for complex64 frames of whole
     16-sample rows and >= 2048 outputs with delays below 128 samples, the cp.async window kernel otherwise when its walk
     pays, the gather kernel for the rest; large arrays add the tensor-core GEMM."""
-    V = {0: "gather", 1: "window", 2: "tma", 3: "fused"}
+    V = {0: "gather", 1: "window", 2: "tma", 3: "fused", 4: "siso"}
+    st, info = _plan(num_tx=1, num_rx=1, sos_mode="poly_siso")  # one antenna per side: the time-packed kernel on request
+    assert st == 0 and V[info.variant] == "siso" and info.tile == 2048 and info.launches == 2
+    st, info = _plan(num_tx=1, num_rx=1, num_samples=500, io128=True, sos_mode="poly_siso")
+    assert st == 0 and V[info.variant] == "siso" and info.tile == 1024  # 544 outputs: one CTA
+    dense1 = np.arange(0, 45, 3).astype(np.int32)
+    st, info = _plan(num_tx=1, num_rx=1, num_taps=dense1.size, tap_delay=dense1)  # 1 x 1 AUTO: the window kernel, not TMA
+    assert st == 0 and V[info.variant] == "window"
+    st, info = _plan(num_tx=1, num_rx=1, num_taps=dense1.size, tap_delay=dense1, sos_mode="poly_tma")
+    assert st == 0 and V[info.variant] == "tma"
+    st, info = _plan(num_tx=2, num_rx=1, sos_mode="poly_siso")
+    assert st == _lib.HB_ERR_UNSUPPORTED
     st, info = _plan()  # C2 shape, three taps in 0..44
     assert st == 0 and V[info.variant] == "tma" and info.tile == 1024 and info.poly_tile % 1024 == 0
     st, info = _plan(sos_mode="poly_window")
@@ -121,8 +132,8 @@ def test_planner_fuzz_never_crashes_and_respects_its_own_limits():
     """Host logic: random shapes / delay tables / Doppler through hb_fading_plan -- every answer is a status code, and an
     accepted plan is self-consistent (tile sizes, Taylor window multiples, launch counts, error bound)."""
     rng = np.random.default_rng(2026)
-    V = {0: "gather", 1: "window", 2: "tma", 3: "fused"}
-    accepted = {"gather": 0, "window": 0, "tma": 0, "fused": 0, "direct": 0}
+    V = {0: "gather", 1: "window", 2: "tma", 3: "fused", 4: "siso"}
+    accepted = {"gather": 0, "window": 0, "tma": 0, "fused": 0, "siso": 0, "direct": 0}
     for _ in range(400):
         ntx, nrx = int(rng.choice([1, 2, 3, 4, 5, 8, 10, 16, 33, 64, 70])), int(rng.choice([1, 2, 4, 7, 8, 16, 40, 64, 66]))
         T = int(rng.choice([0, 1, 37, 500, 1024, 2048, 4100, 15344, 16384, 1 << 20]))
@@ -133,11 +144,14 @@ def test_planner_fuzz_never_crashes_and_respects_its_own_limits():
         delays[-1] = dmax
         delays = np.sort(delays).astype(np.int32)
         omega = float(rng.choice([0.0, 1e-7, 3.3e-6, 1e-4, 1e-2, 0.5]))
+        sos_mode = str(rng.choice(["auto", "auto", "poly", "direct", "poly_window", "poly_gather", "poly_tma", "poly_fused",
+                                   "poly_fused", "poly_siso"]))
+        if sos_mode == "poly_siso" and rng.random() < 0.7:
+            ntx = nrx = 1  # the only shape that mode takes
         st, info = _plan(batch=int(rng.integers(0, 5000)), num_tx=ntx, num_rx=nrx, num_samples=T, max_delay=dmax,
                          num_taps=L, num_sinusoids=int(rng.choice([0, 1, 8, 20])), omega_max=omega, tap_delay=delays,
                          io128=bool(rng.random() < 0.3), precision=str(rng.choice(["f32", "f32", "f64"])),
-                         sos_mode=str(rng.choice(["auto", "auto", "poly", "direct", "poly_window", "poly_gather", "poly_tma",
-                                                  "poly_fused", "poly_fused"])))
+                         sos_mode=sos_mode)
         assert st in (0, _lib.HB_ERR_INVALID, _lib.HB_ERR_UNSUPPORTED), st
         if st != 0:
             assert _lib.load().hb_last_error()  # a refused problem always says why
@@ -150,6 +164,8 @@ def test_planner_fuzz_never_crashes_and_respects_its_own_limits():
             assert info.poly_tile % info.tile == 0 or v == "gather"
             if v == "tma":
                 assert info.tile == 1024 and T % 16 == 0 and T + dmax >= 2048 and dmax <= 127
+            if v == "siso":
+                assert ntx == 1 and nrx == 1 and info.tile in (512, 1024, 2048) and info.poly_tile >= 512 and info.launches == 2
             if v == "fused":
                 assert info.tile == 64 and 16 <= ntx <= 64 and 16 <= nrx <= 64 and dmax <= 128 and info.launches == 2
         else:

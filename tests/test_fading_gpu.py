@@ -89,8 +89,8 @@ def test_window_variant_tiles_and_edges(ntx, nrx, T, B):
     err, info = _run_case(B=B, L=14, N=12, ntx=ntx, nrx=nrx, T=T, fs=30.72e6, doppler=250.0, max_delay_s=1.4e-6,
                           precision="f32", sos_mode="auto", io=np.complex64, seed=T + ntx)
     tma_shape = ntx <= 4 and T % 16 == 0 and T + 43 >= 2048
-    assert info["variant"] == ("tma" if tma_shape else "window"), info
-    assert info["poly_tile"] % info["tile"] == 0 and info["tile"] in (256, 512, 1024), info
+    assert info["variant"] == ("window" if (ntx, nrx) == (1, 1) else "tma" if tma_shape else "window"), info  # 1 x 1: window
+    assert info["poly_tile"] % info["tile"] == 0 and info["tile"] in (256, 512, 1024, 2048), info
     assert err < F32_TOL, (err, info)
 
 
@@ -292,3 +292,34 @@ def test_stream_count_mismatch_raises():
     fb = FadingBatch.from_numpy(**stack_param_blocks([p]))
     with pytest.raises(ValueError):
         fading_propagate(torch.zeros((1, 3, 10), dtype=torch.complex64, device="cuda"), fb)
+
+
+@pytest.mark.parametrize("io", [np.complex64, np.complex128])
+@pytest.mark.parametrize("T,max_delay_s,L,doppler,B", [
+    (37, 0.0, 3, 300.0, 2),            # shorter than one pair row, no delay
+    (500, 1e-7, 23, 100.0, 9),         # config C1 shape: one delay group, one 512-output tile
+    (1025, 3e-6, 40, 300.0, 3),        # odd frame length (unaligned pair stores on odd links), odd and even delays
+    (4094, 2.15e-6, 20, 50.0, 2),      # COST259-like spread, last tile nearly empty
+    (70000, 2.15e-6, 20, 50.0, 2),     # many 2048-output tiles, several Taylor windows
+    (9000, 1e-5, 2, 2e3, 2),           # two taps 307 samples apart, fast fading (short Taylor windows)
+    (3000, 3.3e-5, 200, 300.0, 1),     # 1014-sample delay spread: halo as long as half a tile
+])
+def test_siso_kernel(T, max_delay_s, L, doppler, B, io):
+    """tdl_siso_kernel (fading_siso.cuh): planar staging, pairs of consecutive outputs in one FFMA2 -- frame edges, delay
+    parities, tile sizes 512 / 1024 / 2048, both frame element types, against the float64 oracle."""
+    err, info = _run_case(B=B, L=L, N=12, ntx=1, nrx=1, T=T, fs=30.72e6, doppler=doppler, max_delay_s=max_delay_s,
+                          precision="f32", sos_mode="poly_siso", io=io, seed=T)
+    assert info["mode"] == "poly" and info["variant"] == "siso" and info["launches"] == 2, info
+    assert info["tile"] in (512, 1024, 2048) and info["poly_tile"] % info["tile"] == 0, info
+    assert err < F32_TOL, (err, info)
+    err_w, info_w = _run_case(B=B, L=L, N=12, ntx=1, nrx=1, T=T, fs=30.72e6, doppler=doppler, max_delay_s=max_delay_s,
+                              precision="f32", sos_mode="poly_gather", io=io, seed=T)
+    assert info_w["variant"] == "gather" and err_w < F32_TOL
+
+
+def test_siso_mode_is_refused_for_arrays():
+    from hermespy_b200 import _lib
+
+    with pytest.raises(_lib.HermesB200Error):
+        _run_case(B=1, L=4, N=8, ntx=2, nrx=1, T=600, fs=30.72e6, doppler=10.0, max_delay_s=1e-7, precision="f32",
+                  sos_mode="poly_siso", io=np.complex64)
