@@ -430,6 +430,8 @@ class Workload:
                 return "spatial_gemm", "spatial_gemm_3xtf32_kernel", "hbm"
             name = {"window": "tdl_window_kernel", "gather": "tdl_poly_kernel", "tma": "tdl_tma_kernel", "siso": "tdl_siso_kernel"}.get(
                 info.get("variant"), "tdl_poly_kernel")
+            if self.precision == "f64":
+                name = "tdl_poly64_kernel"  # the float64 Taylor path (fading_poly64.cuh)
             return "tdl_poly", name, "hbm"
         return "tdl_direct", "tdl_direct_kernel", "hbm"
 

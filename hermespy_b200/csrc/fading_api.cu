@@ -450,6 +450,19 @@ static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_prob
 template <int P>
 static int launch_coef(const FadingArgs& a, const DelayTable& dt, cudaStream_t st) {
   ProfileScope prof(KIND_SOS_COEF, st);
+  if (a.ntiles >= 2) {
+    // several Taylor windows per link: the rotating form (one sincos per pair and warp, then FP64 rotations).  Windows per
+    // warp: as many as keep ~32 warps per SM in flight, at least 8 so that the start-up sincos is amortized.
+    const long long bg = (long long)a.B * dt.num_groups;
+    int wchunk = a.ntiles;
+    const long long want = 32ll * device_sm_count();
+    if (bg < want) wchunk = (int)std::max<long long>(std::min<long long>(8, a.ntiles), a.ntiles * bg / want);
+    const int nchunk = (a.ntiles + wchunk - 1) / wchunk;
+    const long long items = bg * nchunk;
+    sos_poly_coef_rot_kernel<P><<<(unsigned)((items + 3) / 4), 128, 0, st>>>(a, dt, wchunk, nchunk);
+    HB_CUDA(cudaGetLastError());
+    return HB_OK;
+  }
   FadingArgs ak = a;
   ak.coef_flat = dt.num_groups < 4;  // few delay groups: one warp per (link, window, group), see the kernel
   const size_t blocks = ak.coef_flat ? ((size_t)a.ntiles * a.B * dt.num_groups + 3) / 4 : (size_t)a.ntiles * a.B;

@@ -166,6 +166,132 @@ __global__ void __launch_bounds__(128) sos_poly_coef_kernel(const FadingArgs a,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1, rotating form (links spanning several Taylor windows).  The phase of a sinusoid advances by omega * tile from one
+// window centre to the next, so only the FIRST window of a warp's range pays the range reduction and the sincos; every
+// further window is one FP64 complex rotation of the running phasor (4 FP64 operations; rounding 1e-16 per step, i.e.
+// 5e-14 after the 513 windows of a 2^20-sample frame) followed by the FP32 moment recurrence.  Per (pair, window) that
+// is ~22 issue slots instead of ~100 (FP64 reduction + full-range sincosf).
+//   warp = (link, delay group, chunk of `wchunk` consecutive windows); lanes over the (tap, sinusoid) pairs of the group,
+//   four pairs per lane and pass; the per-window sums use the same transposing butterfly and lane assignment every time
+//   (deterministic).  grid = ceil(B G nchunk / 4) CTAs of 128 threads.
+template <int P>
+__global__ void __launch_bounds__(128) sos_poly_coef_rot_kernel(const FadingArgs a, const __grid_constant__ DelayTable dt,
+                                                                const int wchunk, const int nchunk) {
+  constexpr int kSlots = 4;
+  constexpr int NV = 2 * P <= 2 ? 2 : (2 * P <= 4 ? 4 : (2 * P <= 8 ? 8 : 16));
+  constexpr int LOG = NV == 2 ? 1 : (NV == 4 ? 2 : (NV == 8 ? 3 : 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = a.K, G = dt.num_groups;
+  if (blockIdx.x == 0 && a.tile_counters != nullptr)
+    for (int i = threadIdx.x; i < a.num_counters; i += blockDim.x) a.tile_counters[i] = 0u;
+  const long long item = (long long)blockIdx.x * 4 + warp;
+  if (item >= (long long)a.B * G * nchunk) return;
+  const int c = (int)(item % nchunk);
+  const long long bg = item / nchunk;
+  const int g = (int)(bg % G), b = (int)(bg / G);
+  const int q0 = c * wchunk, q1 = min(a.ntiles, q0 + wchunk);
+  if (g == 0 && c == 0 && a.spatial32 != nullptr && a.s32_tpl > 0) {
+    // FP32 spatial matrix, chunked, for the bulk-copy staged kernel
+    const int tpl = a.s32_tpl, nch = (a.ntx + tpl - 1) / tpl, per = a.nrx * tpl;
+    for (int i = lane; i < nch * per; i += 32) {
+      const int cc = i / per, r = i - cc * per, irx = r / tpl, j = cc * tpl + (r - irx * tpl);
+      float2 v = make_float2(0.f, 0.f);
+      if (j < a.ntx) v = to_c32(a.spatial[((size_t)b * a.nrx + irx) * a.ntx + j]);
+      a.spatial32[((size_t)b * nch + cc) * a.s32_stride + r] = v;
+    }
+  }
+  const double* om_b = a.omega + (size_t)b * a.L * K;
+  const double* ph_b = a.phi + (size_t)b * a.L * K;
+  const double* am_b = a.amp + (size_t)b * a.L * 2;
+  const int i0 = dt.group_start[g] * K, i1 = dt.group_start[g + 1] * K;
+  const double shift0 = (double)q0 * a.tile + 0.5 * a.tile - (double)dt.group_delay[g];
+  // which of the NV reduced values this lane ends up holding (lane bit 4 is the most significant index bit)
+  int vi = 0;
+#pragma unroll
+  for (int sft = 0; sft < LOG; ++sft) vi |= ((lane >> (4 - sft)) & 1) << (LOG - 1 - sft);
+  const bool writer = (lane & ((32 >> LOG) - 1)) == 0 && vi < 2 * P;
+
+  for (int s0 = i0; s0 < i1; s0 += 32 * kSlots) {
+    double xr[kSlots], xi[kSlots], rr[kSlots], ri[kSlots];
+    float uu[kSlots];
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j) {
+      const int idx = s0 + 32 * j + lane;
+      xr[j] = xi[j] = ri[j] = 0.0;
+      rr[j] = 1.0;
+      uu[j] = 0.f;
+      if (idx < i1) {
+        const int l = idx / K, k = idx - l * K;
+        const double om = om_b[idx];
+        double t = fma(om, shift0, ph_b[idx]) * kInvTwoPi;
+        t -= rint(t);
+        double sn, cs;
+        sincospi(2.0 * t, &sn, &cs);
+        const double am = am_b[2 * l + (k != 0 ? 1 : 0)];
+        xr[j] = am * cs;
+        xi[j] = am * sn;
+        const double step = om * (double)a.tile;
+        uu[j] = (float)step;
+        if (q1 - q0 > 1) {
+          double ts = step * kInvTwoPi;
+          ts -= rint(ts);
+          sincospi(2.0 * ts, &ri[j], &rr[j]);
+        }
+      }
+    }
+    const int nslot = min(kSlots, (i1 - s0 + 31) >> 5);  // warp-uniform: C2's one-tap groups fill a single slot
+    for (int q = q0; q < q1; ++q) {
+      float v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j) {
+        if (j < nslot) {
+        float tr = (float)xr[j], ti = (float)xi[j];
+        v[0] += tr;
+        v[1] += ti;
+#pragma unroll
+        for (int p = 1; p < P; ++p) {
+          const float f = uu[j] * (1.0f / (float)p);
+          const float nr = -ti * f, ni = tr * f;  // times (j u / p)
+          tr = nr;
+          ti = ni;
+          v[2 * p] += tr;
+          v[2 * p + 1] += ti;
+        }
+        const double nx = xr[j] * rr[j] - xi[j] * ri[j];  // advance the phasor to the next window centre
+        xi[j] = fma(xr[j], ri[j], xi[j] * rr[j]);
+        xr[j] = nx;
+        }
+      }
+      int n = NV, off = 16;
+#pragma unroll
+      for (int stepi = 0; stepi < 4; ++stepi) {
+        if (n > 1) {
+          const int half = n >> 1;
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < NV / 2; ++i) {
+            if (i < half) {
+              const float send = upper ? v[i] : v[i + half];
+              const float keep = upper ? v[i + half] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          n = half;
+          off >>= 1;
+        }
+      }
+      for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+      if (writer) {
+        float* out = reinterpret_cast<float*>(const_cast<float2*>(a.coef) + ((size_t)b * a.ntiles + q) * a.coef_stride + g * P) + vi;
+        *out = s0 == i0 ? v[0] : *out + v[0];  // groups of more than 128 pairs: further passes add, same lane, same order
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stage x[b, tx0 : tx0+NTX, q*tile - Dpad : q*tile + tile) into shared memory, zero outside [0, T).
 template <int NTX, typename C, typename IO>
 __device__ __forceinline__ void stage_x_tile(C* xs, const FadingArgs& a, int b, int q, int W) {
