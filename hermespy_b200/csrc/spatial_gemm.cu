@@ -81,9 +81,9 @@ int launch_spatial_gemm(const double2* S, const float2* z, float2* y, int B, int
       a.accumulate = tx0 > 0;
       ProfileScope prof(KIND_SPATIAL_GEMM, st);
       if (a.nrx == kGemmMaxAnt && a.ntx == kGemmMaxAnt && !a.accumulate)
-        spatial_gemm_3xtf32_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(a);
+        spatial_gemm_3xtf32_kernel<true><<<grid, kGemmLaunchThreads, kGemmSmemBytes, st>>>(a);
       else
-        spatial_gemm_3xtf32_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(a);
+        spatial_gemm_3xtf32_kernel<false><<<grid, kGemmLaunchThreads, kGemmSmemBytes, st>>>(a);
       HB_CUDA(cudaGetLastError());
     }
   }

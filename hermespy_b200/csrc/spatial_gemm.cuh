@@ -16,16 +16,23 @@
 // each; row groups SBO = 128 bytes apart, 16-byte K chunks LBO = 2048 bytes apart), validated bit-exactly by
 // tools/microbench/umma_probe.cu, which also measured the issue cost: 99 clk per 128x128x8 MMA from shared memory.
 //
-// Schedule: persistent CTA (256 threads, one per SM), work item = (link, segment of consecutive tiles): S is
-// converted and split once per item; per tile all threads stage z (global -> registers -> hi/lo -> shared, loads
-// prefetched one tile ahead), one thread issues the 3 x K/8 MMAs into one of two TMEM accumulators, and all threads
-// run the epilogue of the previous tile (tcgen05.ld -> shuffle -> global) while the tensor core works.
+// Schedule: persistent CTA (one per SM), work item = (link, segment of consecutive tiles): S is converted and split once
+// per item.  256 WORKER threads stage z (global -> registers -> hi/lo -> shared, loads prefetched one tile ahead) and run
+// the epilogue of the previous tile (tcgen05.ld -> shuffle -> global); two ISSUER warps (tiles of even / odd index, each
+// with its own TMEM accumulator and A buffer) issue the 3 x K/8 MMAs.  Round 1 issued from thread 0 of worker warp 0:
+// its 24 MMAs (~99 clk each from one thread) stalled that warp's epilogue and, through the CTA barrier, everyone else --
+// 5286 clk per tile against 2376 of issue time.  Workers and issuers now meet only on mbarriers (`staged` / `mma_done`).
 #pragma once
 #include "hb_common.cuh"
 
 namespace hb {
 
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 512;                 // worker threads (staging + epilogue): the CUDA-core side of a tile is ~5400
+                                                  // warp instructions (hi / lo splits, pair shuffles), 16 warps hide its latencies
+constexpr int kGemmChunksPerPass = kGemmThreads / 64;    // K chunks (4 antennas) staged per pass: 2 warps cover 64 samples
+constexpr int kGemmColParts = kGemmThreads / 128;        // epilogue: column parts per TMEM lane quadrant
+constexpr int kGemmPiecesPerWarp = 4 / kGemmColParts;    // 32-column pieces (16 receive streams) per epilogue warp
+constexpr int kGemmLaunchThreads = kGemmThreads + 64;  // + two MMA-issuing warps
 constexpr int kGemmTileSamples = 64;              // complex samples per MMA tile (M = 128 real rows)
 constexpr int kGemmMaxAnt = 64;                   // antennas per block on either side
 constexpr uint32_t kGemmLbo = 2048;               // bytes between 16-byte K chunks (16 row groups x 128 B)
@@ -70,6 +77,23 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// issued from warp-convergent code by the elected lane: the same lane for a given member mask every time
+__device__ __forceinline__ void mma_tf32_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_addr(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -122,10 +146,10 @@ __device__ __forceinline__ uint32_t gemm_operand_offset(int r, int k) {
 // FULL: a full 64 x 64 antenna block without accumulation -- interior tiles (all 64 samples inside the frame) then run
 // without a single bounds predicate: plain loads, pair-shuffled 8-byte stores.
 template <bool FULL>
-__global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__(kGemmLaunchThreads, 1) spatial_gemm_3xtf32_kernel(const GemmArgs a) {
   using namespace umma;
   extern __shared__ unsigned char gemm_smem_raw[];
-  __shared__ uint64_t mma_done[2];
+  __shared__ uint64_t mma_done[2], staged[2];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem0 = (smem_addr(gemm_smem_raw) + 1023u) & ~1023u;
@@ -146,6 +170,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
   if (tid == 0) {
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
+    mbar_init(&staged[0], kGemmThreads);
+    mbar_init(&staged[1], kGemmThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_before_sync();
@@ -154,18 +180,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
   const uint32_t tmem = tmem_base_slot;
   const uint32_t idesc = instr_desc_tf32(128, Np);
 
-  // staging task of this thread in pass p: K chunk kc = 4 p + (warp >> 1), sample ms = 32 (warp & 1) + lane
+  // staging task of this thread in pass p: K chunk kc = kGemmChunksPerPass p + (warp >> 1), sample ms = 32 (warp & 1) + lane
   const int ms = ((warp & 1) << 5) + lane;
   const int kc0 = warp >> 1;
-  constexpr int kMaxPass = kGemmMaxAnt / 4 / 4;  // 4 passes of 4 chunks cover 64 antennas
+  constexpr int kMaxPass = kGemmMaxAnt / 4 / kGemmChunksPerPass;  // passes of kGemmChunksPerPass chunks cover 64 antennas
   const uint32_t a_off = (uint32_t)(ms >> 2) * kGemmSbo + (uint32_t)(ms & 3) * 32;  // rows 2 ms, 2 ms + 1
 
-  // epilogue role: TMEM lane quadrant and column half
-  const int quad = warp & 3, chalf = warp >> 2;
+  // epilogue role: TMEM lane quadrant and column part
+  const int quad = warp & 3, cpart = warp >> 2;
   const int em = (quad << 4) + (lane >> 1);  // sample of this thread's TMEM lane inside the tile
   const int comp = lane & 1;                 // 0: real row, 1: imaginary row
 
   uint32_t phase_bits = 0u;  // bit s: parity the next wait on accumulator slot s expects
+
+  if (warp >= kGemmThreads / 32) {
+    // ================================ MMA issue: warp 8 + w takes the tiles of local index i = w (mod 2) ================
+    const int w = warp - kGemmThreads / 32;
+    const uint32_t ahi = sA0 + (uint32_t)w * 2 * kGemmOperandBytes, alo = ahi + kGemmOperandBytes;
+    const uint32_t d = tmem + (uint32_t)w * 128;
+    uint32_t use = 0;  // tiles this warp has issued: phase of staged[w]
+    for (int item = blockIdx.x; item < a.B * a.nseg; item += gridDim.x) {
+      const int seg = item % a.nseg;
+      const int ntile = min(a.ntiles, (seg + 1) * a.seg_tiles) - seg * a.seg_tiles;
+      for (int i = w; i < ntile; i += 2, ++use) {
+        mbar_wait(&staged[w], use & 1u);  // all workers: A buffer w (and S) staged, accumulator w drained
+        fence_after_sync();
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t adv = (uint32_t)ks * 2 * kGemmLbo;
+          const uint64_t dah = smem_desc(ahi + adv, kGemmLbo, kGemmSbo), dal = smem_desc(alo + adv, kGemmLbo, kGemmSbo);
+          const uint64_t dbh = smem_desc(sB_hi + adv, kGemmLbo, kGemmSbo), dbl = smem_desc(sB_lo + adv, kGemmLbo, kGemmSbo);
+          mma_tf32_elect(d, dal, dbh, idesc, (uint32_t)ks);
+          mma_tf32_elect(d, dah, dbl, idesc, 1u);
+          mma_tf32_elect(d, dah, dbh, idesc, 1u);
+        }
+        commit_elect(&mma_done[w]);
+      }
+    }
+  } else
 
   for (int item = blockIdx.x; item < a.B * a.nseg; item += gridDim.x) {
     const int b = item / a.nseg, seg = item - b * a.nseg;
@@ -204,12 +255,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
 #pragma unroll
         for (int p = 0; p < kMaxPass; ++p)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) zr[p][i] = ldg_stream(zp + (size_t)(16 * p + i) * a.ldz);
+          for (int i = 0; i < 4; ++i) zr[p][i] = ldg_stream(zp + (size_t)(4 * kGemmChunksPerPass * p + i) * a.ldz);
         return;
       }
 #pragma unroll
       for (int p = 0; p < kMaxPass; ++p) {
-        const int kc = 4 * p + kc0;
+        const int kc = kGemmChunksPerPass * p + kc0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int k = 4 * kc + i;
@@ -223,7 +274,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
       const uint32_t hi0 = sA0 + (uint32_t)buf * 2 * kGemmOperandBytes + a_off, lo0 = hi0 + kGemmOperandBytes;
 #pragma unroll
       for (int p = 0; p < kMaxPass; ++p) {
-        const int kc = 4 * p + kc0;
+        const int kc = kGemmChunksPerPass * p + kc0;
         if (kc < kchunks) {
           float hr[4], lr[4], hi_[4], li[4];
 #pragma unroll
@@ -239,34 +290,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
         }
       }
     };
-    auto issue_mma = [&](int buf) {  // one thread
-      const uint32_t ahi = sA0 + (uint32_t)buf * 2 * kGemmOperandBytes, alo = ahi + kGemmOperandBytes;
-      const uint32_t d = tmem + (uint32_t)buf * 128;
-      uint32_t acc = 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t adv = (uint32_t)ks * 2 * kGemmLbo;
-        const uint64_t dah = smem_desc(ahi + adv, kGemmLbo, kGemmSbo), dal = smem_desc(alo + adv, kGemmLbo, kGemmSbo);
-        const uint64_t dbh = smem_desc(sB_hi + adv, kGemmLbo, kGemmSbo), dbl = smem_desc(sB_lo + adv, kGemmLbo, kGemmSbo);
-        mma_tf32(d, dal, dbh, idesc, acc);
-        mma_tf32(d, dah, dbl, idesc, 1u);
-        mma_tf32(d, dah, dbh, idesc, 1u);
-        acc = 1u;
-      }
-      commit(&mma_done[buf]);
+    // hand buffer `buf` (A operand staged, accumulator drained by this thread's earlier epilogue) to its issuer warp
+    auto hand_over = [&](int buf) {
+      fence_async_smem();
+      fence_before_sync();
+      mbar_arrive(&staged[buf]);
     };
     auto epilogue = [&](int t, int buf) {
       mbar_wait(&mma_done[buf], (phase_bits >> buf) & 1u);
       phase_bits ^= 1u << buf;
       fence_after_sync();
       const int n = t * kGemmTileSamples + em;
-      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 128 + (uint32_t)chalf * 64;
+      const int piece0 = cpart * kGemmPiecesPerWarp;  // first 32-column piece (16 receive streams) of this warp
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * 128 + (uint32_t)piece0 * 32;
       if (FULL && (t + 1) * kGemmTileSamples <= a.T) {  // CTA-uniform
         // Pair shuffle: for receive streams (j0, j0 + 1) the even lane (Re z row: P, Q) finishes stream j0 and the odd
         // lane (Im z row: U, V) finishes j0 + 1; each receives the partner's two coefficients of ITS stream, so every
         // thread stores one complete complex sample (8 bytes); a warp writes two 128-byte row segments per instruction.
-        float2* yrow = reinterpret_cast<float2*>(yb) + (size_t)(chalf * 32 + comp) * a.T + n;
+        float2* yrow = reinterpret_cast<float2*>(yb) + (size_t)(piece0 * 16 + comp) * a.T + n;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kGemmPiecesPerWarp; ++h) {
           uint32_t v[32];
           tmem_ld32(taddr + h * 32, v);
           tmem_ld_wait();
@@ -292,8 +335,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
         return;
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (chalf * 64 + h * 32 < Np) {  // warp-uniform
+      for (int h = 0; h < kGemmPiecesPerWarp; ++h) {
+        if ((piece0 + h) * 32 < Np) {  // warp-uniform
           uint32_t v[32];
           tmem_ld32(taddr + h * 32, v);
           tmem_ld_wait();
@@ -304,7 +347,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
             const float keep = __uint_as_float(v[2 * jj]);
             const float recv = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[2 * jj + 1]), 1);
             float out = comp ? keep + recv : keep - recv;
-            const int j = chalf * 32 + h * 16 + jj;
+            const int j = (piece0 + h) * 16 + jj;
             if (j < a.nrx && n < a.T) {
               float* dst = yb + ((size_t)j * a.T + n) * 2 + comp;
               if (a.accumulate) out += *dst;
@@ -319,29 +362,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spatial_gemm_3xtf32_kernel(co
     load_tile(t_begin);
     stage_tile(0);
     if (ntile > 1) load_tile(t_begin + 1);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    if (tid == 0) issue_mma(0);
+    hand_over(0);
     for (int i = 0; i < ntile; ++i) {
       if (i + 1 < ntile) {
         stage_tile((i + 1) & 1);  // buffer last read by the MMAs of tile i - 1 (waited for in its epilogue)
         if (i + 2 < ntile) load_tile(t_begin + i + 2);
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
-        if (tid == 0) issue_mma((i + 1) & 1);  // accumulator last read by the epilogue of tile i - 1
+        hand_over((i + 1) & 1);   // accumulator last read by this thread's epilogue of tile i - 1
       }
       epilogue(t_begin + i, i & 1);
     }
-    // all MMAs of the item have completed (waited for by the epilogues); order the TMEM reads and the shared
-    // operands before the next item overwrites them
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
+    // every MMA of the item has completed (each worker waited for them in its epilogues): S and the A buffers may be
+    // overwritten by this thread; the accumulators are re-used only after all 256 workers handed the next tile over
   }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
