@@ -570,7 +570,7 @@ def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allre
     if bound == "hbm":
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": _traffic(cfg, kname, B), "peak_source": peak_src}
+                    "frac": achieved / hbm_peak, "traffic": None if sinc else _traffic(cfg, kname, B), "peak_source": peak_src}
     elif bound == "tensor":
         # CDL contraction on tcgen05 (cdl_umma_kernel): ALGORITHMIC flops = 8 P G Nrx Ntx per output sample; the kernel runs
         # them as 3xTF32 (three TF32 products per FP32 product), so the tensor pipe executes 3x that.  Peak: dense TF32 =
@@ -580,7 +580,7 @@ def measure(cfg, precision, args, world, rank, dev, steps, with_cpu, stats_allre
         peak_tf = 0.5 * bf16_tf[0]
         achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None,
+                    "frac": achieved / peak_tf, "traffic": _traffic(cfg, kname, B),
                     "peak_source": f"dense TF32 = 0.5 x bf16_tflops ({bf16_tf[1]})",
                     "tensor_flops_executed_per_algorithmic_flop": 3.0,
                     "tensor_pipe_frac_3xtf32": 3.0 * achieved / peak_tf,
