@@ -166,18 +166,24 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
     }
   }
   if (!poly && p->precision == HB_F32) {
+    // FP32-pipe kernel: tile = 128 R outputs; fast links (whose four-term Taylor bound fails on the 512-sample tile) get
+    // shorter tiles before the planner gives the problem to the per-ray path
     pl->Dpad = (p->max_delay + 1) & ~1;
-    pl->R = pl->nrx_tpl <= 4 ? 4 : 2;
-    pl->tile = pl->threads * pl->R;
-    double bound = 0.0;
-    const int P = cdl_poly_order(p, pl->tile, pl->max_group_terms, &bound);
-    pl->smem = P ? cdl_smem(pl->tile, pl->Dpad, tb.num_groups, P, pl->nrx_tpl) : 0;
-    if (P && pl->smem <= 200 * 1024) {
-      pl->mode = HB_SOS_POLY;
-      pl->P = P;
-      pl->bound = bound;
-      poly = true;
-    }  // else: Doppler too fast for four Taylor terms, or delay spread too long for the tile: per-ray path
+    for (int R = pl->nrx_tpl <= 4 ? 4 : 2; R >= 1 && !poly; R >>= 1) {
+      const int tile = pl->threads * R;
+      double bound = 0.0;
+      const int P = cdl_poly_order(p, tile, pl->max_group_terms, &bound);
+      const size_t smem = P ? cdl_smem(tile, pl->Dpad, tb.num_groups, P, pl->nrx_tpl) : 0;
+      if (P && smem <= 200 * 1024) {
+        pl->mode = HB_SOS_POLY;
+        pl->R = R;
+        pl->tile = tile;
+        pl->smem = smem;
+        pl->P = P;
+        pl->bound = bound;
+        poly = true;
+      }
+    }  // none: Doppler too fast for four Taylor terms on 128 samples, or delay spread too long for shared memory: per-ray path
   }
   if (!poly) {
     pl->mode = HB_SOS_DIRECT;
@@ -239,13 +245,24 @@ static int launch_poly_p(int P, const CdlArgs& a, const CdlTable& tb, size_t sme
   }
 }
 
+// R = outputs per thread = tile / 128: 4 (2 for 8 receive antennas) by default, halved for fast links whose Taylor bound needs
+// shorter windows (make_cdl_plan)
+template <int NRX, typename IO>
+static int launch_poly_r(int R, int P, const CdlArgs& a, const CdlTable& tb, size_t smem, cudaStream_t st) {
+  if constexpr (NRX <= 4) {
+    if (R == 4) return launch_poly_p<NRX, 4, IO>(P, a, tb, smem, st);
+  }
+  if (R == 2) return launch_poly_p<NRX, 2, IO>(P, a, tb, smem, st);
+  return launch_poly_p<NRX, 1, IO>(P, a, tb, smem, st);
+}
+
 template <typename IO>
-static int launch_poly_nrx(int nrx_tpl, int P, const CdlArgs& a, const CdlTable& tb, size_t smem, cudaStream_t st) {
+static int launch_poly_nrx(int nrx_tpl, int R, int P, const CdlArgs& a, const CdlTable& tb, size_t smem, cudaStream_t st) {
   switch (nrx_tpl) {
-    case 1: return launch_poly_p<1, 4, IO>(P, a, tb, smem, st);
-    case 2: return launch_poly_p<2, 4, IO>(P, a, tb, smem, st);
-    case 4: return launch_poly_p<4, 4, IO>(P, a, tb, smem, st);
-    default: return launch_poly_p<8, 2, IO>(P, a, tb, smem, st);
+    case 1: return launch_poly_r<1, IO>(R, P, a, tb, smem, st);
+    case 2: return launch_poly_r<2, IO>(R, P, a, tb, smem, st);
+    case 4: return launch_poly_r<4, IO>(R, P, a, tb, smem, st);
+    default: return launch_poly_r<8, IO>(R, P, a, tb, smem, st);
   }
 }
 
@@ -355,8 +372,8 @@ static int cdl_propagate_device(const hb_cdl_problem* p, const CdlTable& tb, con
         rc = io128 ? launch_cdl_umma_io<double2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st)
                    : launch_cdl_umma_io<float2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st);
       else
-        rc = io128 ? launch_poly_nrx<double2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st)
-                   : launch_poly_nrx<float2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st);
+        rc = io128 ? launch_poly_nrx<double2>(pl.nrx_tpl, pl.R, pl.P, a, tb, pl.smem, st)
+                   : launch_poly_nrx<float2>(pl.nrx_tpl, pl.R, pl.P, a, tb, pl.smem, st);
     }
   } else if (rc == HB_OK) {
     ProfileScope prof(KIND_CDL_PROPAGATE, st);

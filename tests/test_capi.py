@@ -222,3 +222,11 @@ def test_cdl_planner_kernel_variants():
     assert rc == _lib.HB_ERR_UNSUPPORTED and "tensor-core" in _lib.load().hb_last_error().decode()
     rc, _ = _cdl_plan(32, 4, 2048, delays, variant=7)
     assert rc == _lib.HB_ERR_INVALID
+    # fast links: four Taylor terms do not cover a 512-sample window any more -> the FP32-pipe kernel with shorter tiles,
+    # and only beyond those the per-ray path
+    rc, d = _cdl_plan(32, 4, 2048, delays, speed=60.0)
+    assert rc == 0 and d["mode"] == 1 and d["variant"] == 1 and d["tile"] == 256 and d["error_bound"] <= 5e-8
+    rc, d = _cdl_plan(32, 4, 2048, delays, speed=110.0)
+    assert rc == 0 and d["mode"] == 1 and d["variant"] == 1 and d["tile"] == 128
+    rc, d = _cdl_plan(32, 4, 2048, delays, speed=400.0)
+    assert rc == 0 and d["mode"] == 2

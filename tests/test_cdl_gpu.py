@@ -148,3 +148,20 @@ def test_tensor_core_variant_against_oracle_and_gather(dims_tx, dims_rx, speed, 
             assert yu[k].shape == refs[b].shape
             assert rel_l2(yu[k], refs[b]) < 1e-5
             assert rel_l2(yu[k], yg[k]) < 3e-6
+
+
+@pytest.mark.parametrize("speed,tile", [((60.0, 0.0, 0.0), 256), ((100.0, 40.0, 5.0), 128)])
+def test_fast_links_stay_on_the_taylor_path(speed, tile):
+    """Links too fast for four Taylor terms on a 512-sample window run the FP32-pipe kernel with shorter tiles (f32 mode) instead
+    of dropping to the per-ray FP64 kernel."""
+    from hermespy_b200.kernels import CdlBlock, cdl_propagate_host
+
+    rng = np.random.default_rng(3)
+    tx = mirror_cdl_device(((4, 2, 1), (0.0, 0.1, 0.0), (0.0, 0.0, 25.0), (0, 0, 0)))
+    rx = mirror_cdl_device(((2, 1, 1), (0, 0, 0.2), (80.0, 20.0, 1.5), speed))
+    s = MC.CDL(MC.CDLType.A, 300e-9, seed=9).realize().sample(tx, rx)
+    x = (rng.standard_normal((8, 1500)) + 1j * rng.standard_normal((8, 1500))) / np.sqrt(2)
+    ref = co.propagate(oracle_params(s), x)
+    y, info = cdl_propagate_host(x[None], CdlBlock.stack([s.kernel_block()]), precision="f32", return_info=True)
+    assert info["mode"] == "poly" and info["variant"] == "gather" and info["tile"] == tile, info
+    assert rel_l2(y[0], ref) < 1e-5
