@@ -410,7 +410,8 @@ class Workload:
                                     return_info=return_info)
         from hermespy_b200.kernels import cdl_propagate
 
-        return cdl_propagate(self.x, self.dblk, precision=self.precision, out=self.y, return_info=return_info)
+        return cdl_propagate(self.x, self.dblk, precision=self.precision, out=self.y, return_info=return_info,
+                             variant=os.environ.get("HB_BENCH_CDL_VARIANT", "auto"))  # experiments: gather | umma | umma_bf16
 
     # -- algorithmic work ------------------------------------------------------------------------------
     def algorithmic_bytes(self):
@@ -420,8 +421,8 @@ class Workload:
     def dominant(self, prof, info):
         """(accounting kind, kernel name, bound) of the step's dominant kernel."""
         if self.cfg["kind"] == "cdl":
-            if info.get("variant") == "umma":
-                return "cdl_propagate", "cdl_umma_kernel", "tensor"
+            if info.get("variant") in ("umma", "umma_bf16"):
+                return "cdl_propagate", "cdl_umma_kernel" if info["variant"] == "umma" else "cdl_umma_bf16_kernel", "tensor"
             return "cdl_propagate", ("cdl_poly_kernel" if info.get("mode") == "poly" else "cdl_direct_f64_kernel"), "fp32"
         if info.get("variant") == "fused":
             return "spatial_gemm", "fused_gemm_tdl_kernel", "hbm"

@@ -6,6 +6,7 @@
 
 #include "cdl_kernels.cuh"
 #include "cdl_umma.cuh"
+#include "cdl_umma_bf16.cuh"
 
 namespace hb {
 
@@ -120,7 +121,7 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
   pl->max_group_terms = 1;
   for (int g = 0; g < tb.num_groups; ++g)
     pl->max_group_terms = std::max(pl->max_group_terms, (int)tb.group_start[g + 1] - (int)tb.group_start[g]);
-  if (p->variant < HB_CDL_VARIANT_AUTO || p->variant > HB_CDL_VARIANT_UMMA) {
+  if (p->variant < HB_CDL_VARIANT_AUTO || p->variant > HB_CDL_VARIANT_UMMA_BF16) {
     set_error("unknown CDL variant %d", p->variant);
     return HB_ERR_INVALID;
   }
@@ -129,14 +130,17 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
     // tensor-core kernel (cdl_umma.cuh): the Taylor window is 128 MT samples, MT fixed by the accumulator width, so the
     // order is searched with the window it implies.  AUTO takes it from 8 transmit antennas (below, K is too short to pay
     // for the operand staging).
-    const bool want = p->variant == HB_CDL_VARIANT_UMMA || p->num_tx >= 8;
+    const bool want = p->variant == HB_CDL_VARIANT_UMMA || p->variant == HB_CDL_VARIANT_UMMA_BF16 || p->num_tx >= 8;
     const int Dpad = (p->max_delay + 7) & ~7;
     // Joint choice of the Taylor order P and the window (1, 2, 4 or 8 K6 tiles): the K6 cost does not depend on either
     // (N is padded to 16 columns), the moment kernel's is proportional to windows x P.
     int best_cost = 1 << 30;
+    const bool bf16 = p->variant == HB_CDL_VARIANT_UMMA_BF16;  // BF16x3 form: 256-sample tiles, 8 antennas per K stage
     for (int cand = 1; cand <= 4 && want; ++cand) {
-      const int tile = cu_tile(pl->nrx_tpl, cand);
-      const size_t smem = cu_smem_bytes(pl->nrx_tpl, cand, Dpad, tb.num_groups);
+      if (bf16 && !cb_eligible(pl->nrx_tpl, cand)) continue;
+      const int tile = bf16 ? kCbTile : cu_tile(pl->nrx_tpl, cand);
+      const size_t smem = bf16 ? cb_smem_bytes(pl->nrx_tpl, cand, Dpad, tb.num_groups)
+                               : cu_smem_bytes(pl->nrx_tpl, cand, Dpad, tb.num_groups);
       if (smem > 226 * 1024 || tile + Dpad >= 16384) continue;  // both operand images of a K stage, two slots
       for (int tw = 8; tw >= 1; tw >>= 1) {
         const double bound = cdl_poly_bound(p, tile * tw, cand, pl->max_group_terms);
@@ -145,7 +149,7 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
         if (nwin * cand < best_cost) {
           best_cost = nwin * cand;
           pl->mode = HB_SOS_POLY;
-          pl->variant = HB_CDL_VARIANT_UMMA;
+          pl->variant = bf16 ? HB_CDL_VARIANT_UMMA_BF16 : HB_CDL_VARIANT_UMMA;
           pl->P = cand;
           pl->tile = tile;
           pl->ptile = tile * tw;
@@ -158,7 +162,7 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
         break;  // smaller windows of this order only cost more
       }
     }
-    if (!poly && p->variant == HB_CDL_VARIANT_UMMA) {
+    if (!poly && (p->variant == HB_CDL_VARIANT_UMMA || p->variant == HB_CDL_VARIANT_UMMA_BF16)) {
       set_error("the tensor-core CDL kernel does not take this problem (Doppler too fast for four Taylor terms, or the "
                 "operand images of %d delay groups and a %d-sample delay halo exceed the shared memory of one SM)",
                 tb.num_groups, Dpad);
@@ -193,7 +197,7 @@ static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* p
     pl->smem = 0;
   }
   pl->ntiles = std::max(1, (Tout + pl->tile - 1) / pl->tile);
-  if (pl->variant != HB_CDL_VARIANT_UMMA || pl->mode != HB_SOS_POLY) pl->ptile = pl->tile;
+  if ((pl->variant != HB_CDL_VARIANT_UMMA && pl->variant != HB_CDL_VARIANT_UMMA_BF16) || pl->mode != HB_SOS_POLY) pl->ptile = pl->tile;
   pl->nwin = std::max(1, (Tout + pl->ptile - 1) / pl->ptile);
   return HB_OK;
 }
@@ -368,7 +372,9 @@ static int cdl_propagate_device(const hb_cdl_problem* p, const CdlTable& tb, con
     for (int rx0 = 0; rx0 < p->num_rx && rc == HB_OK; rx0 += pl.nrx_tpl) {
       a.rx0 = rx0;
       a.nrx_chunk = std::min(pl.nrx_tpl, p->num_rx - rx0);
-      if (pl.variant == HB_CDL_VARIANT_UMMA)
+      if (pl.variant == HB_CDL_VARIANT_UMMA_BF16)
+        rc = launch_cdl_umma_bf16(pl.nrx_tpl, pl.P, io128, a, tb, pl.smem, st);
+      else if (pl.variant == HB_CDL_VARIANT_UMMA)
         rc = io128 ? launch_cdl_umma_io<double2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st)
                    : launch_cdl_umma_io<float2>(pl.nrx_tpl, pl.P, a, tb, pl.smem, st);
       else

@@ -620,13 +620,13 @@ class CdlBlock:
                 self.carrier_frequency, self.sampling_rate, self.line_of_sight, self.los_delay, self.los_amplitude, el)
 
 
-_CDL_VARIANT = {"auto": 0, "gather": 1, "umma": 2}
+_CDL_VARIANT = {"auto": 0, "gather": 1, "umma": 2, "umma_bf16": 3}
 
 
 def _cdl_info_dict(info: FadingPlanInfo) -> dict:
     d = info.as_dict()
     d["mode"] = _SOS_NAME.get(d["mode"], d["mode"])
-    d["variant"] = {1: "gather", 2: "umma"}.get(d["variant"]) if d["mode"] == "poly" else None
+    d["variant"] = {1: "gather", 2: "umma", 3: "umma_bf16"}.get(d["variant"]) if d["mode"] == "poly" else None
     return d
 
 

@@ -165,3 +165,54 @@ def test_fast_links_stay_on_the_taylor_path(speed, tile):
     y, info = cdl_propagate_host(x[None], CdlBlock.stack([s.kernel_block()]), precision="f32", return_info=True)
     assert info["mode"] == "poly" and info["variant"] == "gather" and info["tile"] == tile, info
     assert rel_l2(y[0], ref) < 1e-5
+
+
+@pytest.mark.parametrize("dims_tx,dims_rx,speed,T,cdl_type,io", [
+    ((8, 4, 1), (2, 2, 1), (10.0, -3.0, 0.0), 2048, "C", np.complex64),    # config C3 shape: 8 full tiles of 256 + the delay tail
+    ((8, 4, 1), (2, 2, 1), (10.0, -3.0, 0.0), 700, "C", np.complex128),    # partial tile, complex128 frames
+    ((4, 4, 1), (4, 2, 1), (0.0, 0.0, 0.0), 300, "A", np.complex64),       # static: P = 1, 8 receive antennas (16 columns per term)
+    ((3, 1, 1), (3, 1, 1), (30.0, 0.0, 0.0), 64, "E", np.complex64),       # odd antenna counts, frame shorter than one M-tile
+    ((1, 1, 1), (1, 1, 1), (25.0, 0.0, 0.0), 1500, "B", np.complex64),     # SISO: one K stage with one antenna of eight
+    ((5, 3, 1), (2, 1, 1), (3.0, 3.0, 0.0), 1100, "D", np.complex64),      # 15 transmit antennas (ragged second K stage), LOS term
+])
+def test_bf16x3_tensor_core_variant(dims_tx, dims_rx, speed, T, cdl_type, io):
+    """K6 as BF16x3 on tcgen05 (``variant="umma_bf16"``, cdl_umma_bf16.cuh) against the float64 oracle and the 3xTF32 kernel."""
+    from hermespy_b200 import _lib
+    from hermespy_b200.kernels import CdlBlock, cdl_propagate_host
+
+    rng = np.random.default_rng(12)
+    tx = mirror_cdl_device((dims_tx, (0.0, 0.1, 0.0), (0.0, 0.0, 25.0), (0, 0, 0)))
+    ch = MC.CDL(getattr(MC.CDLType, cdl_type), 300e-9, seed=6)
+    ntx = int(np.prod(dims_tx))
+    samples, xs, refs = [], [], []
+    for b in range(4):
+        rx = mirror_cdl_device((dims_rx, (0, 0, 0.3 * b), (100.0 + 7 * b, 20.0, 1.5), speed))
+        s = ch.realize().sample(tx, rx)
+        x = (rng.standard_normal((ntx, T)) + 1j * rng.standard_normal((ntx, T))) / np.sqrt(2)
+        samples.append(s), xs.append(x), refs.append(co.propagate(oracle_params(s), x))
+    groups = {}
+    for b, s in enumerate(samples):
+        groups.setdefault(s.kernel_block().group_key(), []).append(b)
+    for idx in groups.values():
+        blk = CdlBlock.stack([samples[b].kernel_block() for b in idx])
+        x = np.stack([xs[b] for b in idx]).astype(io)
+        before = _lib.launch_counts()["cdl_propagate"]
+        yb, info = cdl_propagate_host(x, blk, precision="f32", variant="umma_bf16", return_info=True)
+        assert info["variant"] == "umma_bf16" and info["tile"] == 256 and _lib.launch_counts()["cdl_propagate"] > before
+        yt = cdl_propagate_host(x, blk, precision="f32", variant="umma")
+        for k, b in enumerate(idx):
+            assert yb[k].shape == refs[b].shape
+            assert rel_l2(yb[k], refs[b]) < 1e-5
+            assert rel_l2(yb[k], yt[k]) < 3e-6
+
+
+def test_bf16x3_variant_is_refused_beyond_32_columns():
+    from hermespy_b200 import _lib
+    from hermespy_b200.kernels import CdlBlock, cdl_plan
+
+    tx = mirror_cdl_device(((4, 2, 1), (0.0, 0.1, 0.0), (0.0, 0.0, 25.0), (0, 0, 0)))
+    rx = mirror_cdl_device(((4, 2, 1), (0, 0, 0.0), (100.0, 20.0, 1.5), (20.0, 0.0, 0.0)))  # 8 receive antennas, P > 2
+    blk = CdlBlock.stack([MC.CDL(MC.CDLType.C, 300e-9, seed=1).realize().sample(tx, rx).kernel_block()])
+    with pytest.raises(_lib.HermesB200Error):
+        cdl_plan(blk, 2048, "f32", variant="umma_bf16")
+    assert cdl_plan(blk, 2048, "f32", variant="umma")["variant"] == "umma"
