@@ -218,7 +218,7 @@ static void fill_cdl_info(const CdlPlan& pl, const CdlTable& tb, const hb_cdl_pr
 template <int P>
 static int launch_moments(const CdlArgs& a, const CdlTable& tb, cudaStream_t st) {
   ProfileScope prof(KIND_CDL_RAYS, st);
-  const size_t smem = sizeof(float2) * ((size_t)kMomTerms * kMomWin * P + (size_t)kMomTerms * a.rank * (a.nrx + a.ntx));
+  const size_t smem = sizeof(float2) * (size_t)kMomTerms * kMomWin * P + sizeof(double2) * (size_t)kMomTerms * a.rank * (a.nrx + a.ntx);
   if (smem <= 48 * 1024) {  // one CTA per (link, delay group), all Taylor windows at once
     cdl_moment_all_kernel<P><<<(unsigned)((size_t)a.B * tb.num_groups), 128, smem, st>>>(a, tb);
   } else {  // arrays beyond ~80 elements per side: the per-window kernel reads the steering phases from global memory

@@ -309,8 +309,7 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
 // K5b, second form: one CTA per (link, delay group) forms the moments of ALL Taylor windows of the frame.
 //   gamma[t][q][p] = alpha_t e^{j w_t (centre_q - k_g)} (j w_t tile)^p / p!     (phase reduced in FP64, stored FP32)
 //   M[q][g][p][i][j] = sum_{t in g} gamma[t][q][p] * (u_t[i] v_t[j])           (FP32 FMA pipe)
-// The steering phases u, v are converted to FP32 once per term and CTA (they are unit-modulus, so the product keeps
-// 2^-24 relative accuracy) and the ray product u_i v_j is formed once per term instead of once per (term, window).
+// The ray product u_i v_j is formed once per term (FP64, rounded once to FP32) instead of once per (term, window).
 // Windows are a.ptile samples long (a multiple of the K6 tile).  grid = B * G, 128 threads over (i, j); dynamic shared memory: gamma[kMomTerms][kMomWin][P] | us | vs.
 constexpr int kMomTerms = 32;  // ray terms staged per pass
 constexpr int kMomWin = 4;     // Taylor windows accumulated per pass
@@ -319,8 +318,8 @@ template <int P>
 __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
   extern __shared__ __align__(16) unsigned char mom_smem[];
   float2* gam = reinterpret_cast<float2*>(mom_smem);                 // [kMomTerms][kMomWin][P]
-  float2* us = gam + kMomTerms * kMomWin * P;                         // [kMomTerms][nrx * rank]
-  float2* vs = us + kMomTerms * a.nrx * a.rank;                       // [kMomTerms][ntx * rank]
+  double2* us = reinterpret_cast<double2*>(gam + kMomTerms * kMomWin * P);  // [kMomTerms][nrx * rank]
+  double2* vs = us + kMomTerms * a.nrx * a.rank;                            // [kMomTerms][ntx * rank]
   const int G = tb.num_groups;
   const int b = blockIdx.x / G, g = blockIdx.x - b * G;
   const int t0 = tb.group_start[g], t1 = tb.group_start[g + 1];
@@ -365,29 +364,26 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
         }
         for (int e = tid; e < nc * nu; e += 128) {
           const int k = e / nu, c = e - k * nu;
-          const double2 v = a.u[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nu + c];
-          us[k * nu + c] = make_float2((float)v.x, (float)v.y);
+          us[k * nu + c] = a.u[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nu + c];
         }
         for (int e = tid; e < nc * nv; e += 128) {
           const int k = e / nv, c = e - k * nv;
-          const double2 v = a.v[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nv + c];
-          vs[k * nv + c] = make_float2((float)v.x, (float)v.y);
+          vs[k * nv + c] = a.v[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nv + c];
         }
         __syncthreads();
         if (ij < nij) {
           auto accumulate = [&](auto nq_tag) {  // fully unrolled over the windows of this pass
             constexpr int NQ = decltype(nq_tag)::value;
             for (int k = 0; k < nc; ++k) {
-              float2 uv;
-              if (a.rank == 1) {
-                const float2 u0 = us[k * nu + i], v0 = vs[k * nv + j];
-                uv = make_float2(u0.x * v0.x - u0.y * v0.y, u0.x * v0.y + u0.y * v0.x);
-              } else {
-                const float2 u0 = us[k * nu + 2 * i], v0 = vs[k * nv + 2 * j];
-                const float2 u1 = us[k * nu + 2 * i + 1], v1 = vs[k * nv + 2 * j + 1];
-                uv = make_float2(u0.x * v0.x - u0.y * v0.y + u1.x * v1.x - u1.y * v1.y,
-                                 u0.x * v0.y + u0.y * v0.x + u1.x * v1.y + u1.y * v1.x);
+              // the ray product in FP64, rounded once (an FP32 product of FP32-rounded phases costs the small-array f32 path
+              // a factor two in accuracy: the reference's own 6-decimal unit tests notice)
+              double2 uvd = cmul(us[k * nu + a.rank * i], vs[k * nv + a.rank * j]);
+              if (a.rank == 2) {
+                const double2 r1 = cmul(us[k * nu + 2 * i + 1], vs[k * nv + 2 * j + 1]);
+                uvd.x += r1.x;
+                uvd.y += r1.y;
               }
+              const float2 uv = make_float2((float)uvd.x, (float)uvd.y);
               const float2* gk = gam + k * kMomWin * P;
 #pragma unroll
               for (int q = 0; q < NQ; ++q)

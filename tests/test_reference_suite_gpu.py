@@ -37,8 +37,15 @@ NEEDS_ABSENT_PACKAGES = re.compile(r"serializ|plot|visualization", re.I)  # h5py
 # test_channel_gain (test_fading.py:560-591) compares two propagations of UNSEEDED Gaussian samples, one scaled by
 # sqrt(10), element-wise to 6 decimals (1.5e-6 absolute): outputs reach |y| ~ 10, where one complex64 rounding is 6e-7, so the
 # outcome depends on the draw (it passed in two of three GPU runs of this round).  Relative L2 of the pair is ~1e-7.
+#
+# test_cdl.py:110-119 (propagate vs dense CSI of a 2 x 2 CDL link at fs = 1 MHz, outputs of magnitude ~10, 6 decimals): the link
+# moves at 5 m/s, which at that sampling rate is "fast" (1.1e-4 rad per sample).  Until the planner gave fast links shorter Taylor
+# tiles it fell through to the per-ray FP64 kernel even in the f32 mode and passed by being exact; now it runs the FP32 kernel
+# (relative L2 ~1e-7 against the oracle, tests/test_cdl_gpu.py::test_fast_links_stay_on_the_taylor_path) and misses the absolute
+# 1.5e-6 of the element-wise check.
 F32_PRECISION_EXCEPTIONS = {"unit_tests.channel.test_fading.TestMultipathFadingSample.test_propagate_state",
-                            "unit_tests.channel.test_fading.TestMultipathFadingChannel.test_channel_gain"}
+                            "unit_tests.channel.test_fading.TestMultipathFadingChannel.test_channel_gain",
+                            "unit_tests.channel.test_cdl.TestClusterDelayLineSample.test_propagate_state"}
 
 
 def _flatten(suite):
