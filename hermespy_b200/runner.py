@@ -336,10 +336,9 @@ def _worker_main(conn, make_lanes) -> None:
     global _rpc_conn
     _rpc_conn = conn
     lanes = make_lanes()
-    try:  # one thread per helper: the helpers ARE the parallelism (BLAS / OpenMP pools would oversubscribe the cores)
-        import torch
-
-        torch.set_num_threads(1)
+    try:  # one thread per helper: the helpers ARE the parallelism (BLAS / OpenMP pools would oversubscribe the cores).
+        # NOT through torch: ``torch.set_num_threads`` in a forked child whose parent already ran a torch thread pool
+        # blocks ~5 s (measured: tools/experiments/runner_overhead.py) and the helpers never call torch.
         from threadpoolctl import threadpool_limits
 
         threadpool_limits(1)
@@ -593,6 +592,7 @@ def batched_actor_run(self) -> None:
 
     lanes = LaneSet(scenario, self._MonteCarloActor__grid, self._MonteCarloActor__evaluators, config.batch_drops,
                     config.workers, base_seed=scenario.seed if scenario.seed is not None else 0)
+    stats["seconds"] = lanes.seconds  # live: ``Simulation.run()`` returns when the last result is in, before this thread ends
 
     try:
         def sections():  # the queue hands out one section per active grid point per call, until the campaign is served
@@ -617,7 +617,6 @@ def batched_actor_run(self) -> None:
             print(e)
         if done:
             results.append(put(done))
-        stats["seconds"] = dict(lanes.seconds)
     finally:
         lanes.close()
 
