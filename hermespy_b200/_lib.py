@@ -269,6 +269,9 @@ class CdlProblem(C.Structure):
         ("variant", C.c_int32),
         ("tx_elements", C.c_void_p),
         ("rx_elements", C.c_void_p),
+        ("link_term_delay", C.POINTER(C.c_int32)),
+        ("link_los_delay", C.POINTER(C.c_int32)),
+        ("link_los_amplitude", C.POINTER(C.c_double)),
     ]
 
 

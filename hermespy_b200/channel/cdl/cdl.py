@@ -188,14 +188,15 @@ class ClusterDelayLineSample(ChannelSample):
 
 def cdl_propagate_batch(samples: Sequence[ClusterDelayLineSample], signals: Sequence[np.ndarray],
                         precision: Optional[str] = None) -> List[np.ndarray]:
-    """Propagate many (sample, signal) pairs with one pipeline call per shared delay structure."""
+    """Propagate many (sample, signal) pairs with one pipeline call per array geometry and block length; samples with
+    different delay structures (models, delay spreads, line-of-sight states) share it through per-link delay tables."""
     from ...kernels import CdlBlock, cdl_propagate_host
 
     precision = config.precision if precision is None else precision
     groups = {}
     for i, (s, x) in enumerate(zip(samples, signals)):
         x = np.asarray(x)
-        key = (s.kernel_block().group_key(), x.shape, x.dtype.str)
+        key = (s.kernel_block().geometry_key(), x.shape, x.dtype.str)
         groups.setdefault(key, []).append(i)
     out: List[Optional[np.ndarray]] = [None] * len(samples)
     for idx in groups.values():
@@ -205,7 +206,7 @@ def cdl_propagate_batch(samples: Sequence[ClusterDelayLineSample], signals: Sequ
             x = x.astype(np.complex128)
         y = cdl_propagate_host(x, blk, precision=precision)
         for k, i in enumerate(idx):
-            out[i] = y[k]
+            out[i] = y[k] if blk.link_max_delay is None else np.ascontiguousarray(y[k][:, : x.shape[2] + int(blk.link_max_delay[k])])
     return out  # type: ignore[return-value]
 
 

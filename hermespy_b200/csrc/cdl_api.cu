@@ -20,46 +20,12 @@ struct CdlPlan {
 
 constexpr double kCdlPolyTarget = 5e-8;
 
-static int build_cdl_table(const hb_cdl_problem* p, CdlTable* tb) {
-  if (!p) {
-    set_error("problem pointer is NULL");
-    return HB_ERR_INVALID;
-  }
-  if (p->batch < 0 || p->num_tx < 1 || p->num_rx < 1 || p->num_samples < 0 || p->max_delay < 0 || p->num_terms < 0) {
-    set_error("invalid CDL problem shape (B=%d Ntx=%d Nrx=%d T=%d D=%d terms=%d)", p->batch, p->num_tx, p->num_rx,
-              p->num_samples, p->max_delay, p->num_terms);
-    return HB_ERR_INVALID;
-  }
-  const int Rt = p->num_terms + (p->line_of_sight ? 1 : 0);
-  if (Rt < 1 || Rt > kCdlMaxTerms) {
-    set_error("number of ray terms %d outside [1, %d]", Rt, kCdlMaxTerms);
-    return Rt < 1 ? HB_ERR_INVALID : HB_ERR_UNSUPPORTED;
-  }
-  if (p->num_terms > 0 && !p->term_delay) {
-    set_error("term_delay is NULL");
-    return HB_ERR_INVALID;
-  }
-  if (p->precision != HB_F32 && p->precision != HB_F64) {
-    set_error("unknown precision %d", p->precision);
-    return HB_ERR_INVALID;
-  }
-  if (!(p->sampling_rate > 0.0) || p->carrier_frequency < 0.0) {
-    set_error("sampling rate must be positive and carrier frequency non-negative");
-    return HB_ERR_INVALID;
-  }
-  if (p->element_mode < HB_ELEMENTS_IDEAL || p->element_mode > HB_ELEMENTS_PER_ELEMENT) {
-    set_error("unknown element_mode %d", p->element_mode);
-    return HB_ERR_INVALID;
-  }
-  memset(tb, 0, sizeof(*tb));
-  tb->num_terms = Rt;
-  tb->has_los = p->line_of_sight ? 1 : 0;
-  std::vector<int> delay(Rt);
-  for (int t = 0; t < p->num_terms; ++t) delay[t] = p->term_delay[t];
-  if (p->line_of_sight) delay[Rt - 1] = p->los_delay;
+// Terms of one link grouped by delay index (stable: the summation order inside a group is the term order).
+static int group_terms(const std::vector<int>& delay, int max_delay, CdlTable* tb) {
+  const int Rt = (int)delay.size();
   for (int t = 0; t < Rt; ++t) {
-    if (delay[t] < 0 || delay[t] > p->max_delay || delay[t] > 65535) {
-      set_error("ray term %d: delay index %d outside [0, max_delay=%d]", t, delay[t], p->max_delay);
+    if (delay[t] < 0 || delay[t] > max_delay || delay[t] > 65535) {
+      set_error("ray term %d: delay index %d outside [0, max_delay=%d]", t, delay[t], max_delay);
       return HB_ERR_INVALID;
     }
     tb->term_delay[t] = (uint16_t)delay[t];
@@ -83,6 +49,93 @@ static int build_cdl_table(const hb_cdl_problem* p, CdlTable* tb) {
   }
   tb->num_groups = g + 1;
   tb->group_start[tb->num_groups] = (uint16_t)Rt;
+  return HB_OK;
+}
+
+static int max_group_terms_of(const CdlTable& tb) {
+  int m = 1;
+  for (int g = 0; g < tb.num_groups; ++g) m = std::max(m, (int)tb.group_start[g + 1] - (int)tb.group_start[g]);
+  return m;
+}
+
+// Host-side tables of a problem: the launch-uniform one (kernel parameter space) and, for heterogeneous batches
+// (hb_cdl_problem.link_term_delay), one table per link padded to the batch's largest group count.
+struct CdlTables {
+  CdlTable tb;
+  std::vector<CdlTable> links;  // empty: uniform batch
+  std::vector<double> los_amp;  // [B] with `links`
+  int max_group_terms = 1;
+};
+
+static int build_cdl_table(const hb_cdl_problem* p, CdlTables* out) {
+  CdlTable* tb = &out->tb;
+  if (!p) {
+    set_error("problem pointer is NULL");
+    return HB_ERR_INVALID;
+  }
+  if (p->batch < 0 || p->num_tx < 1 || p->num_rx < 1 || p->num_samples < 0 || p->max_delay < 0 || p->num_terms < 0) {
+    set_error("invalid CDL problem shape (B=%d Ntx=%d Nrx=%d T=%d D=%d terms=%d)", p->batch, p->num_tx, p->num_rx,
+              p->num_samples, p->max_delay, p->num_terms);
+    return HB_ERR_INVALID;
+  }
+  const int Rt = p->num_terms + (p->line_of_sight ? 1 : 0);
+  if (Rt < 1 || Rt > kCdlMaxTerms) {
+    set_error("number of ray terms %d outside [1, %d]", Rt, kCdlMaxTerms);
+    return Rt < 1 ? HB_ERR_INVALID : HB_ERR_UNSUPPORTED;
+  }
+  const bool per_link = p->link_term_delay != nullptr && p->batch > 0;
+  if (p->num_terms > 0 && !p->term_delay && !per_link) {
+    set_error("term_delay is NULL");
+    return HB_ERR_INVALID;
+  }
+  if (p->precision != HB_F32 && p->precision != HB_F64) {
+    set_error("unknown precision %d", p->precision);
+    return HB_ERR_INVALID;
+  }
+  if (!(p->sampling_rate > 0.0) || p->carrier_frequency < 0.0) {
+    set_error("sampling rate must be positive and carrier frequency non-negative");
+    return HB_ERR_INVALID;
+  }
+  if (p->element_mode < HB_ELEMENTS_IDEAL || p->element_mode > HB_ELEMENTS_PER_ELEMENT) {
+    set_error("unknown element_mode %d", p->element_mode);
+    return HB_ERR_INVALID;
+  }
+  memset(tb, 0, sizeof(*tb));
+  out->links.clear();
+  out->los_amp.clear();
+  std::vector<int> delay(Rt);
+  if (!per_link) {
+    for (int t = 0; t < p->num_terms; ++t) delay[t] = p->term_delay[t];
+    if (p->line_of_sight) delay[Rt - 1] = p->los_delay;
+    if (int e = group_terms(delay, p->max_delay, tb)) return e;
+    tb->num_terms = Rt;
+    tb->has_los = p->line_of_sight ? 1 : 0;
+    out->max_group_terms = max_group_terms_of(*tb);
+    return HB_OK;
+  }
+  out->links.resize((size_t)p->batch);
+  out->los_amp.assign((size_t)p->batch, p->los_amplitude);
+  int gmax = 0;
+  out->max_group_terms = 1;
+  for (int b = 0; b < p->batch; ++b) {
+    CdlTable* lt = &out->links[(size_t)b];
+    memset(lt, 0, sizeof(*lt));
+    for (int t = 0; t < p->num_terms; ++t) delay[t] = p->link_term_delay[(size_t)b * p->num_terms + t];
+    if (p->line_of_sight) {
+      delay[Rt - 1] = p->link_los_delay ? p->link_los_delay[b] : p->los_delay;
+      if (p->link_los_amplitude) out->los_amp[(size_t)b] = p->link_los_amplitude[b];
+    }
+    if (int e = group_terms(delay, p->max_delay, lt)) return e;
+    lt->num_terms = Rt;
+    lt->has_los = p->line_of_sight ? 1 : 0;
+    gmax = std::max(gmax, lt->num_groups);
+    out->max_group_terms = std::max(out->max_group_terms, max_group_terms_of(*lt));
+  }
+  for (CdlTable& lt : out->links) {  // empty groups up to the batch maximum: zero moments, no terms
+    for (int g = lt.num_groups + 1; g <= gmax; ++g) lt.group_start[g] = (uint16_t)Rt;
+    lt.num_groups = gmax;
+  }
+  *tb = out->links[0];  // shapes (terms, groups, LOS slot) are what the kernels read from the launch table
   return HB_OK;
 }
 
@@ -112,15 +165,14 @@ static int cdl_poly_order(const hb_cdl_problem* p, int tile, int max_group_terms
   return 0;
 }
 
-static int make_cdl_plan(const hb_cdl_problem* p, const CdlTable& tb, CdlPlan* pl) {
+static int make_cdl_plan(const hb_cdl_problem* p, const CdlTables& tabs, CdlPlan* pl) {
+  const CdlTable& tb = tabs.tb;
   const int Tout = p->num_samples + p->max_delay;
   pl->nrx_tpl = p->num_rx <= 1 ? 1 : (p->num_rx <= 2 ? 2 : (p->num_rx <= 4 ? 4 : 8));
   pl->threads = 128;
   pl->bound = 0.0;
   pl->variant = HB_CDL_VARIANT_GATHER;
-  pl->max_group_terms = 1;
-  for (int g = 0; g < tb.num_groups; ++g)
-    pl->max_group_terms = std::max(pl->max_group_terms, (int)tb.group_start[g + 1] - (int)tb.group_start[g]);
+  pl->max_group_terms = tabs.max_group_terms;
   if (p->variant < HB_CDL_VARIANT_AUTO || p->variant > HB_CDL_VARIANT_UMMA_BF16) {
     set_error("unknown CDL variant %d", p->variant);
     return HB_ERR_INVALID;
@@ -340,14 +392,17 @@ static int launch_rays(const CdlArgs& a, const CdlTable& tb, cudaStream_t st) {
   return HB_OK;
 }
 
+// d_link_tab / d_link_los: device copies of the per-link tables of THIS batch slice (nullptr: uniform batch).
 static int cdl_propagate_device(const hb_cdl_problem* p, const CdlTable& tb, const CdlPlan& pl, const void* x, void* y,
-                                cudaStream_t st) {
+                                cudaStream_t st, const CdlTable* d_link_tab = nullptr, const double* d_link_los = nullptr) {
   const int Tout = p->num_samples + p->max_delay;
   if (p->batch == 0 || Tout == 0) return HB_OK;
   CdlArgs a;
   fill_args(p, tb, pl, &a);
   a.x = x;
   a.y = y;
+  a.link_tab = d_link_tab;
+  a.link_los_amp = d_link_los;
   if ((size_t)a.B * a.ntiles * std::max(1, tb.num_groups) > 0x7fffffffull) {
     set_error("CDL grid exceeds the launch limit; split the batch");
     return HB_ERR_UNSUPPORTED;
@@ -400,19 +455,20 @@ using namespace hb;
 extern "C" {
 
 int hb_cdl_plan(const hb_cdl_problem* p, hb_cdl_plan_info* info) {
-  CdlTable tb;
-  if (int e = build_cdl_table(p, &tb)) return e;
+  CdlTables tabs;
+  if (int e = build_cdl_table(p, &tabs)) return e;
   CdlPlan pl;
-  if (int e = make_cdl_plan(p, tb, &pl)) return e;
-  fill_cdl_info(pl, tb, p, info);
+  if (int e = make_cdl_plan(p, tabs, &pl)) return e;
+  fill_cdl_info(pl, tabs.tb, p, info);
   return HB_OK;
 }
 
 int hb_cdl_propagate(const hb_cdl_problem* p, const void* x, void* y, void* stream, hb_cdl_plan_info* info) {
-  CdlTable tb;
-  if (int e = build_cdl_table(p, &tb)) return e;
+  CdlTables tabs;
+  if (int e = build_cdl_table(p, &tabs)) return e;
+  const CdlTable& tb = tabs.tb;
   CdlPlan pl;
-  if (int e = make_cdl_plan(p, tb, &pl)) return e;
+  if (int e = make_cdl_plan(p, tabs, &pl)) return e;
   fill_cdl_info(pl, tb, p, info);
   if (int e = require_device()) return e;
   if (p->batch > 0 && (!x || !y || !p->tx_pose || !p->rx_pose || !p->rel_velocity || !p->tx_topology ||
@@ -421,17 +477,32 @@ int hb_cdl_propagate(const hb_cdl_problem* p, const void* x, void* y, void* stre
     set_error("NULL device pointer in CDL problem");
     return HB_ERR_INVALID;
   }
-  return cdl_propagate_device(p, tb, pl, x, y, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tabs.links.empty()) return cdl_propagate_device(p, tb, pl, x, y, st);
+  // heterogeneous batch: the per-link tables go to the device first (pageable source: the copy is staged before the call
+  // returns, so the vectors may die with this frame)
+  CdlTable* d_tab = nullptr;
+  double* d_los = nullptr;
+  HB_CUDA(cudaMallocAsync((void**)&d_tab, sizeof(CdlTable) * tabs.links.size(), st));
+  cudaError_t e = cudaMallocAsync((void**)&d_los, sizeof(double) * tabs.los_amp.size(), st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, tabs.links.data(), sizeof(CdlTable) * tabs.links.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_los, tabs.los_amp.data(), sizeof(double) * tabs.los_amp.size(), cudaMemcpyHostToDevice, st);
+  int rc = e == cudaSuccess ? cdl_propagate_device(p, tb, pl, x, y, st, d_tab, d_los) : cuda_fail(e, "per-link CDL tables");
+  cudaFreeAsync(d_tab, st);
+  if (d_los) cudaFreeAsync(d_los, st);
+  return rc;
 }
 
 int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32_t chunk_links,
                           hb_cdl_plan_info* info) {
-  CdlTable tb;
-  if (int e = build_cdl_table(p, &tb)) return e;
+  CdlTables tabs;
+  if (int e = build_cdl_table(p, &tabs)) return e;
+  const CdlTable& tb = tabs.tb;
   CdlPlan pl;
-  if (int e = make_cdl_plan(p, tb, &pl)) return e;
+  if (int e = make_cdl_plan(p, tabs, &pl)) return e;
   fill_cdl_info(pl, tb, p, info);
   if (int e = require_device()) return e;
+  const bool per_link = !tabs.links.empty();
   const int Tout = p->num_samples + p->max_delay;
   if (p->batch == 0 || Tout == 0) return HB_OK;
   if (!x || !y || !p->tx_pose || !p->rx_pose || !p->rel_velocity || !p->tx_topology || !p->rx_topology ||
@@ -466,7 +537,8 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
   const size_t off_x = take(x_link * chunk), off_y = take(y_link * chunk), off_ang = take(ang_link * chunk),
                off_jon = take(jon_link * chunk), off_amp = take(amp_link * chunk), off_tp = take(96 * (size_t)chunk),
                off_rp = take(96 * (size_t)chunk), off_rv = take(24 * (size_t)chunk), off_tt = take(topo_tx),
-               off_rt = take(topo_rx), off_et = take(el_tx), off_er = take(el_rx);
+               off_rt = take(topo_rx), off_et = take(el_tx), off_er = take(el_rx),
+               off_lt = take(per_link ? sizeof(CdlTable) * (size_t)chunk : 0), off_la = take(per_link ? 8 * (size_t)chunk : 0);
   const size_t total = off;
 
   std::lock_guard<std::mutex> lock(g_pipe.mu);
@@ -505,6 +577,8 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
         {off_rt, p->rx_topology, topo_rx},
         {off_et, p->tx_elements, el_tx},
         {off_er, p->rx_elements, el_rx},
+        {off_lt, per_link ? (const void*)(tabs.links.data() + b0) : nullptr, per_link ? sizeof(CdlTable) * (size_t)nb : 0},
+        {off_la, per_link ? (const void*)(tabs.los_amp.data() + b0) : nullptr, per_link ? 8 * (size_t)nb : 0},
         {off_x, (const char*)x + x_link * b0, x_link * nb},
     };
     for (const Cp& c : cps) {
@@ -516,7 +590,8 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
       }
     }
     if (rc != HB_OK) break;
-    rc = cdl_propagate_device(&q, tb, pl, base + off_x, base + off_y, st);
+    rc = cdl_propagate_device(&q, tb, pl, base + off_x, base + off_y, st,
+                              per_link ? (const CdlTable*)(base + off_lt) : nullptr, per_link ? (const double*)(base + off_la) : nullptr);
     if (rc != HB_OK) break;
     cudaError_t e = cudaMemcpyAsync((char*)y + y_link * b0, base + off_y, y_link * nb, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(D2H, cdl)");
@@ -529,8 +604,13 @@ int hb_cdl_propagate_host(const hb_cdl_problem* p, const void* x, void* y, int32
 }
 
 int hb_cdl_state(const hb_cdl_problem* p, void* h, int32_t* group_delay_out, int32_t* num_groups_out, void* stream) {
-  CdlTable tb;
-  if (int e = build_cdl_table(p, &tb)) return e;
+  CdlTables tabs;
+  if (int e = build_cdl_table(p, &tabs)) return e;
+  if (!tabs.links.empty()) {
+    set_error("hb_cdl_state takes batches of one delay structure (link_term_delay must be NULL): its output is indexed by delay group");
+    return HB_ERR_UNSUPPORTED;
+  }
+  const CdlTable& tb = tabs.tb;
   if (num_groups_out) *num_groups_out = tb.num_groups;
   if (group_delay_out)
     for (int g = 0; g < tb.num_groups; ++g) group_delay_out[g] = tb.group_delay[g];

@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(128) cdl_ray_kernel(const CdlArgs a, const __g
     j10 = make_double2(-1.0, 0.0);
     j11 = make_double2(0.0, 0.0);
     const double2 ph = phasor_neg_turns(dist * a.wavelength_factor);
-    scale = make_double2(a.los_amp * ph.x, a.los_amp * ph.y);
+    const double los_amp = a.link_los_amp ? a.link_los_amp[b] : a.los_amp;
+    scale = make_double2(los_amp * ph.x, los_amp * ph.y);
   }
 
   // polarization towards normalize(target - array position)
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
   const int G = tb.num_groups;
   const int bq = blockIdx.x / G, g = blockIdx.x - bq * G;
   const int b = bq / a.nwin, q = bq - b * a.nwin;
-  const int t0 = tb.group_start[g], t1 = tb.group_start[g + 1];
-  const double shift = (double)q * a.ptile + 0.5 * a.ptile - (double)tb.group_delay[g];
+  const int t0 = cdl_group_start(a, tb, b, g), t1 = cdl_group_start(a, tb, b, g + 1);
+  const double shift = (double)q * a.ptile + 0.5 * a.ptile - (double)cdl_group_delay(a, tb, b, g);
   const int nij = a.nrx * a.ntx;
   float2* out = a.moments + ((((size_t)b * a.nwin + q) * G + g) * P) * nij;
   for (int ij0 = 0; ij0 < nij; ij0 += blockDim.x) {
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
     for (int c0 = t0; c0 < t1; c0 += 64) {
       __syncthreads();
       if (threadIdx.x < 64 && c0 + threadIdx.x < t1) {
-        const int t = tb.term_order[c0 + threadIdx.x];
+        const int t = cdl_term_order(a, tb, b, c0 + threadIdx.x);
         const double w = a.w[(size_t)b * a.Rt + t];
         double turns = w * shift * kInvTwoPi;
         turns -= rint(turns);
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
       if (ij < nij) {
         const int nc = min(64, t1 - c0);
         for (int k = 0; k < nc; ++k) {
-          const int t = tb.term_order[c0 + k];
+          const int t = cdl_term_order(a, tb, b, c0 + k);
           const double2 uv = ray_entry(a, b, t, i, j);
           const float uvr = (float)uv.x, uvi = (float)uv.y;
           float tr = beta[k].x * uvr - beta[k].y * uvi, ti = beta[k].x * uvi + beta[k].y * uvr;
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
   double2* vs = us + kMomTerms * a.nrx * a.rank;                            // [kMomTerms][ntx * rank]
   const int G = tb.num_groups;
   const int b = blockIdx.x / G, g = blockIdx.x - b * G;
-  const int t0 = tb.group_start[g], t1 = tb.group_start[g + 1];
+  const int t0 = cdl_group_start(a, tb, b, g), t1 = cdl_group_start(a, tb, b, g + 1);
+  const int gdelay = cdl_group_delay(a, tb, b, g);
   const int nij = a.nrx * a.ntx;
   const int nu = a.nrx * a.rank, nv = a.ntx * a.rank;
   const int tid = threadIdx.x;
@@ -341,9 +343,9 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
         __syncthreads();
         for (int e = tid; e < nc * nq; e += 128) {
           const int k = e / nq, q = e - k * nq;
-          const int t = tb.term_order[c0 + k];
+          const int t = cdl_term_order(a, tb, b, c0 + k);
           const double w = a.w[(size_t)b * a.Rt + t];
-          const double shift = (double)(q0 + q) * a.ptile + 0.5 * a.ptile - (double)tb.group_delay[g];
+          const double shift = (double)(q0 + q) * a.ptile + 0.5 * a.ptile - (double)gdelay;
           double turns = w * shift * kInvTwoPi;
           turns -= rint(turns);
           double sn, cs;
@@ -364,11 +366,11 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
         }
         for (int e = tid; e < nc * nu; e += 128) {
           const int k = e / nu, c = e - k * nu;
-          us[k * nu + c] = a.u[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nu + c];
+          us[k * nu + c] = a.u[((size_t)b * a.Rt + cdl_term_order(a, tb, b, c0 + k)) * nu + c];
         }
         for (int e = tid; e < nc * nv; e += 128) {
           const int k = e / nv, c = e - k * nv;
-          vs[k * nv + c] = a.v[((size_t)b * a.Rt + tb.term_order[c0 + k]) * nv + c];
+          vs[k * nv + c] = a.v[((size_t)b * a.Rt + cdl_term_order(a, tb, b, c0 + k)) * nv + c];
         }
         __syncthreads();
         if (ij < nij) {
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(THREADS) cdl_poly_kernel(const CdlArgs a, cons
     __syncthreads();
 
     for (int g = 0; g < G; ++g) {
-      const int off = tid + a.Dpad - tb.group_delay[g];
+      const int off = tid + a.Dpad - cdl_group_delay(a, tb, b, g);
       const float2* mg = ms + (size_t)g * P * NRX * kCdlTxChunk;
       for (int jj = 0; jj < nj; ++jj) {
         float2 xv[R];
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(128) cdl_direct_f64_kernel(const CdlArgs a, co
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = make_double2(0.0, 0.0);
     for (int t = 0; t < a.Rt; ++t) {
-      const int n = m - (int)tb.term_delay[t];
+      const int n = m - cdl_term_delay(a, tb, b, t);
       if (n < 0 || n >= a.T) continue;
       const double2* v = a.v + ((size_t)b * a.Rt + t) * a.ntx * a.rank;
       double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
@@ -578,8 +580,8 @@ __global__ void __launch_bounds__(128) cdl_state_kernel(const CdlArgs a, const _
   if (n >= a.T) return;
   const int i = ij / a.ntx, j = ij - i * a.ntx;
   double2 h = make_double2(0.0, 0.0);
-  for (int c = tb.group_start[g]; c < tb.group_start[g + 1]; ++c) {
-    const int t = tb.term_order[c];
+  for (int c = cdl_group_start(a, tb, b, g); c < cdl_group_start(a, tb, b, g + 1); ++c) {
+    const int t = cdl_term_order(a, tb, b, c);
     double sn, cs;
     sincos(a.w[(size_t)b * a.Rt + t] * (double)n, &sn, &cs);
     const double2 uv = ray_entry(a, b, t, i, j);

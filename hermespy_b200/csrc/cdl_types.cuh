@@ -49,6 +49,24 @@ struct CdlArgs {
   int tile, ntiles, Dpad, P;
   int ptile, nwin;  // Taylor window length (a multiple of tile) and windows per frame: moments are [B, nwin, G, P, Nrx, Ntx]
   int rx0, nrx_chunk;
+  // heterogeneous batches (hb_cdl_problem.link_term_delay): one table per link in device memory, padded to the launch
+  // table's num_terms / num_groups (empty groups: group_start[g] == group_start[g + 1]); NULL = the launch-uniform table
+  const CdlTable* link_tab;
+  const double* link_los_amp;  // [B], NULL = los_amp
 };
+
+// Table lookups: the per-link table of link b when the batch carries one, else the launch-uniform table in parameter space.
+__device__ __forceinline__ int cdl_group_delay(const CdlArgs& a, const CdlTable& tb, int b, int g) {
+  return a.link_tab ? a.link_tab[b].group_delay[g] : tb.group_delay[g];
+}
+__device__ __forceinline__ int cdl_group_start(const CdlArgs& a, const CdlTable& tb, int b, int g) {
+  return a.link_tab ? (int)a.link_tab[b].group_start[g] : (int)tb.group_start[g];
+}
+__device__ __forceinline__ int cdl_term_order(const CdlArgs& a, const CdlTable& tb, int b, int c) {
+  return a.link_tab ? (int)a.link_tab[b].term_order[c] : (int)tb.term_order[c];
+}
+__device__ __forceinline__ int cdl_term_delay(const CdlArgs& a, const CdlTable& tb, int b, int t) {
+  return a.link_tab ? (int)a.link_tab[b].term_delay[t] : (int)tb.term_delay[t];
+}
 
 }  // namespace hb

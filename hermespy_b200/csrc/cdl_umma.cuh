@@ -246,6 +246,12 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
         const int q = item % a.ntiles;
         const bool active = mt * 128 < min(S::TILE, Tout - q * S::TILE);
+        int gd0 = 0, gd1 = 0;  // heterogeneous batch: this link's group delays, lane l holds groups l and l + 32
+        if (a.link_tab) {
+          const int32_t* gdl = a.link_tab[item / a.ntiles].group_delay;
+          gd0 = lane < G ? gdl[lane] : 0;
+          gd1 = lane + 32 < G ? gdl[lane + 32] : 0;
+        }
         if (ic >= 1) {  // the epilogue has drained this M-tile's accumulators of the previous window
           mbar_wait(&bar_acc_empty[mt], (ic - 1u) & 1u);
           fence_after_sync();
@@ -260,7 +266,8 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
             const uint64_t da_hi = smem_desc(sA, a_plane, 128u), da_lo = smem_desc(sA + 2u * a_plane, a_plane, 128u);
             uint64_t db = smem_desc(smem0 + (uint32_t)slot * stage_bytes + a_bytes, b_chunk, 128u);
             for (int g = 0; g < G; ++g) {
-              const uint64_t k = (uint64_t)(uint32_t)tb.group_delay[g];  // start-address field counts 16-byte rows
+              // start-address field counts 16-byte rows
+              const uint64_t k = (uint64_t)(uint32_t)(a.link_tab ? __shfl_sync(0xffffffffu, g < 32 ? gd0 : gd1, g & 31) : tb.group_delay[g]);
               mma_tf32_elect(d, da_hi - k, db, idesc_full, (uint32_t)((s >> 1) | g));
               mma_tf32_elect(d + S::N1P, da_lo - k, db, idesc_hi, 1u);
               db += (uint64_t)(b_group >> 4);

@@ -210,6 +210,12 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_bf16_kernel(const CdlA
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
         const int q = item % a.ntiles;
         const bool active = mt * 128 < min(kCbTile, Tout - q * kCbTile);
+        int gd0 = 0, gd1 = 0;  // heterogeneous batch: this link's group delays, lane l holds groups l and l + 32
+        if (a.link_tab) {
+          const int32_t* gdl = a.link_tab[item / a.ntiles].group_delay;
+          gd0 = lane < G ? gdl[lane] : 0;
+          gd1 = lane + 32 < G ? gdl[lane + 32] : 0;
+        }
         if (ic >= 1) {  // the epilogue has drained this M-tile's accumulator of the previous item
           mbar_wait(&bar_acc_empty[mt], (ic - 1u) & 1u);
           fence_after_sync();
@@ -225,7 +231,8 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_bf16_kernel(const CdlA
                            da2 = smem_desc(sA + 2u * a_split, a_plane, 128u);
             uint64_t db = smem_desc(smem0 + (uint32_t)slot * stage_bytes + a_bytes, b_chunk, 128u);
             for (int g = 0; g < G; ++g) {
-              const uint64_t k = (uint64_t)(uint32_t)tb.group_delay[g];  // start-address field counts 16-byte rows
+              // start-address field counts 16-byte rows
+              const uint64_t k = (uint64_t)(uint32_t)(a.link_tab ? __shfl_sync(0xffffffffu, g < 32 ? gd0 : gd1, g & 31) : tb.group_delay[g]);
               mma_bf16_elect(d, da0 - k, db, id3, (uint32_t)(s | g));
               mma_bf16_elect(d + N1P, da1 - k, db, id2, 1u);
               mma_bf16_elect(d + 2 * N1P, da2 - k, db, id1, 1u);

@@ -546,9 +546,25 @@ class CdlBlock:
     #: None = unrotated ideal isotropic elements (include/hermes_b200.h, hb_element_mode)
     tx_elements: Optional[np.ndarray] = None
     rx_elements: Optional[np.ndarray] = None
+    #: heterogeneous batch (``hb_cdl_problem.link_term_delay``): per-link delay indices int32 [B, Rn], line-of-sight delay
+    #: int32 [B] and amplitude f64 [B] (0 = link without a line of sight) and the links' own ``max_delay`` int [B] (the
+    #: batch runs with the largest; a link's output is the first ``T + link_max_delay[b]`` samples).  None = uniform batch.
+    link_term_delay: Optional[np.ndarray] = None
+    link_los_delay: Optional[np.ndarray] = None
+    link_los_amplitude: Optional[np.ndarray] = None
+    link_max_delay: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.term_delay = np.ascontiguousarray(self.term_delay, dtype=np.int32)
+        if self.link_term_delay is not None:
+            B = np.asarray(self.angles).shape[0]
+            self.link_term_delay = np.ascontiguousarray(self.link_term_delay, dtype=np.int32).reshape(B, -1)
+            if self.link_term_delay.shape[1] != self.term_delay.shape[0]:
+                raise ValueError("link_term_delay must have shape [B, Rn]")
+            full = lambda v, fill, dt: np.ascontiguousarray(np.full(B, fill) if v is None else v, dtype=dt).reshape(B)
+            self.link_los_delay = full(self.link_los_delay, self.los_delay, np.int32)
+            self.link_los_amplitude = full(self.link_los_amplitude, self.los_amplitude, np.float64)
+            self.link_max_delay = full(self.link_max_delay, self.max_delay, np.int64)
         self.angles = np.ascontiguousarray(self.angles, dtype=np.float64)
         self.jones = np.ascontiguousarray(self.jones, dtype=np.complex128)
         self.amplitude = np.ascontiguousarray(self.amplitude, dtype=np.float64)
@@ -601,23 +617,62 @@ class CdlBlock:
             d[k] = getter(getattr(self, k)) if self.tx_elements is not None else None
         return d
 
+    def per_link(self):
+        """``(term_delay [B, Rn], los_delay [B], los_amplitude [B], max_delay [B])`` of this block, uniform or not."""
+        if self.link_term_delay is not None:
+            return self.link_term_delay, self.link_los_delay, self.link_los_amplitude, self.link_max_delay
+        B = self.batch
+        return (np.broadcast_to(self.term_delay, (B, self.term_delay.shape[0])), np.full(B, self.los_delay, dtype=np.int32),
+                np.full(B, self.los_amplitude if self.line_of_sight else 0.0), np.full(B, self.max_delay, dtype=np.int64))
+
     @classmethod
     def stack(cls, blocks) -> "CdlBlock":
+        """Blocks of one array geometry along the batch axis.  Blocks that differ in their delay structure (cluster delays,
+        ray count, line-of-sight state, delay spread: stochastic scenario realizations) give a heterogeneous batch: rays
+        padded with zero-amplitude copies of each link's first ray, per-link delay tables, the largest ``max_delay``."""
         b0 = blocks[0]
-        return cls(
-            term_delay=b0.term_delay, max_delay=b0.max_delay,
-            angles=np.concatenate([b.angles for b in blocks]), jones=np.concatenate([b.jones for b in blocks]),
-            amplitude=np.concatenate([b.amplitude for b in blocks]), tx_pose=np.concatenate([b.tx_pose for b in blocks]),
-            rx_pose=np.concatenate([b.rx_pose for b in blocks]),
-            rel_velocity=np.concatenate([b.rel_velocity for b in blocks]), tx_topology=b0.tx_topology,
-            rx_topology=b0.rx_topology, carrier_frequency=b0.carrier_frequency, sampling_rate=b0.sampling_rate,
-            line_of_sight=b0.line_of_sight, los_delay=b0.los_delay, los_amplitude=b0.los_amplitude,
-            max_speed=max(b.max_speed for b in blocks), tx_elements=b0.tx_elements, rx_elements=b0.rx_elements)
+        cat = lambda f: np.concatenate([getattr(b, f) for b in blocks])
+        common = dict(tx_pose=cat("tx_pose"), rx_pose=cat("rx_pose"), rel_velocity=cat("rel_velocity"),
+                      tx_topology=b0.tx_topology, rx_topology=b0.rx_topology, carrier_frequency=b0.carrier_frequency,
+                      sampling_rate=b0.sampling_rate, max_speed=max(b.max_speed for b in blocks),
+                      tx_elements=b0.tx_elements, rx_elements=b0.rx_elements)
+        if all(b.link_term_delay is None and b.delay_key() == b0.delay_key() for b in blocks):
+            return cls(term_delay=b0.term_delay, max_delay=b0.max_delay, angles=cat("angles"), jones=cat("jones"),
+                       amplitude=cat("amplitude"), line_of_sight=b0.line_of_sight, los_delay=b0.los_delay,
+                       los_amplitude=b0.los_amplitude, **common)
+        rn = max(1, max(b.term_delay.shape[0] for b in blocks))
+
+        def pad(a, fill_first: bool):  # [B, Rn_b, ...] -> [B, rn, ...]: zero amplitudes, finite angles / polarizations
+            if a.shape[1] == rn:
+                return a
+            out = np.zeros((a.shape[0], rn) + a.shape[2:], dtype=a.dtype)
+            out[:, : a.shape[1]] = a
+            if fill_first:
+                out[:, a.shape[1]:] = a[:, :1] if a.shape[1] else 1.0
+            return out
+
+        parts = [b.per_link() for b in blocks]
+        return cls(term_delay=np.zeros(rn, dtype=np.int32), max_delay=int(max(p[3].max() for p in parts)),
+                   angles=np.concatenate([pad(b.angles, True) for b in blocks]),
+                   jones=np.concatenate([pad(b.jones, True) for b in blocks]),
+                   amplitude=np.concatenate([pad(b.amplitude, False) for b in blocks]),
+                   line_of_sight=any(b.line_of_sight for b in blocks), los_delay=0, los_amplitude=0.0,
+                   link_term_delay=np.concatenate([pad(np.ascontiguousarray(p[0]), False) for p in parts]),
+                   link_los_delay=np.concatenate([p[1] for p in parts]),
+                   link_los_amplitude=np.concatenate([p[2] for p in parts]),
+                   link_max_delay=np.concatenate([p[3] for p in parts]), **common)
+
+    def delay_key(self):
+        """What a launch-uniform delay table is built from."""
+        return (self.term_delay.tobytes(), self.max_delay, self.line_of_sight, self.los_delay, self.los_amplitude)
+
+    def geometry_key(self):
+        """What blocks must share to travel in one (possibly heterogeneous) batch: arrays, elements, carrier, rate."""
+        el = b"" if self.tx_elements is None else self.tx_elements.tobytes() + self.rx_elements.tobytes()
+        return (self.tx_topology.tobytes(), self.rx_topology.tobytes(), self.carrier_frequency, self.sampling_rate, el)
 
     def group_key(self):
-        el = b"" if self.tx_elements is None else self.tx_elements.tobytes() + self.rx_elements.tobytes()
-        return (self.term_delay.tobytes(), self.max_delay, self.tx_topology.tobytes(), self.rx_topology.tobytes(),
-                self.carrier_frequency, self.sampling_rate, self.line_of_sight, self.los_delay, self.los_amplitude, el)
+        return self.delay_key() + self.geometry_key()
 
 
 _CDL_VARIANT = {"auto": 0, "gather": 1, "umma": 2, "umma_bf16": 3}
@@ -650,6 +705,10 @@ def _cdl_problem(blk: CdlBlock, num_samples: int, precision, io128: bool, ptrs: 
     p.los_amplitude = float(blk.los_amplitude)
     p.max_speed = float(blk.max_speed)
     p.term_delay = blk.term_delay.ctypes.data_as(C.POINTER(C.c_int32))
+    if blk.link_term_delay is not None:  # host arrays in every entry (include/hermes_b200.h)
+        p.link_term_delay = blk.link_term_delay.ctypes.data_as(C.POINTER(C.c_int32))
+        p.link_los_delay = blk.link_los_delay.ctypes.data_as(C.POINTER(C.c_int32))
+        p.link_los_amplitude = blk.link_los_amplitude.ctypes.data_as(C.POINTER(C.c_double))
     p.angles = ptrs["angles"]
     p.jones = ptrs["jones"]
     p.amplitude = ptrs["amplitude"]

@@ -170,8 +170,10 @@ def finish_links(matrix, pending: Sequence[_Pending], results: Sequence[np.ndarr
 def propagate_requests(requests: Sequence[tuple], precision: str | None = None, device: int | None = None) -> List[np.ndarray]:
     """All (kind, parameter block, x, zero) requests -> propagated blocks, ONE host-buffer launch per delay structure.
 
-    ``hb_fading_propagate_host`` / ``hb_cdl_propagate_host`` take launch-uniform delay tables, so requests are grouped by
-    (kind, delay table, antenna counts, block length); the links of a group are stacked along the batch axis."""
+    ``hb_fading_propagate_host`` takes a launch-uniform delay table: fading requests are grouped by (delay table, antenna
+    counts, block length).  CDL requests are grouped by array geometry and block length only: realizations with their own
+    cluster delays / cluster counts / line-of-sight state (the stochastic 3GPP scenarios) travel as ONE heterogeneous batch
+    with per-link delay tables (``hb_cdl_problem.link_term_delay``)."""
     from .kernels import CdlBlock, cdl_propagate_host, fading_propagate_host
 
     precision = config.precision if precision is None else precision
@@ -190,7 +192,7 @@ def propagate_requests(requests: Sequence[tuple], precision: str | None = None, 
             if zero:
                 out[i] = np.zeros((blk.num_rx, x.shape[1] + blk.max_delay), dtype=np.complex128)
                 continue
-            key = ("cdl", blk.group_key(), x.shape)
+            key = ("cdl", blk.geometry_key(), x.shape)  # delay structures may differ: CdlBlock.stack pads, per-link tables
         groups.setdefault(key, []).append(i)
     for key, idx in groups.items():
         x = np.stack([requests[i][2] for i in idx])
@@ -201,7 +203,13 @@ def propagate_requests(requests: Sequence[tuple], precision: str | None = None, 
                                       stack("spatial"), omega_max=max(requests[i][1]["omega_max"] for i in idx),
                                       precision=precision, sos_mode=config.sos_mode, device=device)
         else:
-            y = cdl_propagate_host(x, CdlBlock.stack([requests[i][1] for i in idx]), precision=precision, device=device)
+            blk = CdlBlock.stack([requests[i][1] for i in idx])
+            y = cdl_propagate_host(x, blk, precision=precision, device=device)
+            if blk.link_max_delay is not None:  # heterogeneous batch: every link keeps its own T + max_delay samples
+                T = x.shape[2]
+                for k, i in enumerate(idx):
+                    out[i] = np.ascontiguousarray(y[k][:, : T + int(blk.link_max_delay[k])])
+                continue
         for k, i in enumerate(idx):
             out[i] = y[k]
     return out

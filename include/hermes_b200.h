@@ -226,6 +226,15 @@ typedef struct hb_cdl_problem {
   int32_t variant;             /* hb_cdl_variant: which K6 kernel the POLY mode runs (f32 only)     */
   const double* tx_elements;   /* DEVICE f64 [Ntx or 1, HB_ELEMENT_STRIDE]                          */
   const double* rx_elements;   /* DEVICE f64 [Nrx or 1, HB_ELEMENT_STRIDE]                          */
+  /* Heterogeneous batches: links whose realizations drew their own cluster delays, cluster counts and line-of-sight
+   * state (the stochastic 3GPP scenarios, cluster_delay_lines.py:1824-2013) in ONE launch set.  link_term_delay != NULL
+   * switches the delay structure from launch-uniform to per link: every link gets its own term -> delay-group table in
+   * device memory, padded to the batch maximum of groups.  num_terms and line_of_sight stay batch-wide: links with fewer
+   * rays are padded by the caller with zero-amplitude rays, links without a line of sight carry link_los_amplitude 0.
+   * The three arrays are HOST memory in both the device-pointer and the host-buffer entry (like term_delay). */
+  const int32_t* link_term_delay;   /* HOST int32 [B, Rn], NULL = term_delay for every link               */
+  const int32_t* link_los_delay;    /* HOST int32 [B] (only read when line_of_sight), NULL = los_delay    */
+  const double* link_los_amplitude; /* HOST f64 [B] (only read when line_of_sight), NULL = los_amplitude  */
 } hb_cdl_problem;
 
 typedef struct hb_cdl_plan_info {
