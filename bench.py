@@ -688,8 +688,8 @@ def measure_simulation(args, world, rank, dev):
     workers = max(1, cores - 1) if world == 1 else 0
     out = {"api": "hermespy.simulation.Simulation.run() (unmodified script), dropin.enable(precision='f64', batch_drops, workers)",
            "host_cores": cores, "helper_processes_per_rank": workers}
-    for name, samples, lanes in (("c1", 200 if world == 1 else 40, 128 if world == 1 else 32),
-                                 ("ofdm", 32 if world == 1 else 8, 64 if world == 1 else 16)):
+    for name, samples, lanes in (("c1", 400 if world == 1 else 40, 64 if world == 1 else 32),
+                                 ("ofdm", 64 if world == 1 else 8, 64 if world == 1 else 16)):
         rec = sc.run_gpu(name, samples, "f64", lanes, workers)
         t = torch.tensor([rec["seconds"]], dtype=torch.float64, device=dev)
         if world > 1:

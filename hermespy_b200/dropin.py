@@ -171,7 +171,21 @@ def _dev_fading_propagate(b: dict, x: np.ndarray) -> np.ndarray:
                                  sos_mode=config.sos_mode, device=config.device)[0]
 
 
-def _dev_fading_state(b: dict, keep: np.ndarray, num_samples: int):
+def _to_host(t, out_alloc=None) -> np.ndarray:
+    """Device tensor -> numpy; ``out_alloc(shape, dtype)`` supplies the destination (the runner hands out slices of the
+    calling helper's page-locked shared-memory window, so the copy is one DMA and nothing is pickled)."""
+    if out_alloc is None:
+        return t.cpu().numpy()
+    import torch
+
+    dst = out_alloc(tuple(t.shape), np.complex128 if t.dtype == torch.complex128 else np.complex64)
+    if dst is None:
+        return t.cpu().numpy()
+    torch.from_numpy(dst).copy_(t)
+    return dst
+
+
+def _dev_fading_state(b: dict, keep: np.ndarray, num_samples: int, out_alloc=None):
     from . import _lib
     from .kernels import FadingBatch, fading_state
 
@@ -180,7 +194,7 @@ def _dev_fading_state(b: dict, keep: np.ndarray, num_samples: int):
                                 b["amp"][None][:, keep], b["spatial"][None], omega_max=b["omega_max"],
                                 device=f"cuda:{config.device}")
     h, group_delay = fading_state(fb, int(num_samples), precision=config.precision, io128=True)
-    return h[0].cpu().numpy(), group_delay
+    return _to_host(h[0], out_alloc), group_delay
 
 
 def _dev_cdl_propagate(blk, x: np.ndarray) -> np.ndarray:
@@ -189,17 +203,19 @@ def _dev_cdl_propagate(blk, x: np.ndarray) -> np.ndarray:
     return cdl_propagate_host(x[None], blk, precision=config.precision, device=config.device)[0]
 
 
-def _dev_cdl_state(blk, num_samples: int):
+def _dev_cdl_state(blk, num_samples: int, out_alloc=None):
     from . import _lib
     from .kernels import CdlDeviceBlock, cdl_state
 
     _lib.set_device(config.device)
     h, gd = cdl_state(CdlDeviceBlock(blk, device=f"cuda:{config.device}"), int(num_samples))
-    return h[0].cpu().numpy(), gd  # [G, Nrx, Ntx, T]
+    return _to_host(h[0], out_alloc), gd  # [G, Nrx, Ntx, T]
 
 
 DEVICE_CALLS = {"fading_propagate": _dev_fading_propagate, "fading_state": _dev_fading_state,
                 "cdl_propagate": _dev_cdl_propagate, "cdl_state": _dev_cdl_state}
+#: calls whose large result can be written straight into a caller-supplied buffer (keyword ``out_alloc``)
+DEVICE_CALLS_WITH_OUT = frozenset(("fading_state", "cdl_state"))
 
 
 def _device(name: str, *args):

@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import copy
 import multiprocessing as mp
+import os
 import queue
 import threading
 import time
@@ -316,6 +317,105 @@ class Lane(object):
 
 _rpc_conn = None  # inside a lane worker: the pipe to the process that owns the GPU
 _rpc_stash: list = []  # work messages that arrived while a device call was waiting for its answer (pipelined rounds)
+_rpc_shm = None  # inside a lane worker: its shared-memory window for the large results of device calls
+
+#: bytes of the shared-memory window each helper offers for device-call results (ideal-CSI ``state()`` arrays: megabytes
+#: per drop).  The GPU owner page-locks the windows and copies device -> window in one DMA; only a descriptor crosses
+#: the pipe.  0 disables the windows (results are pickled through the pipe).
+RPC_SHM_BYTES = int(os.environ.get("HB_RPC_SHM_BYTES", 64 << 20))
+
+
+class _ShmRef(object):
+    """Descriptor of an array that lives in the helper's shared-memory window."""
+
+    __slots__ = ("offset", "shape", "dtype")
+
+    def __init__(self, offset, shape, dtype):
+        self.offset, self.shape, self.dtype = int(offset), tuple(shape), str(dtype)
+
+
+class _Window(object):
+    """One helper's shared-memory window, created by the GPU owner BEFORE the fork (the helper inherits the mapping) and
+    page-locked AFTER it (CUDA marks registered ranges MADV_DONTFORK).  The owner unlinks it, whatever happens to the helper."""
+
+    def __init__(self, nbytes: int) -> None:
+        from multiprocessing import shared_memory
+
+        self.shm = shared_memory.SharedMemory(create=True, size=int(nbytes))
+        self.pinned = False
+
+    def pin(self) -> None:
+        import ctypes
+        import sys
+
+        torch = sys.modules.get("torch")  # the GPU owner has it loaded; never pay an import (seconds) for pinning
+        try:
+            if torch is not None and torch.cuda.is_initialized():
+                self._anchor = ctypes.c_char.from_buffer(self.shm.buf)
+                self.pinned = int(torch.cuda.cudart().cudaHostRegister(ctypes.addressof(self._anchor), self.shm.size, 0)) == 0
+        except Exception:
+            self.pinned = False  # pageable windows still work (staged copies)
+
+    def release(self) -> None:
+        import ctypes
+        import sys
+
+        try:
+            if self.pinned:
+                sys.modules["torch"].cuda.cudart().cudaHostUnregister(ctypes.addressof(self._anchor))
+        except Exception:
+            pass
+        self._anchor = None
+        for step in (self.shm.close, self.shm.unlink):
+            try:
+                step()
+            except Exception:  # views handed out earlier may still pin the mapping: the name is gone, the pages follow
+                pass
+
+
+def _serve_device_call(name: str, args, shm) -> Any:
+    """One helper's device call, in the GPU owner.  With a window, large results are written into it and replaced by
+    ``_ShmRef`` descriptors."""
+    from . import dropin
+
+    import inspect
+
+    call = dropin.DEVICE_CALLS[name]
+    if shm is None or name not in dropin.DEVICE_CALLS_WITH_OUT or "out_alloc" not in inspect.signature(call).parameters:
+        return call(*args)
+    used = [0]
+    handed: list = []
+
+    def out_alloc(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        start = (used[0] + 255) & ~255
+        if start + nbytes > shm.size:
+            return None  # does not fit: this array travels through the pipe
+        used[0] = start + nbytes
+        arr = np.ndarray(shape, dtype=dtype, buffer=shm.buf, offset=start)
+        handed.append((arr, start))
+        return arr
+
+    result = call(*args, out_alloc=out_alloc)
+
+    def pack(o):
+        if isinstance(o, tuple):
+            return tuple(pack(v) for v in o)
+        for arr, start in handed:
+            if o is arr:
+                return _ShmRef(start, arr.shape, arr.dtype.str)
+        return o
+
+    return pack(result)
+
+
+def _unpack_shm(o):
+    """Helper side: descriptors -> array views on the own window (valid until the next device call of this process)."""
+    if isinstance(o, tuple):
+        return tuple(_unpack_shm(v) for v in o)
+    if isinstance(o, _ShmRef):
+        return np.ndarray(o.shape, dtype=np.dtype(o.dtype), buffer=_rpc_shm.buf, offset=o.offset)
+    return o
 
 
 def device_call(name: str, *args):
@@ -334,15 +434,17 @@ def device_call(name: str, *args):
         _rpc_stash.append(msg)  # the owner already queued this helper's next stage: keep it for the main loop
     if msg[0] != "rpc_ok":
         raise RuntimeError(f"device call {name} failed in the GPU process: {msg[1]}")
-    return msg[1]
+    return _unpack_shm(msg[1])
 
 
-def _worker_main(conn, make_lanes) -> None:
+def _worker_main(conn, make_lanes, window=None) -> None:
     """Serve the lanes of one helper process: ('pre', {lane: section}) -> requests; ('post', {lane: results}) -> artifacts.
     The helper builds its own lanes (``make_lanes()``: deep copies of the tuple it inherited by fork), so the copies of all
-    helpers are made in parallel instead of one after the other in the parent."""
-    global _rpc_conn
+    helpers are made in parallel instead of one after the other in the parent.  ``window``: the shared-memory object the
+    GPU owner writes large device-call results into (inherited mapping)."""
+    global _rpc_conn, _rpc_shm
     _rpc_conn = conn
+    _rpc_shm = window
     lanes = make_lanes()
     try:  # one thread per helper: the helpers ARE the parallelism (BLAS / OpenMP pools would oversubscribe the cores).
         # NOT through torch: ``torch.set_num_threads`` in a forked child whose parent already ran a torch thread pool
@@ -373,7 +475,7 @@ def _worker_main(conn, make_lanes) -> None:
             conn.send(("error", (op, tag, f"{type(e).__name__}: {e}\n{traceback.format_exc()}")))
 
 
-def _writer_main(conn, outbox) -> None:
+def _writer_main(conn, outbox, lock) -> None:
     """Messages to one helper leave through this thread: the GPU owner must keep READING the helpers' replies while a
     large payload (propagated blocks) is still draining into a pipe whose other end is busy sending its own reply --
     two blocking sends facing each other would never finish."""
@@ -382,7 +484,8 @@ def _writer_main(conn, outbox) -> None:
         if msg is None:
             return
         try:
-            conn.send(msg)
+            with lock:
+                conn.send(msg)
         except Exception:  # the helper is gone or the pipe was closed under us: nothing left to deliver
             return
 
@@ -405,8 +508,10 @@ class LaneSet(object):
         self.local: dict = {}
         self.procs: list = []
         self.outbox: list = []
+        self.send_lock: list = []  # per helper pipe: one sender at a time (writer thread / device-call answers)
         self.writers: list = []
         self._mail: dict = {}
+        self.windows: list = []  # per helper: _Window or None
         #: where the GPU owner's wall time went (run_stream): waiting for the helpers' stages, the device call, hand-over
         self.seconds = {"setup": 0.0, "sections": 0.0, "wait_pre": 0.0, "propagate": 0.0, "send": 0.0, "wait_post": 0.0}
         workers = min(int(workers), self.num_lanes)
@@ -422,17 +527,29 @@ class LaneSet(object):
             for w in range(workers):
                 mine = list(range(w, self.num_lanes, workers))
                 parent, child = ctx.Pipe()
-                p = ctx.Process(target=_worker_main, args=(child, lambda mine=mine: {k: make(k) for k in mine}), daemon=True)
+                window = None
+                if RPC_SHM_BYTES > 0:
+                    try:
+                        window = _Window(RPC_SHM_BYTES)
+                    except Exception:
+                        window = None  # no /dev/shm: results travel through the pipe
+                self.windows.append(window)
+                p = ctx.Process(target=_worker_main, daemon=True,
+                                args=(child, lambda mine=mine: {k: make(k) for k in mine}, None if window is None else window.shm))
                 p.start()
                 child.close()
                 self.procs.append((p, parent))
                 box: queue.SimpleQueue = queue.SimpleQueue()
-                th = threading.Thread(target=_writer_main, args=(parent, box), daemon=True)
+                self.send_lock.append(threading.Lock())
+                th = threading.Thread(target=_writer_main, args=(parent, box, self.send_lock[-1]), daemon=True)
                 th.start()
                 self.outbox.append(box)
                 self.writers.append(th)
                 for k in mine:
                     self.owner[k] = w
+            for window in self.windows:  # after the last fork
+                if window is not None:
+                    window.pin()
         else:
             self.local = {k: make(k) for k in range(self.num_lanes)}
         self.seconds["setup"] = time.perf_counter() - t_setup
@@ -548,10 +665,17 @@ class LaneSet(object):
                     raise RuntimeError(f"lane worker {conns.pop(conn)} died") from None
                 if status == "rpc":
                     name, args = reply
+                    window = self.windows[conns[conn]]
+                    # answered from this thread (the helper is waiting): under the pipe's send lock, because the helper's
+                    # writer thread may be in the middle of a message and two senders would interleave their bytes.  No
+                    # deadlock: a helper that asked is reading its pipe until the answer arrives, so the writer drains.
                     try:
-                        conn.send(("rpc_ok", dropin.DEVICE_CALLS[name](*args)))
+                        shm = None if window is None else window.shm
+                        answer = ("rpc_ok", _serve_device_call(name, args, shm))
                     except Exception as e:
-                        conn.send(("rpc_error", f"{type(e).__name__}: {e}"))
+                        answer = ("rpc_error", f"{type(e).__name__}: {e}")
+                    with self.send_lock[conns[conn]]:
+                        conn.send(answer)
                 elif status == "ok":
                     rop, rtag, payload = reply
                     self._mail.setdefault((rop, rtag), {}).update(payload)
@@ -559,18 +683,30 @@ class LaneSet(object):
                     raise RuntimeError(f"lane worker {conns[conn]} failed in {reply[0]}: {reply[2]}")
         return [box.pop(lane) for lane in lanes]
 
-    def close(self) -> None:
+    def close(self, abort: bool = False) -> None:
+        """Stop the helpers.  ``abort``: the stream ended early (an exception, or the campaign was called off while rounds
+        were in flight): helpers and writer threads may be blocked on full pipes facing each other, so nobody is asked
+        politely -- the helpers are terminated first, which unblocks every sender."""
+        if abort:
+            for p, _ in self.procs:
+                if p.is_alive():
+                    p.terminate()
         for box in self.outbox:
             box.put(("stop", 0, None))
             box.put(None)
-        for th in self.writers:  # the stop messages are on their way before any pipe is closed
-            th.join(timeout=5)
+        deadline = time.monotonic() + 5.0  # one budget for all of them, not one per thread / process
         for p, conn in self.procs:
-            p.join(timeout=5)
+            p.join(timeout=max(0.0, deadline - time.monotonic()))
             if p.is_alive():
                 p.terminate()
+                p.join(timeout=1.0)
             conn.close()
-        self.procs, self.outbox, self.writers = [], [], []
+        for th in self.writers:  # their pipes are closed now: a blocked send has failed, a waiting get has its None
+            th.join(timeout=max(0.1, deadline - time.monotonic()))
+        for window in self.windows:
+            if window is not None:
+                window.release()
+        self.procs, self.outbox, self.writers, self.windows, self.send_lock = [], [], [], [], []
 
 
 # ---- the actor's run loop (replaces MonteCarloActor.run for SimulationActor while the runner is enabled) -----------------
@@ -601,6 +737,7 @@ def batched_actor_run(self) -> None:
     lanes = LaneSet(scenario, self._MonteCarloActor__grid, self._MonteCarloActor__evaluators, config.batch_drops,
                     config.workers, base_seed=scenario.seed if scenario.seed is not None else 0)
     stats["seconds"] = lanes.seconds  # live: ``Simulation.run()`` returns when the last result is in, before this thread ends
+    finished = False
 
     try:
         def sections():  # the queue hands out one section per active grid point per call, until the campaign is served
@@ -619,14 +756,20 @@ def batched_actor_run(self) -> None:
                 if len(done) >= lanes.num_lanes:
                     results.append(put(done))
                     done = []
+            finished = True
         except Exception as e:
-            if not self.catch_exceptions:
-                raise UnmatchableException(f"Actor #{self.index} encountered an error during run: {e}") from e
-            print(e)
-        if done:
+            # The campaign loop collects what it needs and shuts the engine down without waiting for its actors
+            # (monte_carlo.py:404-470 kills them): a queue call failing on the closed engine is the normal end of a run
+            # that still had rounds in flight, not an error of this actor.
+            called_off = isinstance(e, RuntimeError) and "after shutdown" in str(e)
+            if not called_off:
+                if not self.catch_exceptions:
+                    raise UnmatchableException(f"Actor #{self.index} encountered an error during run: {e}") from e
+                print(e)
+        if done and finished:
             results.append(put(done))
     finally:
-        lanes.close()
+        lanes.close(abort=not finished)  # rounds in flight: helpers and writers may be blocked on each other's pipes
 
 
 _original_run = None

@@ -193,6 +193,61 @@ def test_device_calls_from_helper_processes_are_served_by_the_gpu_owner():
         assert [[float(a.to_scalar()) for a in g[k]] for g in got] == want
 
 
+def test_device_call_results_travel_through_the_helpers_shared_memory_windows():
+    """Large device-call results (ideal-CSI ``state()`` arrays) are written by the GPU owner straight into the calling
+    helper's shared-memory window; only a descriptor crosses the pipe.  Same artifacts as through the pipe."""
+    load_reference()
+    import hermespy_b200.dropin as dropin
+    from hermespy_b200 import runner
+    from hermespy_b200.runner import LaneSet
+    from tests.test_dropin_gpu import _ofdm_2x1_alamouti_tdl_b
+
+    scenario, tx, rx, ber = _ofdm_2x1_alamouti_tdl_b(42)
+    through_window = []
+
+    def fake_state(b, keep, num_samples, out_alloc=None):
+        n = np.arange(num_samples)
+        K = b["omega"].shape[1]
+        amp = b["amp"][:, [0] + [1] * (K - 1), None]
+        h = (amp * np.exp(1j * (b["omega"][:, :, None] * n + b["phi"][:, :, None]))).sum(1)[keep]
+        gd = np.unique(b["tap_delay"][keep])
+        res = np.stack([h[b["tap_delay"][keep] == d].sum(0) for d in gd])
+        dst = None if out_alloc is None else out_alloc(res.shape, res.dtype)
+        through_window.append(dst is not None)
+        if dst is None:
+            return res, gd
+        dst[...] = res
+        return dst, gd
+
+    def run(window_bytes):
+        old = runner.RPC_SHM_BYTES
+        runner.RPC_SHM_BYTES = window_bytes
+        dropin.patch_reference()
+        real = dropin.DEVICE_CALLS["fading_state"]
+        dropin.DEVICE_CALLS["fading_state"] = fake_state
+        try:
+            lanes = LaneSet(scenario, [], [ber], 3, 2, base_seed=3, first_lane_is_original=False, propagate=_oracle_propagate)
+            try:
+                return [[float(a.to_scalar()) for a in arts] for arts in lanes.run_round([(), (), ()])]
+            finally:
+                lanes.close()
+        finally:
+            dropin.DEVICE_CALLS["fading_state"] = real
+            dropin.disable()
+            runner.RPC_SHM_BYTES = old
+
+    del through_window[:]
+    with_window = run(64 << 20)
+    assert through_window.count(True) >= 3  # one per helper-lane drop (the warm-up drop runs in this process: no window)
+    del through_window[:]
+    without = run(0)
+    assert not any(through_window)
+    del through_window[:]
+    tiny = run(4096)  # a window too small for the array: falls back to the pipe, same result
+    assert not any(through_window)
+    assert with_window == without == tiny
+
+
 def test_pipelined_stream_over_helper_processes():
     """``run_stream``: two lane groups alternate so that helpers always have a group's stages to run; every section is
     served exactly once and every lane's drops equal the serial reference schedule of that lane."""

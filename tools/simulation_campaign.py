@@ -208,7 +208,12 @@ def main():
     path = args.out or os.path.join(ROOT, "gpurun_out", f"simulation_campaign_{args.config}.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     json.dump(out, open(path, "w"), indent=1)
-    print(json.dumps({k: v for k, v in out.items() if not isinstance(v, dict)}))
+    print(json.dumps({k: v for k, v in out.items() if not isinstance(v, dict)}), flush=True)
+    if os.environ.get("HB_EXIT_WATCHDOG"):  # diagnose a slow interpreter exit: all thread stacks after N seconds, then leave
+        import faulthandler
+
+        faulthandler.dump_traceback_later(float(os.environ["HB_EXIT_WATCHDOG"]), exit=True, file=sys.stderr)
+        print("main() returned at", time.perf_counter(), file=sys.stderr, flush=True)
 
 
 if __name__ == "__main__":
