@@ -173,7 +173,7 @@ def _dev_fading_propagate(b: dict, x: np.ndarray) -> np.ndarray:
 
 def _to_host(t, out_alloc=None) -> np.ndarray:
     """Device tensor -> numpy; ``out_alloc(shape, dtype)`` supplies the destination (the runner hands out slices of the
-    calling helper's page-locked shared-memory window, so the copy is one DMA and nothing is pickled)."""
+    calling helper's shared-memory window: the device-to-host copy lands where the helper reads it, nothing is pickled)."""
     if out_alloc is None:
         return t.cpu().numpy()
     import torch

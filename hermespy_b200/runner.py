@@ -320,8 +320,8 @@ _rpc_stash: list = []  # work messages that arrived while a device call was wait
 _rpc_shm = None  # inside a lane worker: its shared-memory window for the large results of device calls
 
 #: bytes of the shared-memory window each helper offers for device-call results (ideal-CSI ``state()`` arrays: megabytes
-#: per drop).  The GPU owner page-locks the windows and copies device -> window in one DMA; only a descriptor crosses
-#: the pipe.  0 disables the windows (results are pickled through the pipe).
+#: per drop).  The GPU owner copies device -> window and only a descriptor crosses the pipe.  0 disables the windows
+#: (results are pickled through the pipe).
 RPC_SHM_BYTES = int(os.environ.get("HB_RPC_SHM_BYTES", 64 << 20))
 
 
@@ -335,41 +335,21 @@ class _ShmRef(object):
 
 
 class _Window(object):
-    """One helper's shared-memory window, created by the GPU owner BEFORE the fork (the helper inherits the mapping) and
-    page-locked AFTER it (CUDA marks registered ranges MADV_DONTFORK).  The owner unlinks it, whatever happens to the helper."""
+    """One helper's shared-memory window, created by the GPU owner BEFORE the fork (the helper inherits the mapping); the
+    owner unlinks it, whatever happens to the helper.  Deliberately NOT page-locked: ``cudaHostRegister`` of 16 x 64 MB costs
+    0.5 .. 1.5 s per ``Simulation.run()`` and holds the context lock against the propagate launches when done in the
+    background (measured: OFDM campaign 267 -> 141 drops/s), for 0.35 ms per drop of faster copies the owner does not need."""
 
     def __init__(self, nbytes: int) -> None:
         from multiprocessing import shared_memory
 
         self.shm = shared_memory.SharedMemory(create=True, size=int(nbytes))
-        self.pinned = False
-
-    def pin(self) -> None:
-        import ctypes
-        import sys
-
-        torch = sys.modules.get("torch")  # the GPU owner has it loaded; never pay an import (seconds) for pinning
-        try:
-            if torch is not None and torch.cuda.is_initialized():
-                self._anchor = ctypes.c_char.from_buffer(self.shm.buf)
-                self.pinned = int(torch.cuda.cudart().cudaHostRegister(ctypes.addressof(self._anchor), self.shm.size, 0)) == 0
-        except Exception:
-            self.pinned = False  # pageable windows still work (staged copies)
 
     def release(self) -> None:
-        import ctypes
-        import sys
-
-        try:
-            if self.pinned:
-                sys.modules["torch"].cuda.cudart().cudaHostUnregister(ctypes.addressof(self._anchor))
-        except Exception:
-            pass
-        self._anchor = None
         for step in (self.shm.close, self.shm.unlink):
             try:
                 step()
-            except Exception:  # views handed out earlier may still pin the mapping: the name is gone, the pages follow
+            except Exception:  # views handed out earlier may still hold the mapping: the name is gone, the pages follow
                 pass
 
 
@@ -522,6 +502,7 @@ class LaneSet(object):
             warm = Lane.clone_of(scenario, grid, evaluators, 10**6, base_seed, stage_arguments)
             warm.after_propagate(self.propagate(warm.before_propagate()))
             del warm
+            self.seconds["setup_warm_drop"] = time.perf_counter() - t_setup
             ctx = mp.get_context("fork")  # lanes travel by fork: no pickling of scenarios, exactly the parent's objects
             self.owner = {}
             for w in range(workers):
@@ -547,9 +528,7 @@ class LaneSet(object):
                 self.writers.append(th)
                 for k in mine:
                     self.owner[k] = w
-            for window in self.windows:  # after the last fork
-                if window is not None:
-                    window.pin()
+            self.seconds["setup_fork"] = time.perf_counter() - t_setup - self.seconds.get("setup_warm_drop", 0.0)
         else:
             self.local = {k: make(k) for k in range(self.num_lanes)}
         self.seconds["setup"] = time.perf_counter() - t_setup

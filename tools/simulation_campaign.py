@@ -8,6 +8,8 @@ drop runner with the channel on the GPU.
            (the reference's getting-started simulation).
 * ``ofdm`` the C2 frame through a modem the reference can demodulate: 2x1 Alamouti OFDM, 1024 subcarriers x 14 symbols
            (15 344 samples @30.72 MHz), ideal CSI, TDL-B 300 ns with Doppler, 7 SNR points.
+* ``uma``  the same link over the stochastic 3GPP Urban Macrocell model (cluster_delay_lines.py:1824-2013): every drop draws
+           its own line-of-sight state, cluster count and cluster delays; 3 SNR points.
 
 Arms, same script text, same box:
   reference   ``cores`` processes, each running ``Simulation.run()`` on its share of the samples with the reference's numpy
@@ -56,7 +58,15 @@ def build_c1(num_samples, seed):
     return sim
 
 
-def build_ofdm(num_samples, seed):
+def build_uma(num_samples, seed):
+    """The OFDM link of ``build_ofdm`` over a STOCHASTIC 3GPP scenario (UMa, line-of-sight state drawn per realization):
+    every drop has its own cluster delays / cluster count, so a batch of drops is a heterogeneous CDL batch."""
+    from hermespy.channel import UrbanMacrocells
+
+    return build_ofdm(num_samples, seed, channel=UrbanMacrocells(seed=seed + 7), snrs=(0, 10, 20), rx_velocity=(3.0, -1.0, 0.0))
+
+
+def build_ofdm(num_samples, seed, channel=None, snrs=(0, 5, 10, 15, 20, 25, 30), rx_velocity=None):
     from hermespy.channel import TDL, TDLType
     from hermespy.core import ConsoleMode, Transformation, dB
     from hermespy.modem import (Alamouti, BitErrorEvaluator, ChannelEqualization, ElementType, GridElement, GridResource,
@@ -74,8 +84,11 @@ def build_ofdm(num_samples, seed):
                               antennas=SimulatedUniformArray(SimulatedIdealAntenna, 0.5 * lam, [n, 1, 1]))
 
     tx, rx = dev(2, (0.0, 0.0, 25.0)), dev(1, (100.0, 20.0, 1.5))
-    rx.noise_level = SNR(dB(15), tx)
-    ch = TDL(TDLType.B, rms_delay=300e-9, doppler_frequency=100.0)
+    if rx_velocity is not None:
+        rx.velocity = np.array(rx_velocity, float)
+    ch = TDL(TDLType.B, rms_delay=300e-9, doppler_frequency=100.0) if channel is None else channel
+    # scenario models carry a path loss: the noise level follows the sample's expected energy scale (noise/level.py:207-241)
+    rx.noise_level = SNR(dB(15), tx) if channel is None else SNR(dB(15), tx, ch)
     sim.set_channel(tx, rx, ch)
     link = SimplexLink(seed=seed + 1)
     tx.transmitters.add(link)
@@ -87,12 +100,12 @@ def build_ofdm(num_samples, seed):
     link.waveform.channel_equalization = ChannelEqualization()
     link.transmit_symbol_coding[0] = Alamouti()
     link.receive_symbol_coding[0] = Alamouti()
-    sim.new_dimension("noise_level", dB(0, 5, 10, 15, 20, 25, 30), rx)
+    sim.new_dimension("noise_level", dB(*snrs), rx)
     sim.add_evaluator(BitErrorEvaluator(link, link))
     return sim
 
 
-BUILDERS = {"c1": (build_c1, 11), "ofdm": (build_ofdm, 7)}
+BUILDERS = {"c1": (build_c1, 11), "ofdm": (build_ofdm, 7), "uma": (build_uma, 3)}
 
 
 def _fast_polling(sim):
