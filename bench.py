@@ -39,7 +39,14 @@ import sys
 import threading
 import time
 
-import numpy as np
+# One BLAS / OpenMP thread per process, set BEFORE numpy loads its BLAS: every CPU leg of this file (cpu_baseline, the
+# reference arm, the reference side of simulation_api) runs one worker PROCESS per host core, like Ray's one actor per core
+# (monte_carlo.py:176,621).  Left at the default, 16 processes x 16 BLAS threads oversubscribe the box and the reference's
+# matmul-heavy CDL code runs 50x slower than it should (measured: UMa 0.53 against 26 drops/s) -- unfair to the reference.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -666,9 +673,9 @@ def _traffic(cfg, kname, B):
 
 def measure_simulation(args, world, rank, dev):
     """End to end through the UNMODIFIED ``Simulation.run()`` API (north_star): drops/s of the reference's own scripts with
-    the channel on the GPU and the batched drop runner (hermespy_b200/runner.py).  Two scripts: BASELINE config C1 (SISO RRC
-    over TDL-A, 11 SNR points) and the C2 frame through a modem the reference can demodulate (2x1 Alamouti OFDM, 1024
-    subcarriers, ideal CSI, TDL-B).  N = 1: helper processes on the host cores, and the stock reference on all host cores
+    the channel on the GPU and the batched drop runner (hermespy_b200/runner.py).  Three scripts: BASELINE config C1 (SISO RRC
+    over TDL-A, 11 SNR points), the C2 frame through a modem the reference can demodulate (2x1 Alamouti OFDM, 1024
+    subcarriers, ideal CSI, TDL-B) and the same link over the stochastic 3GPP UMa scenario (heterogeneous CDL batches).  N = 1: helper processes on the host cores, and the stock reference on all host cores
     beside it.  N > 1: every rank runs its own campaign share with in-process lanes (no fork next to NCCL)."""
     import torch
     import torch.distributed as dist
@@ -689,7 +696,8 @@ def measure_simulation(args, world, rank, dev):
     out = {"api": "hermespy.simulation.Simulation.run() (unmodified script), dropin.enable(precision='f64', batch_drops, workers)",
            "host_cores": cores, "helper_processes_per_rank": workers}
     for name, samples, lanes in (("c1", 400 if world == 1 else 40, 64 if world == 1 else 32),
-                                 ("ofdm", 64 if world == 1 else 8, 64 if world == 1 else 16)):
+                                 ("ofdm", 64 if world == 1 else 8, 64 if world == 1 else 16),
+                                 ("uma", 64 if world == 1 else 8, 64 if world == 1 else 16)):
         rec = sc.run_gpu(name, samples, "f64", lanes, workers)
         t = torch.tensor([rec["seconds"]], dtype=torch.float64, device=dev)
         if world > 1:

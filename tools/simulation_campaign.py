@@ -119,6 +119,12 @@ def _fast_polling(sim):
 def _reference_process(args):
     """One host process of the reference arm: Simulation.run() on its share of the samples (numpy channel)."""
     cfg, samples, seed = args
+    try:  # one thread per process also when the importing program loaded its BLAS with the default thread count
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
     from oracle.refload import load_reference
 
     load_reference()
