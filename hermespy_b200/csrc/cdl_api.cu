@@ -272,7 +272,8 @@ static int launch_moments(const CdlArgs& a, const CdlTable& tb, cudaStream_t st)
   ProfileScope prof(KIND_CDL_RAYS, st);
   const size_t smem = sizeof(float2) * (size_t)kMomTerms * kMomWin * P + sizeof(double2) * (size_t)kMomTerms * a.rank * (a.nrx + a.ntx);
   if (smem <= 48 * 1024) {  // one CTA per (link, delay group), all Taylor windows at once
-    cdl_moment_all_kernel<P><<<(unsigned)((size_t)a.B * tb.num_groups), 128, smem, st>>>(a, tb);
+    if (a.link_tab) cdl_moment_all_kernel<P, true><<<(unsigned)((size_t)a.B * tb.num_groups), 128, smem, st>>>(a, tb);
+    else cdl_moment_all_kernel<P, false><<<(unsigned)((size_t)a.B * tb.num_groups), 128, smem, st>>>(a, tb);
   } else {  // arrays beyond ~80 elements per side: the per-window kernel reads the steering phases from global memory
     const size_t blocks = (size_t)a.B * a.nwin * tb.num_groups;
     cdl_moment_kernel<P><<<(unsigned)blocks, 128, 0, st>>>(a, tb);

@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(128) cdl_moment_kernel(const CdlArgs a, const 
 constexpr int kMomTerms = 32;  // ray terms staged per pass
 constexpr int kMomWin = 4;     // Taylor windows accumulated per pass
 
-template <int P>
+// HET: the batch carries per-link delay tables (a.link_tab); the uniform instantiation reads parameter space only.
+template <int P, bool HET>
 __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, const __grid_constant__ CdlTable tb) {
   extern __shared__ __align__(16) unsigned char mom_smem[];
   float2* gam = reinterpret_cast<float2*>(mom_smem);                 // [kMomTerms][kMomWin][P]
@@ -323,8 +324,11 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
   double2* vs = us + kMomTerms * a.nrx * a.rank;                            // [kMomTerms][ntx * rank]
   const int G = tb.num_groups;
   const int b = blockIdx.x / G, g = blockIdx.x - b * G;
-  const int t0 = cdl_group_start(a, tb, b, g), t1 = cdl_group_start(a, tb, b, g + 1);
-  const int gdelay = cdl_group_delay(a, tb, b, g);
+  const int t0 = HET ? (int)a.link_tab[b].group_start[g] : (int)tb.group_start[g],
+            t1 = HET ? (int)a.link_tab[b].group_start[g + 1] : (int)tb.group_start[g + 1];
+  const uint16_t* lorder = HET ? a.link_tab[b].term_order : nullptr;
+  auto term_at = [&](int c) { return HET ? (int)lorder[c] : (int)tb.term_order[c]; };
+  const int gdelay = HET ? a.link_tab[b].group_delay[g] : tb.group_delay[g];
   const int nij = a.nrx * a.ntx;
   const int nu = a.nrx * a.rank, nv = a.ntx * a.rank;
   const int tid = threadIdx.x;
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
         __syncthreads();
         for (int e = tid; e < nc * nq; e += 128) {
           const int k = e / nq, q = e - k * nq;
-          const int t = cdl_term_order(a, tb, b, c0 + k);
+          const int t = term_at(c0 + k);
           const double w = a.w[(size_t)b * a.Rt + t];
           const double shift = (double)(q0 + q) * a.ptile + 0.5 * a.ptile - (double)gdelay;
           double turns = w * shift * kInvTwoPi;
@@ -366,11 +370,11 @@ __global__ void __launch_bounds__(128) cdl_moment_all_kernel(const CdlArgs a, co
         }
         for (int e = tid; e < nc * nu; e += 128) {
           const int k = e / nu, c = e - k * nu;
-          us[k * nu + c] = a.u[((size_t)b * a.Rt + cdl_term_order(a, tb, b, c0 + k)) * nu + c];
+          us[k * nu + c] = a.u[((size_t)b * a.Rt + term_at(c0 + k)) * nu + c];
         }
         for (int e = tid; e < nc * nv; e += 128) {
           const int k = e / nv, c = e - k * nv;
-          vs[k * nv + c] = a.v[((size_t)b * a.Rt + cdl_term_order(a, tb, b, c0 + k)) * nv + c];
+          vs[k * nv + c] = a.v[((size_t)b * a.Rt + term_at(c0 + k)) * nv + c];
         }
         __syncthreads();
         if (ij < nij) {

@@ -265,12 +265,20 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_kernel(const CdlArgs a
             const uint32_t sA = smem0 + (uint32_t)slot * stage_bytes + (uint32_t)(mt * 128 + a.Dpad) * 16u;
             const uint64_t da_hi = smem_desc(sA, a_plane, 128u), da_lo = smem_desc(sA + 2u * a_plane, a_plane, 128u);
             uint64_t db = smem_desc(smem0 + (uint32_t)slot * stage_bytes + a_bytes, b_chunk, 128u);
-            for (int g = 0; g < G; ++g) {
-              // start-address field counts 16-byte rows
-              const uint64_t k = (uint64_t)(uint32_t)(a.link_tab ? __shfl_sync(0xffffffffu, g < 32 ? gd0 : gd1, g & 31) : tb.group_delay[g]);
-              mma_tf32_elect(d, da_hi - k, db, idesc_full, (uint32_t)((s >> 1) | g));
-              mma_tf32_elect(d + S::N1P, da_lo - k, db, idesc_hi, 1u);
-              db += (uint64_t)(b_group >> 4);
+            if (a.link_tab == nullptr) {  // the uniform loop stays free of the per-link select (it is the critical path)
+              for (int g = 0; g < G; ++g) {
+                const uint64_t k = (uint64_t)(uint32_t)tb.group_delay[g];  // start-address field counts 16-byte rows
+                mma_tf32_elect(d, da_hi - k, db, idesc_full, (uint32_t)((s >> 1) | g));
+                mma_tf32_elect(d + S::N1P, da_lo - k, db, idesc_hi, 1u);
+                db += (uint64_t)(b_group >> 4);
+              }
+            } else {
+              for (int g = 0; g < G; ++g) {
+                const uint64_t k = (uint64_t)(uint32_t)__shfl_sync(0xffffffffu, g < 32 ? gd0 : gd1, g & 31);
+                mma_tf32_elect(d, da_hi - k, db, idesc_full, (uint32_t)((s >> 1) | g));
+                mma_tf32_elect(d + S::N1P, da_lo - k, db, idesc_hi, 1u);
+                db += (uint64_t)(b_group >> 4);
+              }
             }
           }
           commit_elect(&bar_empty[slot]);

@@ -230,13 +230,22 @@ __global__ void __launch_bounds__(kCuThreads, 1) cdl_umma_bf16_kernel(const CdlA
             const uint64_t da0 = smem_desc(sA, a_plane, 128u), da1 = smem_desc(sA + a_split, a_plane, 128u),
                            da2 = smem_desc(sA + 2u * a_split, a_plane, 128u);
             uint64_t db = smem_desc(smem0 + (uint32_t)slot * stage_bytes + a_bytes, b_chunk, 128u);
-            for (int g = 0; g < G; ++g) {
-              // start-address field counts 16-byte rows
-              const uint64_t k = (uint64_t)(uint32_t)(a.link_tab ? __shfl_sync(0xffffffffu, g < 32 ? gd0 : gd1, g & 31) : tb.group_delay[g]);
-              mma_bf16_elect(d, da0 - k, db, id3, (uint32_t)(s | g));
-              mma_bf16_elect(d + N1P, da1 - k, db, id2, 1u);
-              mma_bf16_elect(d + 2 * N1P, da2 - k, db, id1, 1u);
-              db += (uint64_t)(b_group >> 4);
+            if (a.link_tab == nullptr) {  // the uniform loop stays free of the per-link select (it is the critical path)
+              for (int g = 0; g < G; ++g) {
+                const uint64_t k = (uint64_t)(uint32_t)tb.group_delay[g];  // start-address field counts 16-byte rows
+                mma_bf16_elect(d, da0 - k, db, id3, (uint32_t)(s | g));
+                mma_bf16_elect(d + N1P, da1 - k, db, id2, 1u);
+                mma_bf16_elect(d + 2 * N1P, da2 - k, db, id1, 1u);
+                db += (uint64_t)(b_group >> 4);
+              }
+            } else {
+              for (int g = 0; g < G; ++g) {
+                const uint64_t k = (uint64_t)(uint32_t)__shfl_sync(0xffffffffu, g < 32 ? gd0 : gd1, g & 31);
+                mma_bf16_elect(d, da0 - k, db, id3, (uint32_t)(s | g));
+                mma_bf16_elect(d + N1P, da1 - k, db, id2, 1u);
+                mma_bf16_elect(d + 2 * N1P, da2 - k, db, id1, 1u);
+                db += (uint64_t)(b_group >> 4);
+              }
             }
           }
           commit_elect(&bar_empty[slot]);
