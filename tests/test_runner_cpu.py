@@ -316,3 +316,51 @@ def test_large_payloads_do_not_deadlock_the_pipeline():
         dropin.DEVICE_CALLS["fading_state"] = real
         dropin.disable()
     assert len(got) == 24 and served["n"] == 48
+
+
+def test_a_called_off_stream_closes_at_once_and_leaves_no_windows_behind():
+    """The reference's campaign loop collects what it needs and kills its actors while rounds are in flight
+    (monte_carlo.py:404-470).  Helpers and writer threads are then blocked on each other's pipes: ``close(abort=True)``
+    must not wait for them politely (it did: 5 s per thread and process, 80 s at interpreter exit with 16 helpers), and the
+    helpers' shared-memory windows must be gone afterwards."""
+    import os
+    import time
+
+    import hermespy_b200.dropin as dropin
+    from hermespy_b200.runner import LaneSet
+    from tests.test_dropin_gpu import _ofdm_2x1_alamouti_tdl_b
+
+    load_reference()
+    scenario, tx, rx, ber = _ofdm_2x1_alamouti_tdl_b(42)
+
+    def fake_state(b, keep, num_samples, out_alloc=None):
+        gd = np.unique(b["tap_delay"][keep])
+        return np.ones((gd.size, num_samples), dtype=np.complex128), gd
+
+    def sections():  # the engine goes away after ten sections
+        for _ in range(10):
+            yield ()
+        raise RuntimeError("cannot schedule new futures after shutdown")
+
+    shm_before = set(os.listdir("/dev/shm")) if os.path.isdir("/dev/shm") else set()
+    dropin.patch_reference()
+    real = dropin.DEVICE_CALLS["fading_state"]
+    dropin.DEVICE_CALLS["fading_state"] = fake_state
+    try:
+        lanes = LaneSet(scenario, [], [ber], 8, 4, base_seed=5, first_lane_is_original=False, propagate=_oracle_propagate)
+        procs = [p for p, _ in lanes.procs]
+        assert len(lanes.windows) == 4 and all(w is not None for w in lanes.windows)
+        got = []
+        with pytest.raises(RuntimeError, match="after shutdown"):
+            for item in lanes.run_stream(sections(), groups=2):
+                got.append(item)
+        t0 = time.perf_counter()
+        lanes.close(abort=True)
+        dt = time.perf_counter() - t0
+    finally:
+        dropin.DEVICE_CALLS["fading_state"] = real
+        dropin.disable()
+    assert dt < 4.0, f"close(abort=True) took {dt:.1f} s"
+    assert not any(p.is_alive() for p in procs)
+    if os.path.isdir("/dev/shm"):
+        assert set(os.listdir("/dev/shm")) <= shm_before
