@@ -79,6 +79,7 @@ struct Plan {
   int f64poly;      // HB_F64 on the Taylor path (fading_poly64.cuh): FP64 moments + FP64 gather kernel
   int fused;        // large arrays up to 64 x 64: u = S x on the tensor cores with the delay lines on its accumulator (ONE kernel)
   int variant, poly_tile, npoly, threads, large_halo, lin;  // POLY: kernel variant, Taylor window, windows per link, CTA size
+  int unstaged;     // DIRECT: x read from global memory, FP64 evaluation (delay spreads no staged tile can hold)
   size_t smem;
   double bound;
   WindowPlan wp;
@@ -216,7 +217,7 @@ static void plan_tma(const hb_fading_problem* p, const DelayTable& dt, Plan* pl)
   if (pl->lin) pl->bound += curv;
 }
 
-static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl, bool allow_tma = true) {
+static int make_plan_as_asked(const hb_fading_problem* p, const DelayTable& dt, Plan* pl, bool allow_tma) {
   const int Tout = p->num_samples + p->max_delay;
   const int K = p->num_sinusoids + 1;
   pl->Dpad = (p->max_delay + 1) & ~1;
@@ -226,6 +227,7 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
   const int tile_cap = std::max(kThreads, ((Tout + kThreads - 1) / kThreads) * kThreads);
 
   pl->f64poly = 0;
+  pl->unstaged = 0;
   if (f64 && (p->sos_mode == HB_SOS_AUTO || p->sos_mode == HB_SOS_POLY)) {
     // float64 parity mode on the Taylor path (fading_poly64.cuh) when the truncation bound can be held below 1e-14 and
     // (AUTO) the phases of the frame are small enough for the reference's own argument rounding not to matter
@@ -421,6 +423,16 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
                            ((size_t)(pl->tile + pl->Dpad) + p->num_rx);
     pl->smem -= per_ant * (old - pl->ntx_tpl);
   }
+  if (pl->mode == HB_SOS_DIRECT && pl->smem > kSmemHardLimit) {
+    // No staged tile can hold this delay spread: per-sample FP64 evaluation with x read from global memory.  Slow (no
+    // reuse of x in shared memory) but complete -- the reference handles such links and there is no CPU path behind us.
+    pl->unstaged = 1;
+    pl->ntx_tpl = pick_ntx_template(std::min(p->num_tx, 8));
+    int tpc = (int)std::max<size_t>(1, kDirectParamBytes / (K * sizeof(double2)));
+    tpc = std::min(tpc, p->num_taps);
+    pl->taps_per_chunk = tpc;
+    pl->smem = sizeof(double2) * (size_t)p->num_rx * pl->ntx_tpl + (size_t)tpc * K * sizeof(double2) + (size_t)tpc * 2 * sizeof(double);
+  }
   if (pl->variant != HB_VARIANT_TMA && pl->variant != HB_VARIANT_FUSED && pl->smem > kSmemHardLimit) {
     set_error("delay spread of %d samples needs %zu bytes of shared memory per CTA (limit %zu)", p->max_delay,
               pl->smem, kSmemHardLimit);
@@ -428,6 +440,33 @@ static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl,
   }
   pl->ntiles = std::max(1, (Tout + pl->tile - 1) / pl->tile);
   return HB_OK;
+}
+
+// AUTO / POLY requests whose preferred kernel does not fit (the window kernel keeps an [Nrx x Ntx] spatial matrix and all
+// delay groups' coefficients next to its x tile: thousands of receive antennas or very many groups overflow shared
+// memory) fall back to the gather kernel, which chunks the antennas, and then to per-sample evaluation, before the
+// problem is refused -- the drop-in has no CPU path to hand such a link to.
+static int make_plan(const hb_fading_problem* p, const DelayTable& dt, Plan* pl, bool allow_tma = true) {
+  int rc = make_plan_as_asked(p, dt, pl, allow_tma);
+  if (rc != HB_ERR_UNSUPPORTED || (p->sos_mode != HB_SOS_AUTO && p->sos_mode != HB_SOS_POLY)) return rc;
+  hb_fading_problem q = *p;
+  if (p->precision == HB_F32) {
+    q.sos_mode = HB_SOS_POLY_GATHER;
+    Plan alt;
+    if (make_plan_as_asked(&q, dt, &alt, false) == HB_OK) {
+      *pl = alt;
+      return HB_OK;
+    }
+  }
+  if (p->sos_mode == HB_SOS_AUTO) {
+    q.sos_mode = HB_SOS_DIRECT;
+    Plan alt;
+    if (make_plan_as_asked(&q, dt, &alt, false) == HB_OK) {
+      *pl = alt;
+      return HB_OK;
+    }
+  }
+  return make_plan_as_asked(p, dt, pl, allow_tma);  // restores the first refusal's message
 }
 
 static void fill_info(const Plan& pl, const DelayTable& dt, const hb_fading_problem* p,
@@ -557,10 +596,10 @@ static int launch_chunk(const Plan& pl, bool f64, bool io128, const FadingArgs& 
     }
   }
   switch (pl.ntx_tpl) {
-    case 1: return launch_tdl_direct<1>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
-    case 2: return launch_tdl_direct<2>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
-    case 4: return launch_tdl_direct<4>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
-    default: return launch_tdl_direct<8>(f64, io128, a, dt, pl.taps_per_chunk, pl.smem, st);
+    case 1: return launch_tdl_direct<1>(f64, io128, pl.unstaged != 0, a, dt, pl.taps_per_chunk, pl.smem, st);
+    case 2: return launch_tdl_direct<2>(f64, io128, pl.unstaged != 0, a, dt, pl.taps_per_chunk, pl.smem, st);
+    case 4: return launch_tdl_direct<4>(f64, io128, pl.unstaged != 0, a, dt, pl.taps_per_chunk, pl.smem, st);
+    default: return launch_tdl_direct<8>(f64, io128, pl.unstaged != 0, a, dt, pl.taps_per_chunk, pl.smem, st);
   }
 }
 

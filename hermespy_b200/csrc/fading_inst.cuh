@@ -84,10 +84,10 @@ int launch_tdl_window(int P, bool io128, bool large_halo, bool lin, const Fading
                : launch_window_io<NTX, kWindowHaloSmall, float2>(P, lin, a, wp, threads, smem, st);
 }
 
-template <int NTX, typename REAL, typename IO>
+template <int NTX, typename REAL, typename IO, bool STAGED = true>
 static int launch_direct_one(const FadingArgs& a, const DelayTable& dt, int tpc, size_t smem,
                              cudaStream_t st) {
-  auto kern = tdl_direct_kernel<NTX, REAL, IO>;
+  auto kern = tdl_direct_kernel<NTX, REAL, IO, STAGED>;
   if (int e = ensure_smem(kern, smem)) return e;
   dim3 grid((unsigned)((size_t)a.ntiles * a.B));
   kern<<<grid, kThreads, smem, st>>>(a, dt, tpc);
@@ -96,8 +96,12 @@ static int launch_direct_one(const FadingArgs& a, const DelayTable& dt, int tpc,
 }
 
 template <int NTX>
-int launch_tdl_direct(bool f64, bool io128, const FadingArgs& a, const DelayTable& dt, int tpc, size_t smem,
+int launch_tdl_direct(bool f64, bool io128, bool unstaged, const FadingArgs& a, const DelayTable& dt, int tpc, size_t smem,
                       cudaStream_t st) {
+  if (unstaged) {  // any delay spread: FP64 evaluation, x from global memory (both precision modes)
+    return io128 ? launch_direct_one<NTX, double, double2, false>(a, dt, tpc, smem, st)
+                 : launch_direct_one<NTX, double, float2, false>(a, dt, tpc, smem, st);
+  }
   if (f64) {
     return io128 ? launch_direct_one<NTX, double, double2>(a, dt, tpc, smem, st)
                  : launch_direct_one<NTX, double, float2>(a, dt, tpc, smem, st);
@@ -108,7 +112,7 @@ int launch_tdl_direct(bool f64, bool io128, const FadingArgs& a, const DelayTabl
 
 #define HB_INSTANTIATE_FADING(NTX)                                                                        \
   template int launch_tdl_poly<NTX>(int, bool, const FadingArgs&, const DelayTable&, size_t, cudaStream_t); \
-  template int launch_tdl_direct<NTX>(bool, bool, const FadingArgs&, const DelayTable&, int, size_t,        \
+  template int launch_tdl_direct<NTX>(bool, bool, bool, const FadingArgs&, const DelayTable&, int, size_t,  \
                                       cudaStream_t);                                                        \
   template int launch_tdl_window<NTX>(int, bool, bool, bool, const FadingArgs&, const WindowPlan&, int, size_t,  \
                                       cudaStream_t);

@@ -436,7 +436,10 @@ template <> struct SinParam<double> { using type = double2; };  // (phi, omega)
 
 constexpr int kDirectParamBytes = 32 * 1024;  // per tap-chunk staging budget in shared memory
 
-template <int NTX, typename REAL, typename IO>
+// STAGED = false: x is read from global memory (through L1 / L2) instead of a staged tile + delay halo -- the form that
+// takes ANY delay spread (a 60 000-sample halo of four antennas would need 2 MB of shared memory); the planner's last
+// resort before refusing a link, instantiated for REAL = double only.
+template <int NTX, typename REAL, typename IO, bool STAGED = true>
 __global__ void __launch_bounds__(kThreads) tdl_direct_kernel(const FadingArgs a,
                                                               const __grid_constant__ DelayTable dt,
                                                               const int taps_per_chunk) {
@@ -447,12 +450,13 @@ __global__ void __launch_bounds__(kThreads) tdl_direct_kernel(const FadingArgs a
   const int W = a.tile + a.Dpad;
   const int K = a.K;
   C* xs = reinterpret_cast<C*>(smem_raw);
-  C* Ss = xs + NTX * W;
+  C* Ss = STAGED ? xs + NTX * W : xs;
   SP* sp = reinterpret_cast<SP*>(Ss + a.nrx * NTX);
   REAL* am = reinterpret_cast<REAL*>(sp + taps_per_chunk * K);
 
-  stage_x_tile<NTX, C, IO>(xs, a, b, q, W);
+  if constexpr (STAGED) stage_x_tile<NTX, C, IO>(xs, a, b, q, W);
   stage_spatial<NTX, C>(Ss, a, b);
+  const IO* xg = reinterpret_cast<const IO*>(a.x) + ((size_t)b * a.ntx + a.tx0) * a.T;  // unstaged reads
 
   const double* om_b = a.omega + (size_t)b * a.L * K;
   const double* ph_b = a.phi + (size_t)b * a.L * K;
@@ -528,9 +532,18 @@ __global__ void __launch_bounds__(kThreads) tdl_direct_kernel(const FadingArgs a
       C h;
       h.x = am[2 * ll] * lr + am[2 * ll + 1] * sr;
       h.y = am[2 * ll] * li + am[2 * ll + 1] * si;
-      const int off = tid + a.Dpad - d;
+      if constexpr (STAGED) {
+        const int off = tid + a.Dpad - d;
 #pragma unroll
-      for (int j = 0; j < NTX; ++j) cmac<REAL>(z[j], xs[j * W + off], h);
+        for (int j = 0; j < NTX; ++j) cmac<REAL>(z[j], xs[j * W + off], h);
+      } else {
+        const int n = m - d;
+        if (n >= 0 && n < a.T) {
+#pragma unroll
+          for (int j = 0; j < NTX; ++j)
+            if (j < a.ntx_chunk) cmac<REAL>(z[j], Conv<REAL>::from(xg[(size_t)j * a.T + n]), h);
+        }
+      }
     }
   }
   if (m < a.T + a.D) spatial_store<NTX, C, IO>(Ss, z, a, b, m);
@@ -584,7 +597,7 @@ template <int NTX>
 int launch_tdl_poly(int P, bool io128, const FadingArgs& a, const DelayTable& dt, size_t smem,
                     cudaStream_t st);
 template <int NTX>
-int launch_tdl_direct(bool f64, bool io128, const FadingArgs& a, const DelayTable& dt, int taps_per_chunk,
+int launch_tdl_direct(bool f64, bool io128, bool unstaged, const FadingArgs& a, const DelayTable& dt, int taps_per_chunk,
                       size_t smem, cudaStream_t st);
 template <int NTX> constexpr int poly_samples_per_thread() { return NTX <= 2 ? 4 : (NTX <= 4 ? 2 : 1); }
 

@@ -63,6 +63,25 @@ def test_planner_modes():
     assert st == 0 and info.launches == 3  # coefficient kernel + two antenna chunks (8 + 2)
 
 
+def test_planner_falls_back_before_it_refuses():
+    """AUTO / POLY requests whose preferred kernel overflows shared memory (thousands of receive antennas, very
+    long delay spreads) go to the antenna-chunking gather kernel, then to per-sample evaluation -- staged or, for delay
+    spreads no tile can hold, reading x from global memory -- before the problem is refused: the drop-in has no CPU path."""
+    wide = dict(num_tx=8, num_rx=4096, num_taps=64, max_delay=200, num_samples=4096,
+                tap_delay=np.linspace(0, 200, 64).astype(np.int32))
+    st, info = _plan(**wide)
+    assert st == 0 and info.mode == _lib.HB_SOS_POLY and info.variant == 0  # HB_VARIANT_GATHER
+    st, info = _plan(sos_mode="poly_window", **wide)  # an explicit request is not second-guessed
+    assert st == _lib.HB_ERR_UNSUPPORTED and b"shared memory" in _lib.load().hb_last_error()
+    long_spread = dict(num_samples=100000, max_delay=60000, num_taps=23, tap_delay=np.linspace(0, 60000, 23).astype(np.int32))
+    for precision in ("f32", "f64"):
+        st, info = _plan(precision=precision, **long_spread)
+        assert st == 0 and info.mode == _lib.HB_SOS_DIRECT and info.tile == 256, (precision, st)
+    st, info = _plan(precision="f64", num_samples=20000, max_delay=16000, num_taps=20,
+                     tap_delay=np.linspace(0, 16000, 20).astype(np.int32))
+    assert st == 0
+
+
 def test_planner_kernel_variants():
     """Which POLY kernel the planner picks (host logic, no GPU): the persistent TMA kernel for complex64 frames of whole
     16-sample rows and >= 2048 outputs with delays below 128 samples, the cp.async window kernel otherwise when its walk

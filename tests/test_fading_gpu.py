@@ -323,3 +323,22 @@ def test_siso_mode_is_refused_for_arrays():
     with pytest.raises(_lib.HermesB200Error):
         _run_case(B=1, L=4, N=8, ntx=2, nrx=1, T=600, fs=30.72e6, doppler=10.0, max_delay_s=1e-7, precision="f32",
                   sos_mode="poly_siso", io=np.complex64)
+
+
+@pytest.mark.parametrize("precision,io,tol", [("f64", np.complex128, F64_TOL), ("f32", np.complex64, F32_TOL)])
+def test_delay_spread_beyond_any_staged_tile(precision, io, tol):
+    """A 60 000-sample delay spread (2 ms at 30.72 MHz): no kernel can stage the halo, the planner's last resort evaluates
+    per sample in FP64 with x read from global memory.  The reference handles such links; so must the drop-in."""
+    err, info = _run_case(B=2, L=5, N=8, ntx=3, nrx=2, T=9000, fs=30.72e6, doppler=200.0, max_delay_s=60000 / 30.72e6,
+                          precision=precision, sos_mode="auto", io=io, seed=5)
+    assert info["mode"] == "direct"
+    assert err < tol, (err, info)
+
+
+def test_thousands_of_receive_antennas_take_the_gather_kernel():
+    """ADVICE r1: 8 x 3500 antennas overflow the window kernel's shared memory (its [Nrx x 8] spatial block alone is 224 KB);
+    AUTO re-plans with the gather kernel, which halves its antenna chunk until the block fits."""
+    err, info = _run_case(B=1, L=6, N=8, ntx=8, nrx=3500, T=300, fs=30.72e6, doppler=100.0, max_delay_s=1e-6,
+                          precision="f32", sos_mode="auto", io=np.complex64, seed=7, large=True)
+    assert info["mode"] == "poly" and info["variant"] == "gather", info
+    assert err < F32_TOL, (err, info)
