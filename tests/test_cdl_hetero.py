@@ -145,3 +145,51 @@ def test_mirror_batch_call_groups_by_geometry():
     for s, xi, y in zip(samples, xs, ys):
         r = co.propagate(oracle_params(s), xi)
         assert y.shape == r.shape and rel_l2(y, r) < 1e-10
+
+
+@pytest.mark.gpu
+def test_heterogeneous_batch_with_per_element_patterns():
+    """Rank-two ray matrices (cross-polarized linear elements with their own orientations) in a heterogeneous batch: the
+    links differ in their cluster delays, delay spread and line-of-sight state."""
+    from dataclasses import replace
+
+    from hermespy_b200.kernels import CdlBlock, cdl_propagate_host
+    from tests.helpers import cdl_block_from_oracle_params, cdl_params_from_golden
+    from tests.test_cdl_elements import GOLDEN as ELEMENT_GOLDEN
+
+    golden = np.load(ELEMENT_GOLDEN)
+    p = cdl_params_from_golden(golden, "xpol_linear_custom")
+    rng = np.random.default_rng(9)
+    blocks, xs, refs = [], [], []
+    T = 300
+    for b in range(4):
+        q = replace(p, cluster_delays=p.cluster_delays * (1.0 + 0.45 * b), cluster_delay_spread=p.cluster_delay_spread * (1 + b),
+                    line_of_sight=bool(b % 2), rice_factor_db=3.0 + b,
+                    rx=replace(p.rx, velocity=p.rx.velocity * (1 + b)))
+        blocks.append(cdl_block_from_oracle_params(q))
+        x = (rng.standard_normal((blocks[-1].num_tx, T)) + 1j * rng.standard_normal((blocks[-1].num_tx, T))) / np.sqrt(2)
+        xs.append(x)
+        refs.append(co.propagate(q, x))
+    assert len({b.delay_key() for b in blocks}) == 4
+    blk = CdlBlock.stack(blocks)
+    assert blk.link_term_delay is not None and blk.element_mode == _lib.HB_ELEMENTS_PER_ELEMENT
+    for precision, tol in (("f64", 1e-10), ("f32", 1e-5)):
+        y = cdl_propagate_host(np.stack(xs), blk, precision=precision)
+        for k, (b, r) in enumerate(zip(blocks, refs)):
+            assert rel_l2(y[k][:, : T + b.max_delay], r) < tol, (precision, k)
+
+
+@pytest.mark.gpu
+def test_heterogeneous_batch_on_a_large_array():
+    """96 transmit antennas: the steering phases of a pass no longer fit the all-windows moment kernel's shared memory, the
+    per-window moment kernel (global-memory steering phases) serves the heterogeneous batch."""
+    from hermespy_b200.kernels import CdlBlock, cdl_propagate_host
+
+    samples, xs = _mixed_samples((12, 8, 1), (2, 1, 1), (4.0, 1.0, 0.0), 260, mix=MIX[:4])
+    blocks = [s.kernel_block() for s in samples]
+    blk = CdlBlock.stack(blocks)
+    y, info = cdl_propagate_host(np.stack(xs), blk, precision="f32", return_info=True)
+    assert info["mode"] == "poly"
+    for k, (s, xi, b) in enumerate(zip(samples, xs, blocks)):
+        r = co.propagate(oracle_params(s), xi)
+        assert rel_l2(y[k][:, : 260 + b.max_delay], r) < 1e-5, k
