@@ -342,3 +342,39 @@ def test_thousands_of_receive_antennas_take_the_gather_kernel():
                           precision="f32", sos_mode="auto", io=np.complex64, seed=7, large=True)
     assert info["mode"] == "poly" and info["variant"] == "gather", info
     assert err < F32_TOL, (err, info)
+
+
+def test_host_entry_runs_on_the_requested_device_from_a_worker_thread():
+    """CUDA's current device is per thread and defaults to 0, so a rank that pinned its GPU in the main thread used
+    to run the drop-in's calls -- made from an actor's worker thread -- on GPU 0.  The host entries take the device explicitly:
+    a call from a fresh thread with ``device=1`` allocates and launches on GPU 1 and leaves GPU 0 alone."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from hermespy_b200 import _lib
+    from hermespy_b200.kernels import fading_propagate_host
+
+    rng = np.random.default_rng(3)
+    plist = [random_fading_params(rng, 6, 8, 2, 2, 30.72e6, 100.0, 1e-6)]
+    blk = stack_param_blocks(plist)
+    x = random_signal(rng, 2, 40000)[None]  # 1.3 MB in, 1.3 MB out: the pipeline's slot buffers are visible in mem_get_info
+    ref = fo.propagate(plist[0], x[0])
+
+    def call(device):
+        y = fading_propagate_host(x, precision="f64", device=device, **blk)
+        return y, torch.cuda.current_device()
+
+    with ThreadPoolExecutor(1) as pool:
+        y0, _ = pool.submit(call, 0).result()
+    torch.cuda.synchronize(0)
+    free0 = torch.cuda.mem_get_info(0)[0]
+    free1 = torch.cuda.mem_get_info(1)[0]
+    with ThreadPoolExecutor(1) as pool:  # a FRESH thread: its current device starts at 0
+        y1, dev_after = pool.submit(call, 1).result()
+    assert dev_after == 1
+    assert np.array_equal(y0, y1) and rel_l2(y1[0], ref) < F64_TOL
+    assert torch.cuda.mem_get_info(1)[0] < free1            # context / slot buffers appeared on GPU 1 ...
+    assert torch.cuda.mem_get_info(0)[0] >= free0 - (1 << 20)  # ... and nothing was allocated on GPU 0 (its slots were released)
+    _lib.set_device(0)
