@@ -334,6 +334,22 @@ class _ShmRef(object):
         self.offset, self.shape, self.dtype = int(offset), tuple(shape), str(dtype)
 
 
+def _window_bytes(helpers: int) -> int:
+    """Window size per helper: ``RPC_SHM_BYTES``, cut down to what /dev/shm can actually back (half of its free space over
+    all helpers) -- pages of a shared-memory segment are allocated on first touch, and touching more than the tmpfs holds is
+    a SIGBUS, not an exception (container defaults are as small as 64 MB).  Below 1 MB per helper: no windows."""
+    want = int(RPC_SHM_BYTES)
+    if want <= 0 or helpers <= 0:
+        return 0
+    try:
+        st = os.statvfs("/dev/shm")
+        free = int(st.f_bavail) * int(st.f_frsize)
+    except OSError:
+        return 0
+    size = min(want, free // (2 * helpers))
+    return size if size >= (1 << 20) else 0
+
+
 class _Window(object):
     """One helper's shared-memory window, created by the GPU owner BEFORE the fork (the helper inherits the mapping); the
     owner unlinks it, whatever happens to the helper.  Deliberately NOT page-locked: ``cudaHostRegister`` of 16 x 64 MB costs
@@ -504,14 +520,15 @@ class LaneSet(object):
             del warm
             self.seconds["setup_warm_drop"] = time.perf_counter() - t_setup
             ctx = mp.get_context("fork")  # lanes travel by fork: no pickling of scenarios, exactly the parent's objects
+            window_bytes = _window_bytes(workers)
             self.owner = {}
             for w in range(workers):
                 mine = list(range(w, self.num_lanes, workers))
                 parent, child = ctx.Pipe()
                 window = None
-                if RPC_SHM_BYTES > 0:
+                if window_bytes > 0:
                     try:
-                        window = _Window(RPC_SHM_BYTES)
+                        window = _Window(window_bytes)
                     except Exception:
                         window = None  # no /dev/shm: results travel through the pipe
                 self.windows.append(window)

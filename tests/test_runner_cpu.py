@@ -364,3 +364,28 @@ def test_a_called_off_stream_closes_at_once_and_leaves_no_windows_behind():
     assert not any(p.is_alive() for p in procs)
     if os.path.isdir("/dev/shm"):
         assert set(os.listdir("/dev/shm")) <= shm_before
+
+
+def test_window_size_follows_what_dev_shm_can_back(monkeypatch):
+    """Touching more shared memory than the tmpfs holds is a SIGBUS: the windows shrink to half of the free space over all
+    helpers, and disappear below 1 MB each (container defaults are as small as 64 MB)."""
+    import os
+    from types import SimpleNamespace
+
+    from hermespy_b200 import runner
+
+    monkeypatch.setattr(runner, "RPC_SHM_BYTES", 64 << 20)
+    monkeypatch.setattr(os, "statvfs", lambda path: SimpleNamespace(f_bavail=1 << 20, f_frsize=4096))  # 4 GB free
+    assert runner._window_bytes(16) == 64 << 20
+    monkeypatch.setattr(os, "statvfs", lambda path: SimpleNamespace(f_bavail=16384, f_frsize=4096))    # 64 MB free
+    assert runner._window_bytes(16) == (64 << 20) // 32
+    assert runner._window_bytes(64) == 0  # 512 KB each: not worth a window
+    monkeypatch.setattr(runner, "RPC_SHM_BYTES", 0)
+    assert runner._window_bytes(16) == 0
+
+    def gone(path):
+        raise OSError("no /dev/shm")
+
+    monkeypatch.setattr(runner, "RPC_SHM_BYTES", 64 << 20)
+    monkeypatch.setattr(os, "statvfs", gone)
+    assert runner._window_bytes(16) == 0
