@@ -15,6 +15,11 @@ artifacts per cell -- is done here by the ranks of a ``torchrun`` job:
 
 The scenario is built by a user function from the reference's public API; modems, noise, synchronization, equalization
 and the evaluator are reference code.
+
+This is the REPRODUCIBLE form (a result independent of the number of ranks, bit for bit): one drop at a time per rank, so the
+rank's Python modem code -- not the channel -- sets its pace (~140 drops/s on C1).  Throughput is the business of the batched
+drop runner (``hermespy_b200/runner.py``, second form): B drops in flight per actor, the modem stages spread over forked
+helper processes, one channel launch per round for all their links, driven by the unmodified ``Simulation.run()``.
 """
 from __future__ import annotations
 
