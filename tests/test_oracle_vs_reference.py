@@ -131,6 +131,7 @@ def test_cdl_oracle_matches_live_reference_stochastic_scenarios(ref):
         lambda: RC.IndoorFactory(2000.0, 1500.0, RC.FactoryType.DH, expected_state=RC.LOSState.NLOS, seed=7),
     ]
     counts = set()
+    blocks = []
     for build in builders:
         tx, rx = dev((2, 2, 1), (0.0, 0.0, 25.0), (0, 0, 0)), dev((2, 1, 1), (120.0, 40.0, 1.5), (3.0, -1.0, 0.0))
         s = build().realize().sample(tx, rx)
@@ -142,7 +143,24 @@ def test_cdl_oracle_matches_live_reference_stochastic_scenarios(ref):
         assert blk.batch == 1 and blk.num_tx == 4 and blk.num_rx == 2 and blk.max_delay == y.shape[1] - 120
         assert blk.term_delay.size == blk.amplitude.shape[1] == blk.angles.shape[1] and blk.term_delay.max() <= blk.max_delay
         counts.add(int(s.num_clusters))
+        blocks.append(blk)
     assert len(counts) >= 4  # the scenarios really produce different cluster counts
+    # ... and travel as ONE heterogeneous batch: rays padded with zero amplitude, per-link delay tables, largest delay spread
+    from hermespy_b200.kernels import CdlBlock, cdl_plan
+
+    stacked = CdlBlock.stack(blocks)
+    rn = max(b.term_delay.size for b in blocks)
+    assert stacked.batch == len(blocks) and stacked.link_term_delay.shape == (len(blocks), rn)
+    assert stacked.max_delay == max(b.max_delay for b in blocks) and stacked.line_of_sight == any(b.line_of_sight for b in blocks)
+    for k, b in enumerate(blocks):
+        n = b.term_delay.size
+        assert np.array_equal(stacked.link_term_delay[k, :n], b.term_delay) and np.array_equal(stacked.amplitude[k, :n], b.amplitude[0])
+        assert not stacked.amplitude[k, n:].any() and np.isfinite(stacked.jones[k]).all()
+        assert stacked.link_los_amplitude[k] == (b.los_amplitude if b.line_of_sight else 0.0)
+        assert stacked.link_los_delay[k] == b.los_delay and stacked.link_max_delay[k] == b.max_delay
+    plan = cdl_plan(stacked, 2304, precision="f32")  # the planner sizes the launch by the largest per-link group count
+    groups = [np.unique(np.append(b.term_delay, b.los_delay) if b.line_of_sight else b.term_delay).size for b in blocks]
+    assert plan["num_groups"] == max(groups)
 
 
 def test_dropin_extraction_equals_mirror_blocks(ref):
