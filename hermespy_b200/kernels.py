@@ -631,6 +631,8 @@ class CdlBlock:
         ray count, line-of-sight state, delay spread: stochastic scenario realizations) give a heterogeneous batch: rays
         padded with zero-amplitude copies of each link's first ray, per-link delay tables, the largest ``max_delay``."""
         b0 = blocks[0]
+        if any(b.geometry_key() != b0.geometry_key() for b in blocks[1:]):
+            raise ValueError("blocks of one batch must share array topologies, element models, carrier frequency and sampling rate")
         cat = lambda f: np.concatenate([getattr(b, f) for b in blocks])
         common = dict(tx_pose=cat("tx_pose"), rx_pose=cat("rx_pose"), rel_velocity=cat("rel_velocity"),
                       tx_topology=b0.tx_topology, rx_topology=b0.rx_topology, carrier_frequency=b0.carrier_frequency,

@@ -51,6 +51,10 @@ def test_stack_pads_to_one_heterogeneous_block_and_the_planner_takes_it():
     # a heterogeneous block stacks again (nested batching)
     again = CdlBlock.stack([blk, blocks[1]])
     assert again.batch == blk.batch + 1 and again.link_term_delay.shape[1] == rn
+    # blocks of another array geometry do not belong in the batch
+    other, _ = _mixed_samples((2, 1, 1), (2, 1, 1), (3.0, 0.0, 0.0), 64, mix=MIX[:1])
+    with pytest.raises(ValueError, match="share array topologies"):
+        CdlBlock.stack([blocks[0], other[0].kernel_block()])
     # the planner: groups = the largest per-link count, no device needed
     plan = cdl_plan(blk, 2048)
     per_link = [np.unique(np.append(b.term_delay, b.los_delay) if b.line_of_sight else b.term_delay).size for b in blocks]
