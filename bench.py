@@ -671,12 +671,36 @@ def _traffic(cfg, kname, B):
     return None
 
 
+#: set when a leg had to be abandoned on its time limit: threads / helper processes of the hung run may still be alive, so the
+#: process leaves through os._exit once the JSON line is out (an interpreter exit would join them)
+_FORCE_EXIT = False
+SIMULATION_TIME_LIMIT_S = 180  # per script and arm; the three scripts take 2 .. 12 s each
+
+
+def _time_limited(seconds, fn, *a, **k):
+    """``fn(*a, **k)`` in the main thread under a SIGALRM limit: ``TimeoutError`` instead of a bench run that never prints
+    its line.  (The campaign engine polls from the main thread, so the exception surfaces there.)"""
+    import signal
+
+    def on_alarm(signum, frame):
+        raise TimeoutError(f"exceeded its {seconds} s limit")
+
+    old = signal.signal(signal.SIGALRM, on_alarm)
+    signal.alarm(int(seconds))
+    try:
+        return fn(*a, **k)
+    finally:
+        signal.alarm(0)
+        signal.signal(signal.SIGALRM, old)
+
+
 def measure_simulation(args, world, rank, dev):
     """End to end through the UNMODIFIED ``Simulation.run()`` API (north_star): drops/s of the reference's own scripts with
     the channel on the GPU and the batched drop runner (hermespy_b200/runner.py).  Three scripts: BASELINE config C1 (SISO RRC
     over TDL-A, 11 SNR points), the C2 frame through a modem the reference can demodulate (2x1 Alamouti OFDM, 1024
     subcarriers, ideal CSI, TDL-B) and the same link over the stochastic 3GPP UMa scenario (heterogeneous CDL batches).  N = 1: helper processes on the host cores, and the stock reference on all host cores
     beside it.  N > 1: every rank runs its own campaign share with in-process lanes (no fork next to NCCL)."""
+    global _FORCE_EXIT
     import torch
     import torch.distributed as dist
 
@@ -698,15 +722,28 @@ def measure_simulation(args, world, rank, dev):
     for name, samples, lanes in (("c1", 400 if world == 1 else 40, 64 if world == 1 else 32),
                                  ("ofdm", 64 if world == 1 else 8, 64 if world == 1 else 16),
                                  ("uma", 64 if world == 1 else 8, 64 if world == 1 else 16)):
-        rec = sc.run_gpu(name, samples, "f64", lanes, workers)
-        t = torch.tensor([rec["seconds"]], dtype=torch.float64, device=dev)
+        try:
+            rec, err = _time_limited(SIMULATION_TIME_LIMIT_S, sc.run_gpu, name, samples, "f64", lanes, workers), None
+        except Exception as e:  # every rank still takes part in the reduction below: one control flow for all of them
+            rec, err = None, repr(e)
+        t = torch.tensor([rec["seconds"] if rec else float("inf")], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if not np.isfinite(float(t.item())):
+            out[name] = {"error": err or "failed on another rank"}
+            _FORCE_EXIT = True
+            break
         entry = {"drops_per_s": world * rec["drops"] / float(t.item()), "drops_per_rank": rec["drops"], "lanes": lanes,
                  "links_per_launch_round": rec["links_per_round"], "kernel_launches_per_rank": rec["kernel_launches"],
                  "ber": rec["ber"], "owner_seconds": rec.get("owner_seconds")}
         if world == 1 and not args.no_cpu_baseline:
-            ref = sc.run_reference(name, max(cores, samples), cores)
+            try:
+                ref = _time_limited(SIMULATION_TIME_LIMIT_S, sc.run_reference, name, max(cores, samples), cores)
+            except Exception as e:
+                entry["reference_error"] = repr(e)
+                out[name] = entry
+                _FORCE_EXIT = True
+                break
             entry["reference_all_host_cores_drops_per_s"] = ref["drops_per_s"]
             entry["reference_ber"] = ref["ber"]
             entry["reference_propagate_share_of_run"] = ref["propagate_share_of_run"]
@@ -794,7 +831,12 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    rc = run_ours(args)
+    if _FORCE_EXIT:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(rc)
+    return rc
 
 
 if __name__ == "__main__":

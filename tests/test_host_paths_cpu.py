@@ -93,3 +93,20 @@ def test_cdl_block_validates_element_tables():
     assert CdlBlock(**base, tx_elements=dip).element_mode == _lib.HB_ELEMENTS_PER_ELEMENT
     with pytest.raises(ValueError):
         CdlBlock(**base, tx_elements=ideal_elements(4), rx_elements=ideal_elements(2))
+
+
+def test_bench_time_limit_turns_a_hang_into_an_error():
+    """bench.py runs the Simulation.run() scripts under a SIGALRM limit: a leg that hangs becomes an error entry of the JSON
+    line instead of a bench run that never prints it."""
+    import signal
+    import time
+
+    import bench
+
+    assert bench._time_limited(5, lambda a, b=1: a + b, 2, b=3) == 5
+    before = signal.getsignal(signal.SIGALRM)
+    t0 = time.perf_counter()
+    with pytest.raises(TimeoutError, match="1 s limit"):
+        bench._time_limited(1, time.sleep, 30)
+    assert time.perf_counter() - t0 < 5
+    assert signal.getsignal(signal.SIGALRM) == before and signal.alarm(0) == 0  # handler restored, no alarm left pending
