@@ -719,7 +719,7 @@ def measure_simulation(args, world, rank, dev):
     workers = max(1, cores - 1) if world == 1 else 0
     out = {"api": "hermespy.simulation.Simulation.run() (unmodified script), dropin.enable(precision='f64', batch_drops, workers)",
            "host_cores": cores, "helper_processes_per_rank": workers}
-    for name, samples, lanes in (("c1", 400 if world == 1 else 40, 64 if world == 1 else 32),
+    for name, samples, lanes in (("c1", 1000 if world == 1 else 40, 64 if world == 1 else 32),  # N = 1: BASELINE's 11 x 1000 drops
                                  ("ofdm", 64 if world == 1 else 8, 64 if world == 1 else 16),
                                  ("uma", 64 if world == 1 else 8, 64 if world == 1 else 16)):
         try:
